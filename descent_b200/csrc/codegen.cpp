@@ -1,0 +1,842 @@
+// CUDA C emission for every cluster kind.  Semantics per kernel follow SURVEY.md Appendix A and the
+// reference kernels cited at each generator; the code shape is B200-first: views are index
+// arithmetic on compile-time constants, identity operands move as 128-bit vectors, reductions are
+// cooperative and deterministic, GEMM operands (including the im2col view of conv2d) are gathered
+// straight into shared-memory tiles, scatter_add is a sort + segmented sum instead of float atomics.
+#include "codegen.hpp"
+
+#include <cmath>
+#include <cstdio>
+
+namespace descent {
+
+namespace {
+
+std::string replace_all(std::string s, const std::string& from, const std::string& to) {
+    size_t pos = 0;
+    while ((pos = s.find(from, pos)) != std::string::npos) {
+        s.replace(pos, from.size(), to);
+        pos += to.size();
+    }
+    return s;
+}
+std::string subst(std::string s, const std::vector<std::pair<std::string, std::string>>& kv) {
+    for (const auto& p : kv) s = replace_all(s, "{{" + p.first + "}}", p.second);
+    DSC_CHECK(s.find("{{") == std::string::npos, "unsubstituted placeholder in kernel template: " << s.substr(s.find("{{"), 24));
+    return s;
+}
+std::string num(int64_t v) { return std::to_string(v); }
+std::string unum(int64_t v) { return std::to_string(v) + "u"; }
+
+int64_t pow2_ceil(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return p; }
+int64_t pow2_floor(int64_t v) { int64_t p = 1; while (p * 2 <= v) p <<= 1; return p; }
+
+// Emits statements that turn the consumer element index `e` (an unsigned expression) into the
+// producer buffer index, view by view from the consumer side (offset + sum(step*coord),
+// clamped only where the view can leave the axis).  Returns the name of the resulting expression.
+std::string emit_chain(std::ostringstream& os, const ViewChain& chain, const std::string& e, int& uniq, const char* indent = "    ") {
+    std::string cur = e;
+    for (int vi = (int)chain.views.size() - 1; vi >= 0; --vi) {
+        const View& v = chain.views[vi];
+        const int id = uniq++;
+        auto ostr = v.output_shape.strides();
+        auto istr = v.input_shape.strides();
+        int64_t lead = 1;  // product of output extents before axis i
+        for (int i = 0; i < v.output_shape.len(); ++i) {
+            const auto& m = v.output_mapping[i];
+            if (m.is_source && v.output_shape[i] > 1) {
+                os << indent << "const int c" << id << "_" << i << " = (int)(" << cur;
+                if (ostr[i] != 1) os << " / " << unum(ostr[i]);
+                if (lead != 1) os << " % " << unum(v.output_shape[i]);
+                os << ");\n";
+            }
+            lead *= v.output_shape[i];
+        }
+        std::ostringstream sum;
+        int64_t constant = 0;
+        bool any = false;
+        for (int a = 0; a < v.input_shape.len(); ++a) {
+            std::ostringstream t;
+            bool has_terms = false;
+            for (int i = 0; i < v.output_shape.len(); ++i) {
+                const auto& m = v.output_mapping[i];
+                if (m.is_source && m.axis == a && v.output_shape[i] > 1) {
+                    t << (has_terms ? " + " : "");
+                    if (m.step == 1) t << "c" << id << "_" << i;
+                    else t << "(" << m.step << ")*c" << id << "_" << i;
+                    has_terms = true;
+                }
+            }
+            const int64_t off = v.input_offsets[a], len = v.input_shape[a];
+            if (!has_terms) {
+                constant += std::min<int64_t>(std::max<int64_t>(off, 0), len - 1) * istr[a];
+                continue;
+            }
+            std::string expr = t.str();
+            if (off != 0) expr = expr + " + (" + num(off) + ")";
+            if (v.input_needs_clamp(a)) expr = "min(max(" + expr + ", 0), " + num(len - 1) + ")";
+            sum << (any ? " + " : "") << "(" << expr << ")";
+            if (istr[a] != 1) sum << "*" << istr[a];
+            any = true;
+        }
+        os << indent << "const unsigned x" << id << " = (unsigned)(";
+        if (any) os << sum.str();
+        if (constant != 0 || !any) os << (any ? " + " : "") << constant;
+        os << ");\n";
+        cur = "x" + num(id);
+    }
+    return cur;
+}
+
+double chain_bytes(const Graph& g, const ClusterInput& in) {
+    (void)g;
+    return 4.0 * (double)in.chain.addressed_count();
+}
+
+// ---- per-element (reference: PerElementKernel, kernel.rs:195-383) -------------------------------
+
+ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
+    const int64_t n = c.element_count;
+    const int vec = (n % 4 == 0) ? 4 : 1;
+    std::ostringstream os;
+    const std::string name = "k" + num(ci);
+    os << "// " << c.label << "\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(256) " << name << "(";
+    for (size_t i = 0; i < c.inputs.size(); ++i) os << "const float* in" << i << ", ";
+    for (size_t i = 0; i < c.outputs.size(); ++i) os << "float* out" << i << ", ";
+    os << "const unsigned* dsc_step) {\n";
+    os << "    const unsigned dsc_seed = dsc_step[0]; (void)dsc_seed;\n";
+    os << "    const unsigned base = (blockIdx.x * 256u + threadIdx.x) * " << vec << "u;\n";
+    os << "    if (base >= " << unum(n) << ") return;\n";
+    std::vector<bool> vector_load(c.inputs.size(), false);
+    std::vector<bool> is_loaded(c.inputs.size(), false);
+    for (const auto& op : c.ops)
+        if (op.kind == PerElementOp::Load) is_loaded[op.input_index] = true;
+    if (vec == 4) {
+        for (size_t i = 0; i < c.inputs.size(); ++i) {
+            if (is_loaded[i] && c.inputs[i].chain.is_identity()) {
+                vector_load[i] = true;
+                os << "    const float4 q" << i << " = *reinterpret_cast<const float4*>(in" << i << " + base);\n";
+                os << "    const float vin" << i << "[4] = {q" << i << ".x, q" << i << ".y, q" << i << ".z, q" << i << ".w};\n";
+            }
+        }
+        for (size_t i = 0; i < c.outputs.size(); ++i) os << "    float vout" << i << "[4];\n";
+        os << "    #pragma unroll\n    for (int v = 0; v < 4; ++v) {\n";
+        os << "    const unsigned e = base + v;\n";
+    } else {
+        os << "    const unsigned e = base;\n    {\n";
+    }
+    int uniq = 0;
+    for (size_t oi = 0; oi < c.ops.size(); ++oi) {
+        const PerElementOp& op = c.ops[oi];
+        const std::string t = "t" + num(oi);
+        auto A = [&](int k) { return "t" + num(op.args[k]); };
+        switch (op.kind) {
+            case PerElementOp::Load: {
+                const auto& in = c.inputs[op.input_index];
+                if (vector_load[op.input_index]) {
+                    os << "    const float " << t << " = vin" << op.input_index << "[v];\n";
+                } else {
+                    std::string idx = emit_chain(os, in.chain, "e", uniq);
+                    os << "    const float " << t << " = in" << op.input_index << "[" << idx << "];\n";
+                }
+                break;
+            }
+            case PerElementOp::Literal:
+                os << "    const float " << t << " = __uint_as_float(" << op.op.literal_bits << "u);";
+                if (!op.op.literal_is_u32) os << "  // " << op.op.literal_f32_value();
+                os << "\n";
+                break;
+            case PerElementOp::BuiltIn: {
+                std::string idx = emit_chain(os, op.chain, "e", uniq);
+                if (op.op.built_in == BuiltInOp::Coord) {
+                    os << "    const float " << t << " = (float)(int)(" << idx << ");\n";
+                } else {
+                    // flat element index of the *global* (unsharded) tensor: SURVEY.md §8e condition 3
+                    const int64_t offset = (int64_t)opt.dp_rank * op.arg_shape.element_count();
+                    os << "    const float " << t << " = dsc_rand(" << op.op.rand_uid << "u, " << idx << " + " << unum(offset) << ", dsc_seed);\n";
+                }
+                break;
+            }
+            case PerElementOp::Unary: {
+                os << "    const float " << t << " = ";
+                switch (op.op.unary) {
+                    case UnaryOp::Mov: os << A(0); break;
+                    case UnaryOp::Neg: os << "-" << A(0); break;
+                    case UnaryOp::Sqrt: os << "sqrtf(" << A(0) << ")"; break;
+                    case UnaryOp::Exp: os << "expf(" << A(0) << ")"; break;
+                    case UnaryOp::Log: os << "logf(" << A(0) << ")"; break;
+                    case UnaryOp::Sin: os << "sinf(" << A(0) << ")"; break;
+                    case UnaryOp::Cos: os << "cosf(" << A(0) << ")"; break;
+                    case UnaryOp::UintToFloat: os << "__uint2float_rn(__float_as_uint(" << A(0) << "))"; break;
+                    case UnaryOp::FloatToUint: os << "__uint_as_float(__float2uint_rz(" << A(0) << "))"; break;
+                }
+                os << ";\n";
+                break;
+            }
+            case PerElementOp::Binary: {
+                os << "    const float " << t << " = ";
+                auto U = [&](const char* o) { os << "__uint_as_float(__float_as_uint(" << A(0) << ") " << o << " __float_as_uint(" << A(1) << "))"; };
+                switch (op.op.binary) {
+                    case BinaryOp::Add: os << A(0) << " + " << A(1); break;
+                    case BinaryOp::Sub: os << A(0) << " - " << A(1); break;
+                    case BinaryOp::Mul: os << A(0) << " * " << A(1); break;
+                    case BinaryOp::Div: os << A(0) << " / " << A(1); break;
+                    case BinaryOp::Pow: os << "powf(" << A(0) << ", " << A(1) << ")"; break;
+                    case BinaryOp::UAdd: U("+"); break;
+                    case BinaryOp::UMul: U("*"); break;
+                    case BinaryOp::URem: U("%"); break;
+                    case BinaryOp::UBitXor: U("^"); break;
+                }
+                os << ";\n";
+                break;
+            }
+            case PerElementOp::Select:
+                os << "    const float " << t << " = (" << A(0) << (op.op.compare == CompareMode::Eq ? " == " : " > ") << A(1) << ") ? " << A(2)
+                   << " : " << A(3) << ";\n";
+                break;
+            case PerElementOp::Gather: {
+                // out[.., i, ..] = values[.., F2I(index[i]), ..]  (kernel.rs:336-351)
+                const int axis = op.op.axis;
+                int64_t inner = 1;
+                for (int d = axis + 1; d < op.shape.len(); ++d) inner *= op.shape[d];
+                const int64_t len = op.shape[axis], rows = op.arg_shape[axis];
+                const int id = uniq++;
+                os << "    const unsigned g" << id << " = ((e / " << unum(len * inner) << ") * " << unum(rows) << " + (unsigned)__float_as_int(" << A(1)
+                   << ")) * " << unum(inner) << " + (e % " << unum(inner) << ");\n";
+                std::string idx = emit_chain(os, c.inputs[op.input_index].chain, "g" + num(id), uniq);
+                os << "    const float " << t << " = in" << op.input_index << "[" << idx << "];\n";
+                break;
+            }
+        }
+    }
+    for (size_t i = 0; i < c.outputs.size(); ++i) {
+        if (vec == 4) os << "    vout" << i << "[v] = t" << c.output_ops[i] << ";\n";
+        else os << "    out" << i << "[e] = t" << c.output_ops[i] << ";\n";
+    }
+    os << "    }\n";
+    if (vec == 4)
+        for (size_t i = 0; i < c.outputs.size(); ++i)
+            os << "    *reinterpret_cast<float4*>(out" << i << " + base) = make_float4(vout" << i << "[0], vout" << i << "[1], vout" << i
+               << "[2], vout" << i << "[3]);\n";
+    os << "}\n\n";
+
+    ClusterCode code;
+    code.source = os.str();
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)div_round_up(div_round_up(n, vec), 256);
+    l.label = c.label;
+    l.cluster = ci;
+    for (const auto& in : c.inputs) {
+        l.args.push_back({KernelArg::NodeBuffer, in.node_id, 0});
+        l.algorithmic_bytes += chain_bytes(g, in);
+    }
+    for (int out : c.outputs) {
+        l.args.push_back({KernelArg::NodeBuffer, out, 0});
+        l.algorithmic_bytes += 4.0 * (double)n;
+    }
+    code.launches.push_back(l);
+    return code;
+}
+
+// ---- reduce (reference: ReduceKernel, kernel.rs:559-642) ----------------------------------------
+// The reference walks K sequentially in one thread per output.  Here G threads share an output when K
+// is long (G is a power of two chosen from the shape), each walks a strided slice in ascending k, and
+// the G partials meet in a fixed shared-memory tree: deterministic, and coalesced in whichever of
+// {k, output} direction is contiguous in memory.
+
+const char* kReduceTemplate = R"(
+// {{LABEL}}
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, float* out0, const unsigned* dsc_step) {
+    constexpr unsigned O = {{O}}u, K = {{K}}u, INNER = {{INNER}}u, G = {{G}}u, TO = 256u / G;
+    const unsigned tid = threadIdx.x;
+    const unsigned g = {{G_OF_TID}};
+    const unsigned ol = {{O_OF_TID}};
+    const unsigned o = blockIdx.x * TO + ol;
+    float acc = {{INIT}};
+    if (o < O) {
+        const unsigned oo = o / INNER, oi = o % INNER;
+        {{UNROLL}}
+        for (unsigned k = g; k < K; k += G) {
+            const unsigned e = (oo * K + k) * INNER + oi;
+{{CHAIN}}
+            const float v = in0[{{IDX}}];
+            acc = {{OP}};
+        }
+    }
+    if (G > 1) {
+        __shared__ float red[256];
+        red[tid] = acc;
+        __syncthreads();
+        #pragma unroll
+        for (unsigned s = G / 2; s > 0; s >>= 1) {
+            if (g < s) {
+                const float a = red[tid], v = red[tid + s * {{GSTRIDE}}];
+                red[tid] = {{OP_AV}};
+            }
+            __syncthreads();
+        }
+        if (g == 0 && o < O) out0[o] = red[tid];
+    } else if (o < O) {
+        out0[o] = acc;
+    }
+}
+)";
+
+ClusterCode gen_reduce(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
+    const OpNode& node = g.ops().nodes[c.node_id];
+    const ClusterInput& in = c.inputs[0];
+    const int axis = node.op.axis;
+    const int64_t K = in.arg_shape[axis];
+    int64_t inner = 1;
+    for (int d = axis + 1; d < in.arg_shape.len(); ++d) inner *= in.arg_shape[d];
+    const int64_t O = node.shape.element_count();
+    int64_t G = 1;
+    if (K > 16) {
+        const int64_t want = pow2_ceil(div_round_up((int64_t)opt.sm_count * 1024, O));
+        G = std::max<int64_t>(1, std::min<int64_t>({want, (int64_t)256, pow2_floor(K / 4)}));
+    }
+    // is the reduced axis the contiguous one?  probe the chain around the middle of the tensor
+    bool kfast = inner == 1;
+    {
+        const int64_t total = in.arg_shape.element_count();
+        const int64_t mid = (total / 2 / (K * inner)) * K * inner;  // k = 0, oi = 0 of a middle row
+        if (K > 1 && mid + inner < total && inner > 1) {
+            int64_t dk = std::llabs(eval_chain(in.chain, mid + inner) - eval_chain(in.chain, mid));
+            int64_t d_o = std::llabs(eval_chain(in.chain, mid + 1) - eval_chain(in.chain, mid));
+            kfast = dk != 0 && (d_o == 0 || dk < d_o);
+        }
+    }
+    std::ostringstream chain;
+    int uniq = 0;
+    std::string idx = emit_chain(chain, in.chain, "e", uniq, "            ");
+    const bool is_max = node.op.reduce == ReduceOp::Max;
+    const std::string name = "k" + num(ci);
+    ClusterCode code;
+    code.source = subst(kReduceTemplate, {{"LABEL", c.label}, {"NAME", name}, {"O", num(O)}, {"K", num(K)}, {"INNER", num(inner)}, {"G", num(G)},
+                                          {"G_OF_TID", kfast ? "tid % G" : "tid / TO"}, {"O_OF_TID", kfast ? "tid / G" : "tid % TO"},
+                                          {"GSTRIDE", kfast ? "1u" : "TO"}, {"INIT", is_max ? "__uint_as_float(0xff800000u)" : "0.f"},
+                                          {"UNROLL", K <= 16 ? "#pragma unroll" : "#pragma unroll 4"}, {"CHAIN", chain.str()}, {"IDX", idx},
+                                          {"OP", is_max ? "fmaxf(acc, v)" : "acc + v"}, {"OP_AV", is_max ? "fmaxf(a, v)" : "a + v"}});
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)div_round_up(O, 256 / G);
+    l.label = c.label;
+    l.cluster = ci;
+    l.args = {{KernelArg::NodeBuffer, in.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+    l.algorithmic_bytes = chain_bytes(g, in) + 4.0 * (double)O;
+    code.launches.push_back(l);
+    return code;
+}
+
+// ---- matmul (reference: MatMulKernel + kernel_matmul.glsl) ---------------------------------------
+// Strict-FP32 SIMT GEMM, JIT-specialised per shape.  Operands are fetched through their chains
+// directly into k-major shared tiles (zero fill outside M/N/K, kernel.rs:461-487), so the im2col
+// "matrix" of conv2d and every transpose exist only as index arithmetic.  Register tile TMxTN per
+// thread; explicit fmaf (products are accumulated in ascending k inside a split, splits summed in
+// ascending order: SURVEY.md A.6).
+
+const char* kMatMulTemplate = R"(
+// {{LABEL}}
+extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, const float* B, float* C, const unsigned* dsc_step) {
+    constexpr int BM = {{BM}}, BN = {{BN}}, BK = {{BK}}, TM = {{TM}}, TN = {{TN}}, NT = {{NT}};
+    constexpr int M = {{M}}, N = {{N}}, K = {{K}}, KC = {{KC}}, BC = {{BC}};
+    constexpr int TILES_N = (N + BN - 1) / BN;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tile_m = blockIdx.x / TILES_N, tile_n = blockIdx.x % TILES_N;
+    const int batch = blockIdx.y, split = blockIdx.z;
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
+    const int k_begin = split * KC;
+    const int k_end = min(K, k_begin + KC);
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    float acc[TM][TN];
+    #pragma unroll
+    for (int i = 0; i < TM; ++i)
+        #pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        #pragma unroll
+        for (int i = tid; i < BM * BK; i += NT) {
+            {{A_DECODE}}
+            const int gm = m0 + lm, gk = k0 + lk;
+            float v = 0.f;
+            if (gm < M && gk < k_end) {
+                const unsigned e = ((unsigned)batch * M + gm) * K + gk;
+{{A_CHAIN}}
+                v = A[{{A_IDX}}];
+            }
+            As[lk][lm] = v;
+        }
+        #pragma unroll
+        for (int i = tid; i < BK * BN; i += NT) {
+            {{B_DECODE}}
+            const int gk = k0 + lk, gn = n0 + ln;
+            float v = 0.f;
+            if (gn < N && gk < k_end) {
+                const unsigned e = ((unsigned)batch * K + gk) * N + gn;
+{{B_CHAIN}}
+                v = B[{{B_IDX}}];
+            }
+            Bs[lk][ln] = v;
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+            #pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+            #pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+            #pragma unroll
+            for (int i = 0; i < TM; ++i)
+                #pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    #pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int gm = m0 + ty * TM + i;
+        if (gm >= M) continue;
+        #pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int gn = n0 + tx * TN + j;
+            if (gn < N) C[{{C_INDEX}}] = acc[i][j];
+        }
+    }
+}
+)";
+
+const char* kSplitSumTemplate = R"(
+// split-K partial sums of {{LABEL}}, added in ascending split order
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws, float* out0, const unsigned* dsc_step) {
+    constexpr unsigned COUNT = {{COUNT}}u, S = {{S}}u;
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= COUNT) return;
+    float acc = ws[i];
+    #pragma unroll 4
+    for (unsigned s = 1; s < S; ++s) acc += ws[s * COUNT + i];
+    out0[i] = acc;
+}
+)";
+
+struct GemmTile { int bm, bn, bk, tm, tn; };
+
+GemmTile choose_gemm_tile(int64_t M, int64_t N) {
+    GemmTile t;
+    t.bn = N <= 8 ? 8 : N <= 16 ? 16 : N <= 32 ? 32 : 64;
+    t.bm = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
+    t.bk = 16;
+    int per_thread = std::max(1, t.bm * t.bn / 256);
+    t.tn = std::min(4, std::min(per_thread, t.bn / 8));
+    t.tn = std::max(1, t.tn);
+    t.tm = std::max(1, per_thread / t.tn);
+    while (t.tm > 8) { t.tm /= 2; }
+    while (t.bm % t.tm) t.tm /= 2;
+    return t;
+}
+
+ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
+    const OpNode& mm = g.ops().nodes[c.node_id];
+    const ClusterInput& a = c.inputs[0];
+    const ClusterInput& b = c.inputs[1];
+    const int64_t BC = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
+    const int64_t r_graph = mm.shape[0];
+    const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
+    GemmTile t = choose_gemm_tile(M, N);
+    const int nt = (t.bm / t.tm) * (t.bn / t.tn);
+    const int64_t tiles = div_round_up(M, t.bm) * div_round_up(N, t.bn) * BC;
+
+    int64_t S, KC;
+    if (c.matmul_absorbs_reduce || r_graph == 1) {
+        // the backend owns the K split: enough CTAs to fill the machine, chunks of at least 8 k-tiles
+        S = 1;
+        if (tiles < opt.sm_count && K >= 16 * t.bk) S = std::min<int64_t>(div_round_up(2 * opt.sm_count, tiles), K / (8 * t.bk));
+        S = std::max<int64_t>(S, 1);
+        KC = div_round_up(div_round_up(K, S), t.bk) * t.bk;
+        S = div_round_up(K, KC);
+    } else {
+        // graph-level chunks must be honoured because something other than the Reduce reads them (kernel.rs:436)
+        S = r_graph;
+        KC = div_round_up(div_round_up(K, 16), S) * 16;
+    }
+    const bool via_scratch = S > 1 && (c.matmul_absorbs_reduce || r_graph == 1);
+
+    auto fast_axis = [&](const ClusterInput& in, int64_t rows, int64_t cols) {
+        // true when walking the row index is the (more) contiguous direction in memory
+        const int64_t mid = (rows / 2) * cols + cols / 2;
+        int64_t d_col = cols > 1 ? std::llabs(eval_chain(in.chain, mid + (cols / 2 + 1 < cols ? 1 : -1)) - eval_chain(in.chain, mid)) : INT64_MAX;
+        int64_t d_row = rows > 1 ? std::llabs(eval_chain(in.chain, mid + (rows / 2 + 1 < rows ? cols : -cols)) - eval_chain(in.chain, mid)) : INT64_MAX;
+        if (d_col == 0) d_col = INT64_MAX;
+        if (d_row == 0) d_row = INT64_MAX;
+        return d_row < d_col;
+    };
+    const bool a_m_fast = fast_axis(a, M, K);   // A element (m,k): rows = m
+    const bool b_k_fast = fast_axis(b, K, N);   // B element (k,n): rows = k
+    int uniq = 0;
+    std::ostringstream ca, cb;
+    std::string ia = emit_chain(ca, a.chain, "e", uniq, "                ");
+    std::string ib = emit_chain(cb, b.chain, "e", uniq, "                ");
+    const std::string name = "k" + num(ci);
+    std::string c_index = rows_mode ? "(((unsigned)split * M + gm) * BC + batch) * N + gn" : "(((unsigned)split * BC + batch) * M + gm) * N + gn";
+    ClusterCode code;
+    code.source = subst(kMatMulTemplate,
+                        {{"LABEL", c.label}, {"NAME", name}, {"NT", num(nt)}, {"BM", num(t.bm)}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"TM", num(t.tm)},
+                         {"TN", num(t.tn)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"KC", num(KC)}, {"BC", num(BC)},
+                         {"A_DECODE", a_m_fast ? "const int lm = i % BM, lk = i / BM;" : "const int lk = i % BK, lm = i / BK;"},
+                         {"B_DECODE", b_k_fast ? "const int lk = i % BK, ln = i / BK;" : "const int ln = i % BN, lk = i / BN;"},
+                         {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_INDEX", c_index}});
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)(div_round_up(M, t.bm) * div_round_up(N, t.bn));
+    l.grid_y = (uint32_t)BC;
+    l.grid_z = (uint32_t)S;
+    l.block = nt;
+    l.label = c.label;
+    l.cluster = ci;
+    const int64_t out_count = BC * M * N;
+    l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
+    if (via_scratch) l.args.push_back({KernelArg::Scratch, -1, 0});
+    else l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
+    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)out_count;
+    l.flops = 2.0 * (double)BC * (double)M * (double)N * (double)K;
+    code.launches.push_back(l);
+    if (via_scratch) {
+        code.scratch_bytes = S * out_count * 4;
+        const std::string sname = name + "_splitsum";
+        code.source += subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
+        KernelLaunch s;
+        s.entry = sname;
+        s.grid_x = (uint32_t)div_round_up(out_count, 256);
+        s.label = "SplitSum " + c.label;
+        s.cluster = ci;
+        s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+        code.launches.push_back(s);
+    }
+    return code;
+}
+
+// ---- unpad (reference: UnpadKernel, kernel.rs:644-710): adjoint of replicate padding ---------------
+
+const char* kUnpadTemplate = R"(
+// {{LABEL}}
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, float* out0, const unsigned* dsc_step) {
+    constexpr unsigned COUNT = {{COUNT}}u, INNER = {{INNER}}u;
+    constexpr int LEN = {{LEN}}, PAD = {{PAD}};
+    const unsigned o = blockIdx.x * 256u + threadIdx.x;
+    if (o >= COUNT) return;
+    const unsigned oi = o % INNER, oo = o / (INNER * LEN);
+    const int a = (int)(o / INNER % LEN);
+    const int k_min = a + PAD - (a == 0 ? PAD : 0);
+    const int k_max = a + PAD + (a == LEN - 1 ? PAD : 0);
+    float sum = 0.f;
+    for (int k = k_min; k <= k_max; ++k) {
+        const unsigned e = (oo * (LEN + 2 * PAD) + k) * INNER + oi;
+{{CHAIN}}
+        sum += in0[{{IDX}}];
+    }
+    out0[o] = sum;
+}
+)";
+
+ClusterCode gen_unpad(const Graph& g, const Cluster& c, int ci) {
+    const OpNode& node = g.ops().nodes[c.node_id];
+    const ClusterInput& in = c.inputs[0];
+    const int axis = node.op.axis;
+    int64_t inner = 1;
+    for (int d = axis + 1; d < node.shape.len(); ++d) inner *= node.shape[d];
+    std::ostringstream chain;
+    int uniq = 0;
+    std::string idx = emit_chain(chain, in.chain, "e", uniq, "        ");
+    const std::string name = "k" + num(ci);
+    const int64_t count = node.shape.element_count();
+    ClusterCode code;
+    code.source = subst(kUnpadTemplate, {{"LABEL", c.label}, {"NAME", name}, {"COUNT", num(count)}, {"INNER", num(inner)},
+                                         {"LEN", num(node.shape[axis])}, {"PAD", num(node.op.pad)}, {"CHAIN", chain.str()}, {"IDX", idx}});
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)div_round_up(count, 256);
+    l.label = c.label;
+    l.cluster = ci;
+    l.args = {{KernelArg::NodeBuffer, in.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+    l.algorithmic_bytes = chain_bytes(g, in) + 4.0 * (double)count;
+    code.launches.push_back(l);
+    return code;
+}
+
+// ---- windows_to_image (reference: WindowsToImageKernel, kernel.rs:712-810) -------------------------
+// col2im in gather form.  Unlike the reference kernel this checks that the window position lies
+// inside [0,out_h) x [0,out_w): the mathematically correct adjoint.
+
+const char* kW2ITemplate = R"(
+// {{LABEL}}
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, float* out0, const unsigned* dsc_step) {
+    constexpr unsigned COUNT = {{COUNT}}u;
+    constexpr int IN_H = {{IN_H}}, IN_W = {{IN_W}}, IN_C = {{IN_C}};
+    constexpr int OUT_H = {{OUT_H}}, OUT_W = {{OUT_W}}, GROUPS = {{GROUPS}}, FH = {{FH}}, FW = {{FW}}, GNC = {{GNC}}, SW = {{SW}}, SH = {{SH}};
+    const unsigned o = blockIdx.x * 256u + threadIdx.x;
+    if (o >= COUNT) return;
+    const int c = (int)(o % IN_C), x = (int)(o / IN_C % IN_W), y = (int)(o / (IN_C * IN_W) % IN_H);
+    const unsigned batch = o / (IN_C * IN_W * IN_H);
+    const int group = c / GNC, gc = c - group * GNC;
+    float sum = 0.f;
+    for (int fy = y % SH; fy < FH; fy += SH) {
+        const int oy = (y - fy) / SH;
+        if (y < fy || oy >= OUT_H) continue;
+        for (int fx = x % SW; fx < FW; fx += SW) {
+            const int ox = (x - fx) / SW;
+            if (x < fx || ox >= OUT_W) continue;
+            const unsigned e = (((((batch * OUT_H + oy) * OUT_W + ox) * GROUPS + group) * FH + fy) * FW + fx) * GNC + gc;
+{{CHAIN}}
+            sum += in0[{{IDX}}];
+        }
+    }
+    out0[o] = sum;
+}
+)";
+
+ClusterCode gen_w2i(const Graph& g, const Cluster& c, int ci) {
+    const OpNode& node = g.ops().nodes[c.node_id];
+    const ClusterInput& in = c.inputs[0];
+    const Shape& ws = in.arg_shape;
+    const int n = ws.len(), ni = node.shape.len();
+    std::ostringstream chain;
+    int uniq = 0;
+    std::string idx = emit_chain(chain, in.chain, "e", uniq, "            ");
+    const std::string name = "k" + num(ci);
+    const int64_t count = node.shape.element_count();
+    ClusterCode code;
+    code.source = subst(kW2ITemplate,
+                        {{"LABEL", c.label}, {"NAME", name}, {"COUNT", num(count)}, {"IN_H", num(node.shape[ni - 3])}, {"IN_W", num(node.shape[ni - 2])},
+                         {"IN_C", num(node.shape[ni - 1])}, {"OUT_H", num(ws[n - 6])}, {"OUT_W", num(ws[n - 5])}, {"GROUPS", num(ws[n - 4])},
+                         {"FH", num(ws[n - 3])}, {"FW", num(ws[n - 2])}, {"GNC", num(ws[n - 1])}, {"SW", num(node.op.stride_w)},
+                         {"SH", num(node.op.stride_h)}, {"CHAIN", chain.str()}, {"IDX", idx}});
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)div_round_up(count, 256);
+    l.label = c.label;
+    l.cluster = ci;
+    l.args = {{KernelArg::NodeBuffer, in.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+    l.algorithmic_bytes = chain_bytes(g, in) + 4.0 * (double)count;
+    code.launches.push_back(l);
+    return code;
+}
+
+// ---- scatter_add (reference: ScatterAddKernel, kernel.rs:812-874) ----------------------------------
+// The reference uses float atomics (order non-deterministic, README.md:21).  Here each CTA sorts the
+// (row, position) pairs of one chunk of positions in shared memory, sums each run of equal rows with
+// a fixed-shape segmented scan and writes one partial per touched row; a second kernel adds the
+// chunk partials to the accumulator in ascending chunk order.  Bitwise reproducible run to run.
+
+const char* kScatterTemplate = R"(
+// {{LABEL}}: per-chunk sorted partial sums
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part(const float* values, const float* indices, float* partial, const unsigned* dsc_step) {
+    constexpr unsigned CH = {{CH}}u, COUNT = {{COUNT}}u, ROWS = {{ROWS}}u, INNER = {{INNER}}u, OUTER = {{OUTER}}u, PER = CH / 256u;
+    __shared__ unsigned keys[CH];
+    __shared__ float vals[CH];
+    const unsigned tid = threadIdx.x, chunk = blockIdx.x, outer = blockIdx.y;
+    for (unsigned lp = tid; lp < CH; lp += 256u) {
+        const unsigned pos = chunk * CH + lp;
+        unsigned key = 0xffffffffu;
+        if (pos < COUNT) {
+            const unsigned e = pos;
+{{IDX_CHAIN}}
+            const unsigned row = (unsigned)__float_as_int(indices[{{IDX_IDX}}]);
+            if (row < ROWS) key = row * CH + lp;
+        }
+        keys[lp] = key;
+    }
+    __syncthreads();
+    // bitonic sort: keys are unique, so the order (row, then position) is fully determined
+    for (unsigned k = 2; k <= CH; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = tid; i < CH; i += 256u) {
+                const unsigned ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned w = 0; w < INNER; ++w) {
+        for (unsigned i = tid; i < CH; i += 256u) {
+            const unsigned key = keys[i];
+            float v = 0.f;
+            if (key != 0xffffffffu) {
+                const unsigned e = (outer * COUNT + chunk * CH + key % CH) * INNER + w;
+{{VAL_CHAIN}}
+                v = values[{{VAL_IDX}}];
+            }
+            vals[i] = v;
+        }
+        __syncthreads();
+        // segmented inclusive scan (Hillis-Steele); equal rows at distance d imply one segment between them
+        for (unsigned d = 1; d < CH; d <<= 1) {
+            float add[PER];
+            #pragma unroll
+            for (unsigned q = 0; q < PER; ++q) {
+                const unsigned i = tid + q * 256u;
+                add[q] = 0.f;
+                if (i >= d && keys[i] != 0xffffffffu && keys[i - d] / CH == keys[i] / CH) add[q] = vals[i - d];
+            }
+            __syncthreads();
+            #pragma unroll
+            for (unsigned q = 0; q < PER; ++q) {
+                const unsigned i = tid + q * 256u;
+                if (i >= d && keys[i] != 0xffffffffu && keys[i - d] / CH == keys[i] / CH) vals[i] = add[q] + vals[i];
+            }
+            __syncthreads();
+        }
+        for (unsigned i = tid; i < CH; i += 256u) {
+            const unsigned key = keys[i];
+            if (key == 0xffffffffu) continue;
+            const unsigned row = key / CH;
+            const bool tail = (i == CH - 1) || (keys[i + 1] / CH != row);
+            if (tail) partial[((chunk * OUTER + outer) * ROWS + row) * INNER + w] = vals[i];
+        }
+        __syncthreads();
+    }
+}
+
+// {{LABEL}}: accumulator + chunk partials in ascending chunk order
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}_sum({{ACC_PARAM}}const float* partial, float* out0, const unsigned* dsc_step) {
+    constexpr unsigned TOTAL = {{TOTAL}}u, NCHUNK = {{NCHUNK}}u;
+    const unsigned e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= TOTAL) return;
+{{ACC_CHAIN}}
+    float acc = {{ACC_VALUE}};
+    for (unsigned c = 0; c < NCHUNK; ++c) acc += partial[c * TOTAL + e];
+    out0[e] = acc;
+}
+)";
+
+ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci) {
+    const OpNode& node = g.ops().nodes[c.node_id];
+    const ClusterInput& values = c.inputs[0];
+    const ClusterInput& indices = c.inputs[1];
+    const int axis = node.op.axis;
+    const int64_t rows = node.shape[axis], count = values.arg_shape[axis];
+    int64_t inner = 1, outer = 1;
+    for (int d = axis + 1; d < node.shape.len(); ++d) inner *= node.shape[d];
+    for (int d = 0; d < axis; ++d) outer *= node.shape[d];
+    const int64_t ch = std::min<int64_t>(1024, std::max<int64_t>(256, pow2_ceil(count)));
+    DSC_CHECK(rows * ch < (int64_t)0xffffffffLL, "scatter_add table too large for 32-bit sort keys");
+    const int64_t nchunk = div_round_up(count, ch);
+    const int64_t total = node.shape.element_count();
+    const OpNode& acc_node = g.ops().nodes[c.copy_from];
+    const bool acc_literal = acc_node.op.kind == OpKind::Literal;
+
+    int uniq = 0;
+    std::ostringstream ic, vc, ac;
+    std::string ii = emit_chain(ic, indices.chain, "e", uniq, "            ");
+    std::string vi = emit_chain(vc, values.chain, "e", uniq, "                ");
+    std::string acc_value;
+    if (acc_literal) {
+        acc_value = "__uint_as_float(" + num(acc_node.op.literal_bits) + "u)";
+    } else {
+        acc_value = "acc_in[" + emit_chain(ac, c.inputs[2].chain, "e", uniq, "    ") + "]";
+    }
+    const std::string name = "k" + num(ci);
+    ClusterCode code;
+    code.source = subst(kScatterTemplate,
+                        {{"LABEL", c.label}, {"NAME", name}, {"CH", num(ch)}, {"COUNT", num(count)}, {"ROWS", num(rows)}, {"INNER", num(inner)},
+                         {"OUTER", num(outer)}, {"IDX_CHAIN", ic.str()}, {"IDX_IDX", ii}, {"VAL_CHAIN", vc.str()}, {"VAL_IDX", vi},
+                         {"ACC_PARAM", acc_literal ? "" : "const float* acc_in, "}, {"TOTAL", num(total)}, {"NCHUNK", num(nchunk)},
+                         {"ACC_CHAIN", ac.str()}, {"ACC_VALUE", acc_value}});
+    code.scratch_bytes = nchunk * total * 4;
+    KernelLaunch z;
+    z.kind = KernelLaunch::ZeroScratch;
+    z.zero_offset = 0;
+    z.zero_bytes = code.scratch_bytes;
+    z.label = "Fill(0) " + num(nchunk * total);
+    z.cluster = ci;
+    code.launches.push_back(z);
+    KernelLaunch p;
+    p.entry = name + "_part";
+    p.grid_x = (uint32_t)nchunk;
+    p.grid_y = (uint32_t)outer;
+    p.label = c.label;
+    p.cluster = ci;
+    p.args = {{KernelArg::NodeBuffer, values.node_id, 0}, {KernelArg::NodeBuffer, indices.node_id, 0}, {KernelArg::Scratch, -1, 0}};
+    p.algorithmic_bytes = chain_bytes(g, values) + chain_bytes(g, indices) + 2.0 * 4.0 * (double)total;
+    code.launches.push_back(p);
+    KernelLaunch s;
+    s.entry = name + "_sum";
+    s.grid_x = (uint32_t)div_round_up(total, 256);
+    s.label = "ScatterSum " + node.shape.str();
+    s.cluster = ci;
+    if (!acc_literal) s.args.push_back({KernelArg::NodeBuffer, c.copy_from, 0});
+    s.args.push_back({KernelArg::Scratch, -1, 0});
+    s.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
+    code.launches.push_back(s);
+    return code;
+}
+
+}  // namespace
+
+int64_t eval_chain(const ViewChain& chain, int64_t e) {
+    for (int vi = (int)chain.views.size() - 1; vi >= 0; --vi) {
+        const View& v = chain.views[vi];
+        auto ostr = v.output_shape.strides();
+        auto istr = v.input_shape.strides();
+        std::vector<int64_t> in_coord(v.input_offsets.begin(), v.input_offsets.end());
+        for (int i = 0; i < v.output_shape.len(); ++i) {
+            const auto& m = v.output_mapping[i];
+            if (!m.is_source) continue;
+            in_coord[m.axis] += m.step * ((e / ostr[i]) % v.output_shape[i]);
+        }
+        int64_t idx = 0;
+        for (int a = 0; a < v.input_shape.len(); ++a)
+            idx += std::min<int64_t>(std::max<int64_t>(in_coord[a], 0), v.input_shape[a] - 1) * istr[a];
+        e = idx;
+    }
+    return e;
+}
+
+std::string kernel_prelude() {
+    // integer parts are bit-exact restatements of kernel_common.glsl:205-216
+    return R"(// descent-b200 JIT kernels (generated)
+__device__ __forceinline__ unsigned dsc_pcg(unsigned v) {
+    const unsigned state = v * 747796405u + 2891336453u;
+    const unsigned word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+    return (word >> 22u) ^ word;
+}
+// float(hash)/float(0xffffffffu): the divisor rounds to 2^32, so this is an exact scale of the RNE conversion
+__device__ __forceinline__ float dsc_rand(unsigned uid, unsigned index, unsigned seed) {
+    const unsigned hash = dsc_pcg(dsc_pcg(index) + seed + uid);
+    return __uint2float_rn(hash) * 2.3283064365386962890625e-10f;
+}
+
+)";
+}
+
+ClusterCode generate_cluster_code(const Graph& graph, int ci, const CodegenOptions& opt) {
+    const Cluster& c = graph.clusters()[ci];
+    switch (c.kind) {
+        case ClusterKind::PerElement: return gen_per_element(graph, c, ci, opt);
+        case ClusterKind::Reduce: return gen_reduce(graph, c, ci, opt);
+        case ClusterKind::MatMul: return gen_matmul(graph, c, ci, opt);
+        case ClusterKind::Unpad: return gen_unpad(graph, c, ci);
+        case ClusterKind::WindowsToImage: return gen_w2i(graph, c, ci);
+        case ClusterKind::ScatterAdd: return gen_scatter_add(graph, c, ci);
+        case ClusterKind::AllReduce: {
+            ClusterCode code;
+            KernelLaunch l;
+            l.kind = KernelLaunch::AllReduce;
+            l.label = c.label;
+            l.cluster = ci;
+            l.args = {{KernelArg::NodeBuffer, c.outputs[0], 0}};
+            code.launches.push_back(l);
+            return code;
+        }
+    }
+    fail("unknown cluster kind");
+}
+
+}  // namespace descent

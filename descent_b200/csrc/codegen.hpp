@@ -1,0 +1,46 @@
+// CUDA C emission for clusters (replaces the GLSL emission of the reference's src/kernel.rs:151-874).
+// One translation unit per graph is JIT-compiled with NVRTC for sm_100a (runtime.cu).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "graph.hpp"
+
+namespace descent {
+
+struct KernelArg {
+    enum Kind { NodeBuffer, Scratch } kind = NodeBuffer;
+    int node_id = -1;            // NodeBuffer: the op node whose storage is bound
+    int64_t scratch_offset = 0;  // Scratch: byte offset inside the cluster's scratch area
+};
+
+struct KernelLaunch {
+    enum Kind { Kernel, ZeroScratch, AllReduce } kind = Kernel;
+    std::string entry;
+    uint32_t grid_x = 1, grid_y = 1, grid_z = 1, block = 256, smem = 0;
+    std::vector<KernelArg> args;
+    int64_t zero_offset = 0, zero_bytes = 0;  // ZeroScratch
+    std::string label;
+    int cluster = -1;
+    double algorithmic_bytes = 0;  // 4*(sum of min(source, addressed) input elements + outputs)
+    double flops = 0;              // 2*b*m*n*k for GEMMs
+};
+
+struct ClusterCode {
+    std::string source;
+    std::vector<KernelLaunch> launches;
+    int64_t scratch_bytes = 0;
+};
+
+struct CodegenOptions {
+    int sm_count = 148;
+    int dp_rank = 0;
+};
+
+std::string kernel_prelude();
+ClusterCode generate_cluster_code(const Graph& graph, int cluster_index, const CodegenOptions& options);
+
+// host-side evaluation of a chain (tests, layout heuristics): consumer element -> producer element
+int64_t eval_chain(const ViewChain& chain, int64_t e);
+
+}  // namespace descent

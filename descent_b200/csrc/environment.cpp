@@ -1,0 +1,506 @@
+// Executor: static memory plan, in-place parameter updates, one JIT module and one CUDA graph per
+// descent graph.  Reference behaviour being replaced: Environment::run / run_kernel
+// (src/environment.rs:241-516), BufferHeap (src/device/buffer_heap.rs), StagingWriter/Reader.
+#include "environment.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <map>
+
+namespace descent {
+
+void check(int rc) {
+    if (rc != DSC_OK) fail(std::string("device layer: ") + dsc_last_error());
+}
+
+std::string generate_graph_source(const Graph& graph, const CodegenOptions& options, std::vector<ClusterCode>* per_cluster) {
+    std::string src = kernel_prelude();
+    for (int ci = 0; ci < (int)graph.clusters().size(); ++ci) {
+        ClusterCode code = generate_cluster_code(graph, ci, options);
+        src += code.source;
+        if (per_cluster) per_cluster->push_back(std::move(code));
+    }
+    return src;
+}
+
+namespace {
+constexpr int64_t kAlign = 256;
+int64_t align_up(int64_t v, int64_t a = kAlign) { return (v + a - 1) / a * a; }
+
+struct Storage {
+    enum Kind { None, Param, Arena } kind = None;
+    int param = -1;
+    int64_t offset = 0;
+};
+
+// first-fit free list over one growing arena
+struct ArenaAllocator {
+    std::vector<std::pair<int64_t, int64_t>> free_list;  // (offset, size), sorted by offset
+    int64_t top = 0;
+    int64_t alloc(int64_t bytes) {
+        bytes = align_up(std::max<int64_t>(bytes, 4));
+        for (size_t i = 0; i < free_list.size(); ++i) {
+            if (free_list[i].second >= bytes) {
+                int64_t off = free_list[i].first;
+                free_list[i].first += bytes;
+                free_list[i].second -= bytes;
+                if (free_list[i].second == 0) free_list.erase(free_list.begin() + i);
+                return off;
+            }
+        }
+        if (!free_list.empty() && free_list.back().first + free_list.back().second == top) {
+            int64_t off = free_list.back().first;  // extend the trailing hole
+            free_list.pop_back();
+            top = off + bytes;
+            return off;
+        }
+        int64_t off = top;
+        top += bytes;
+        return off;
+    }
+    void release(int64_t off, int64_t bytes) {
+        bytes = align_up(std::max<int64_t>(bytes, 4));
+        auto it = std::lower_bound(free_list.begin(), free_list.end(), std::make_pair(off, (int64_t)0));
+        it = free_list.insert(it, {off, bytes});
+        if (it + 1 != free_list.end() && it->first + it->second == (it + 1)->first) {
+            it->second += (it + 1)->second;
+            free_list.erase(it + 1);
+        }
+        if (it != free_list.begin() && (it - 1)->first + (it - 1)->second == it->first) {
+            (it - 1)->second += it->second;
+            free_list.erase(it);
+        }
+    }
+};
+}  // namespace
+
+struct ResolvedLaunch {
+    KernelLaunch::Kind kind = KernelLaunch::Kernel;
+    dsc_kernel kernel = nullptr;
+    uint32_t gx = 1, gy = 1, gz = 1, block = 256, smem = 0;
+    std::vector<uint64_t> buffers;
+    uint64_t ptr = 0;  // ZeroScratch / AllReduce / Copy target
+    uint64_t src = 0;  // Copy source
+    size_t bytes = 0;  // ZeroScratch / Copy bytes, AllReduce element count
+    uint32_t fill_bits = 0;
+    bool is_copy = false, is_fill = false;
+    std::string label, entry;
+    int cluster = -1;
+    double algorithmic_bytes = 0, flops = 0;
+};
+
+struct Environment::GraphExec {
+    dsc_ctx* ctx = nullptr;
+    dsc_module* module = nullptr;
+    dsc_graph* cuda_graph = nullptr;
+    uint64_t arena = 0;
+    std::vector<ResolvedLaunch> launches;
+    GraphStats stats;
+    std::string source;
+    std::vector<uint64_t> parameter_buffers_at_plan;  // the plan bakes device addresses in
+    void release() {  // the environment is going away (or the graph is): give everything back while the context lives
+        if (cuda_graph) dsc_graph_destroy(cuda_graph);
+        if (module) dsc_module_destroy(module);
+        if (arena && ctx) dsc_free(ctx, arena);
+        cuda_graph = nullptr;
+        module = nullptr;
+        arena = 0;
+        ctx = nullptr;
+    }
+    ~GraphExec() { release(); }
+};
+
+Environment::Environment(int device) : parameters_(std::make_shared<std::vector<ParameterStorage>>()) {
+    if (device < 0) return;  // host-only: graphs and kernel source, never data
+    check(dsc_ctx_create(device, &ctx_));
+    check(dsc_ctx_sm_count(ctx_, &sm_count_));
+}
+void Environment::require_device(const char* what) const {
+    DSC_CHECK(ctx_ != nullptr, what << " needs a CUDA device; this environment is host-only (there is no CPU execution path)");
+}
+Environment::~Environment() {
+    if (ctx_) {
+        dsc_sync(ctx_);
+        for (auto& e : live_execs_) static_cast<GraphExec*>(e.get())->release();
+        live_execs_.clear();
+        for (auto& p : *parameters_)
+            if (p.buffer) dsc_free(ctx_, p.buffer);
+        dsc_ctx_destroy(ctx_);
+    }
+}
+
+Parameter Environment::static_parameter(const Shape& shape, const std::string& name) {
+    ParameterStorage s;
+    s.shape = shape;
+    s.name = name;
+    if (ctx_) check(dsc_alloc(ctx_, (size_t)shape.buffer_size(), &s.buffer));  // eager and never moved: plans bake the address in
+    parameters_->push_back(s);
+    return Parameter((int)parameters_->size() - 1, parameters_);
+}
+Parameter Environment::trainable_parameter(const Shape& shape, const std::string& name, Initializer reset_to) {
+    Parameter p = static_parameter(shape, name);
+    (*parameters_)[p.id()].reset_to = reset_to;
+    return p;
+}
+Parameter Environment::static_parameter_with_data(const Shape& shape, const std::string& name, const std::vector<float>& data) {
+    Parameter p = static_parameter(shape, name);
+    write_parameter(p, data.data(), data.size());
+    return p;
+}
+uint64_t Environment::parameter_buffer(const Parameter& p) const { return (*parameters_)[p.checked_id(parameters_)].buffer; }
+
+void Environment::write_parameter(const Parameter& p, const float* data, size_t count, bool pinned) {
+    if (!ctx_) return;  // host-only tracing: module/optimizer constructors may "write" initial state; nothing can read it back
+    const ParameterStorage& s = (*parameters_)[p.checked_id(parameters_)];
+    const size_t total = (size_t)s.shape.element_count();
+    DSC_CHECK(count <= total, "writing " << count << " floats into parameter '" << s.name << "' of " << total);
+    check(dsc_upload(ctx_, s.buffer, 0, data, count * 4, total * 4, pinned ? 1 : 0));
+}
+void Environment::read_parameter(const Parameter& p, float* dst, size_t count) {
+    require_device("read_parameter");
+    const ParameterStorage& s = (*parameters_)[p.checked_id(parameters_)];
+    DSC_CHECK(count <= (size_t)s.shape.element_count(), "reading past the end of parameter '" << s.name << "'");
+    check(dsc_download(ctx_, s.buffer, 0, dst, count * 4));
+}
+std::vector<float> Environment::read_parameter_to_vec(const Parameter& p) {
+    std::vector<float> v((size_t)p.shape().element_count());
+    read_parameter(p, v.data(), v.size());
+    return v;
+}
+float Environment::read_parameter_scalar(const Parameter& p) {
+    float v = 0.f;
+    read_parameter(p, &v, 1);
+    return v;
+}
+void Environment::reset_parameter(const Parameter& p, HostRng& rng) {
+    DSC_CHECK(p.is_trainable(), "reset_parameter on a static parameter");
+    const Initializer init = *p.reset_to();
+    const size_t n = (size_t)p.shape().element_count();
+    if (init.kind == InitKind::Zero) return zero_fill(p);
+    std::vector<float> data(n);
+    const float pi = 3.14159265358979323846f;
+    for (size_t i = 0; i < n; ++i) {
+        if (init.kind == InitKind::RandNormal) {  // Box-Muller, environment.rs:16-27
+            float u1 = rng.open01(), u2 = rng.open01();
+            data[i] = init.scale * (std::sqrt(-2.0f * std::log(u1)) * std::cos(2.0f * pi * u2));
+        } else {
+            data[i] = init.scale * (rng.open01() * 2.0f - 1.0f);
+        }
+    }
+    write_parameter(p, data.data(), n);
+}
+
+std::unique_ptr<Graph> Environment::build_graph(const std::function<void(Scope&)>& f) const {
+    Scope s(parameters_, dp_);
+    f(s);
+    return std::unique_ptr<Graph>(s.build_graph());
+}
+
+void Environment::init_data_parallel(int world, int rank, const void* id) {
+    if (ctx_) check(dsc_dp_init(ctx_, id, world, rank));
+    dp_.world = world;
+    dp_.rank = rank;
+}
+void Environment::sync() { if (ctx_) check(dsc_sync(ctx_)); }
+
+// ---- planning -------------------------------------------------------------------------------------
+
+Environment::GraphExec& Environment::prepare(const Graph& graph) {
+    require_device("running a graph");
+    if (graph.executor_state) {
+        auto* exec = static_cast<GraphExec*>(graph.executor_state.get());
+        if (exec->ctx == ctx_) return *exec;
+    }
+    DSC_CHECK(graph.parameters() == parameters_, "graph was built for another environment");
+    DSC_CHECK(graph.dp().world == dp_.world && graph.dp().rank == dp_.rank, "graph was built before data parallel was initialised");
+    auto exec_ptr = std::make_shared<GraphExec>();
+    GraphExec& exec = *exec_ptr;
+    exec.ctx = ctx_;
+    const OpGraph& ops = graph.ops();
+    const auto& clusters = graph.clusters();
+    const int n = (int)ops.nodes.size();
+    const int nc = (int)clusters.size();
+    auto cons = ops.consumers();
+
+    CodegenOptions opt;
+    opt.sm_count = sm_count_;
+    opt.dp_rank = dp_.rank;
+    std::vector<ClusterCode> codes;
+    exec.source = generate_graph_source(graph, opt, &codes);
+
+    std::vector<Storage> storage(n);
+    std::vector<int> alias(n, -1);  // AllReduce output -> its input node
+    std::map<int, int> input_node_of_param;
+    for (int id : graph.input_nodes()) {
+        storage[id] = {Storage::Param, ops.nodes[id].op.parameter_id, 0};
+        input_node_of_param[ops.nodes[id].op.parameter_id] = id;
+    }
+    auto cluster_of = [&](int node) { return ops.nodes[node].cluster_id; };
+
+    struct EndOp { bool is_fill; int src_node; uint32_t bits; int param; };
+    std::vector<EndOp> begin_ops, end_ops;
+    for (int out_id : graph.output_nodes()) {
+        const OpNode& out = ops.nodes[out_id];
+        const int p = out.op.parameter_id;
+        DSC_CHECK(out.in.size() == 1 && out.in[0].chain.is_identity(), "Output must read a plain array");
+        const int x = out.in[0].src;
+        const OpNode& xn = ops.nodes[x];
+        if (xn.op.kind == OpKind::Input) {
+            if (xn.op.parameter_id != p) {
+                DSC_CHECK(!input_node_of_param.count(p), "copying one parameter into another that the same graph also reads is not supported");
+                begin_ops.push_back({false, x, 0, p});
+            }
+            continue;
+        }
+        if (xn.op.kind == OpKind::Literal) { end_ops.push_back({true, -1, xn.op.literal_bits, p}); continue; }
+        DSC_CHECK(xn.cluster_id >= 0, "Output of a value no kernel computes (" << xn.op.name() << ")");
+        bool direct = storage[x].kind == Storage::None;
+        auto in_it = input_node_of_param.find(p);
+        if (direct && in_it != input_node_of_param.end()) {
+            // the parameter is also read: write in place only if every read is earlier, or is the same
+            // element in the same per-element kernel (environment.rs:372-383 swaps buffers instead)
+            const int w = cluster_of(x);
+            for (auto [dst, k] : cons[in_it->second]) {
+                const OpNode& d = ops.nodes[dst];
+                if (d.op.kind == OpKind::Output) continue;  // handled as a begin copy
+                const int c = d.cluster_id;
+                const OpEdge& e = d.in[k];
+                bool same_element = c == w && e.chain.is_identity() &&
+                                    ((clusters[w].kind == ClusterKind::PerElement && !d.op.is_gather_arg(e.arg)) ||
+                                     (clusters[w].kind == ClusterKind::ScatterAdd && e.arg == 0));
+                if (!(c < w || same_element)) direct = false;
+            }
+        }
+        if (direct) storage[x] = {Storage::Param, p, 0};
+        else end_ops.push_back({false, x, 0, p});
+    }
+
+    // gradient bucket: every AllReduce runs in place on its input, and the inputs are laid out
+    // back to back so one collective covers them all
+    ArenaAllocator arena;
+    std::vector<int> bucket_nodes;
+    int64_t bucket_bytes = 0;
+    for (int ci = 0; ci < nc; ++ci) {
+        if (clusters[ci].kind != ClusterKind::AllReduce) continue;
+        const int a = clusters[ci].outputs[0], x = clusters[ci].inputs[0].node_id;
+        DSC_CHECK(storage[x].kind == Storage::None && cons[x].size() == 1, "all-reduce input must be a private intermediate");
+        DSC_CHECK(storage[a].kind == Storage::None, "all-reduce output cannot be written straight into a parameter");
+        storage[x] = {Storage::Arena, -1, bucket_bytes};
+        alias[a] = x;
+        bucket_nodes.push_back(x);
+        bucket_bytes += align_up(ops.nodes[x].shape.buffer_size(), 16);
+    }
+    if (bucket_bytes) arena.top = align_up(bucket_bytes);
+
+    // lifetimes of the remaining cluster outputs
+    std::vector<int> death(n, -1);
+    std::vector<char> lives_to_end(n, 0);
+    for (const auto& eo : end_ops)
+        if (!eo.is_fill) lives_to_end[eo.src_node] = 1;
+    for (int id = 0; id < n; ++id) {
+        if (!ops.nodes[id].alive) continue;
+        for (auto [dst, k] : cons[id]) {
+            (void)k;
+            int c = ops.nodes[dst].cluster_id;
+            if (c >= 0) death[id] = std::max(death[id], c);
+        }
+    }
+    std::vector<int64_t> scratch_offset(nc, 0);
+    std::vector<std::vector<int>> dying_at(nc + 1);
+    for (int ci = 0; ci < nc; ++ci) {
+        // release what nobody after the previous cluster needs
+        if (ci > 0)
+            for (int id : dying_at[ci - 1]) arena.release(storage[id].offset, ops.nodes[id].shape.buffer_size());
+        for (int out : clusters[ci].outputs) {
+            if (alias[out] >= 0) {
+                storage[out] = storage[alias[out]];
+                continue;
+            }
+            if (storage[out].kind != Storage::None) continue;  // parameter or bucket
+            storage[out] = {Storage::Arena, -1, arena.alloc(ops.nodes[out].shape.buffer_size())};
+            int d = std::max(death[out], ci);
+            if (!lives_to_end[out]) dying_at[d].push_back(out);
+        }
+        if (codes[ci].scratch_bytes > 0) {
+            scratch_offset[ci] = arena.alloc(codes[ci].scratch_bytes);
+            arena.release(scratch_offset[ci], codes[ci].scratch_bytes);  // free again for the next cluster...
+        }
+        // ...but outputs of this cluster were allocated before the scratch, so they never overlap it
+    }
+    exec.stats.arena_bytes = arena.top;
+    check(dsc_alloc(ctx_, (size_t)std::max<int64_t>(arena.top, 256), &exec.arena));
+    check(dsc_fill_u32(ctx_, exec.arena, 0, 0, (size_t)std::max<int64_t>(arena.top, 256) / 4));
+
+    // compile
+    auto t0 = std::chrono::steady_clock::now();
+    const char* options[] = {"-fmad=false"};
+    bool any_kernel = false;
+    for (const auto& code : codes)
+        for (const auto& l : code.launches) any_kernel |= l.kind == KernelLaunch::Kernel;
+    if (any_kernel) check(dsc_module_jit(ctx_, exec.source.c_str(), options, 1, &exec.module));
+    exec.stats.jit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+    auto device_address = [&](int node) -> uint64_t {
+        const Storage& s = storage[node];
+        DSC_CHECK(s.kind != Storage::None, "node " << node << " (" << ops.nodes[node].op.name() << ") has no storage");
+        return s.kind == Storage::Param ? (*parameters_)[s.param].buffer : exec.arena + (uint64_t)s.offset;
+    };
+    auto add_copy_or_fill = [&](const EndOp& eo) {
+        ResolvedLaunch r;
+        const ParameterStorage& ps = (*parameters_)[eo.param];
+        r.ptr = ps.buffer;
+        r.bytes = (size_t)ps.shape.buffer_size();
+        if (eo.is_fill) {
+            r.is_fill = true;
+            r.fill_bits = eo.bits;
+            r.label = "Fill " + ps.shape.str();
+        } else {
+            r.is_copy = true;
+            r.src = device_address(eo.src_node);
+            r.label = "Copy " + ps.shape.str();
+        }
+        exec.launches.push_back(r);
+    };
+    for (const auto& eo : begin_ops) add_copy_or_fill(eo);
+    bool bucket_done = false;
+    for (int ci = 0; ci < nc; ++ci) {
+        for (const KernelLaunch& l : codes[ci].launches) {
+            ResolvedLaunch r;
+            r.kind = l.kind;
+            r.label = l.label;
+            r.entry = l.entry;
+            r.cluster = ci;
+            r.algorithmic_bytes = l.algorithmic_bytes;
+            r.flops = l.flops;
+            if (l.kind == KernelLaunch::ZeroScratch) {
+                r.ptr = exec.arena + (uint64_t)(scratch_offset[ci] + l.zero_offset);
+                r.bytes = (size_t)l.zero_bytes;
+            } else if (l.kind == KernelLaunch::AllReduce) {
+                if (bucket_done) continue;
+                bucket_done = true;
+                r.ptr = exec.arena;
+                r.bytes = (size_t)(bucket_bytes / 4);
+                r.label = "AllReduce bucket [" + std::to_string(bucket_bytes / 4) + "]";
+            } else {
+                check(dsc_module_get_kernel(exec.module, l.entry.c_str(), &r.kernel));
+                r.gx = l.grid_x; r.gy = l.grid_y; r.gz = l.grid_z; r.block = l.block; r.smem = l.smem;
+                for (const auto& a : l.args)
+                    r.buffers.push_back(a.kind == KernelArg::NodeBuffer ? device_address(a.node_id)
+                                                                        : exec.arena + (uint64_t)(scratch_offset[ci] + a.scratch_offset));
+                exec.stats.kernel_launches += 1;
+                exec.stats.algorithmic_bytes += l.algorithmic_bytes;
+                exec.stats.flops += l.flops;
+            }
+            exec.launches.push_back(r);
+        }
+    }
+    for (const auto& eo : end_ops) add_copy_or_fill(eo);
+    exec.stats.total_nodes = (int)exec.launches.size();
+    for (const auto& p : *parameters_) exec.parameter_buffers_at_plan.push_back(p.buffer);
+
+    graph.executor_state = exec_ptr;
+    live_execs_.push_back(exec_ptr);
+    return exec;
+}
+
+void Environment::launch_all(GraphExec& exec, std::vector<float>* per_launch_ms) {
+    std::vector<void*> events;
+    if (per_launch_ms) {
+        events.resize(exec.launches.size() + 1);
+        for (auto& e : events) check(dsc_event_create(&e));
+        check(dsc_event_record(ctx_, events[0]));
+    }
+    for (size_t i = 0; i < exec.launches.size(); ++i) {
+        const ResolvedLaunch& r = exec.launches[i];
+        if (r.is_copy) check(dsc_copy(ctx_, r.ptr, r.src, r.bytes));
+        else if (r.is_fill) check(dsc_fill_u32(ctx_, r.ptr, 0, r.fill_bits, r.bytes / 4));
+        else if (r.kind == KernelLaunch::ZeroScratch) check(dsc_fill_u32(ctx_, r.ptr, 0, 0, r.bytes / 4));
+        else if (r.kind == KernelLaunch::AllReduce) check(dsc_dp_allreduce_sum_f32(ctx_, r.ptr, r.bytes));
+        else check(dsc_launch(ctx_, r.kernel, r.gx, r.gy, r.gz, r.block, r.smem, r.buffers.data(), (int)r.buffers.size()));
+        if (per_launch_ms) check(dsc_event_record(ctx_, events[i + 1]));
+    }
+    if (per_launch_ms) {
+        per_launch_ms->resize(exec.launches.size());
+        for (size_t i = 0; i < exec.launches.size(); ++i) check(dsc_event_elapsed_ms(events[i], events[i + 1], &(*per_launch_ms)[i]));
+        for (auto& e : events) dsc_event_destroy(e);
+    }
+}
+
+void Environment::run(const Graph& graph, uint32_t rand_seed) {
+    GraphExec& exec = prepare(graph);
+    if (profile_runs_) {
+        check(dsc_set_rand_seed(ctx_, rand_seed));
+        std::vector<float> ms;
+        launch_all(exec, &ms);
+        for (size_t i = 0; i < ms.size(); ++i) {
+            auto it = std::find_if(timing_totals_.begin(), timing_totals_.end(), [&](auto& p) { return p.first == exec.launches[i].label; });
+            if (it == timing_totals_.end()) timing_totals_.push_back({exec.launches[i].label, ms[i]});
+            else it->second += ms[i];
+        }
+        timing_runs_ += 1;
+        return;
+    }
+    if (!use_cuda_graph_) {
+        check(dsc_set_rand_seed(ctx_, rand_seed));
+        launch_all(exec, nullptr);
+        return;
+    }
+    if (!exec.cuda_graph) {
+        check(dsc_graph_begin_capture(ctx_));
+        try {
+            launch_all(exec, nullptr);
+        } catch (...) {
+            dsc_graph* dead = nullptr;
+            dsc_graph_end_capture(ctx_, &dead);
+            if (dead) dsc_graph_destroy(dead);
+            throw;
+        }
+        check(dsc_graph_end_capture(ctx_, &exec.cuda_graph));
+    }
+    check(dsc_graph_launch(ctx_, exec.cuda_graph, rand_seed));
+}
+
+std::vector<KernelTiming> Environment::profile(const Graph& graph, uint32_t rand_seed, int iterations) {
+    GraphExec& exec = prepare(graph);
+    std::vector<KernelTiming> out(exec.launches.size());
+    for (size_t i = 0; i < exec.launches.size(); ++i) {
+        out[i].label = exec.launches[i].label;
+        out[i].entry = exec.launches[i].entry;
+        out[i].cluster = exec.launches[i].cluster;
+        out[i].algorithmic_bytes = exec.launches[i].algorithmic_bytes;
+        out[i].flops = exec.launches[i].flops;
+    }
+    for (int it = 0; it < iterations; ++it) {
+        check(dsc_set_rand_seed(ctx_, rand_seed + (uint32_t)it));
+        std::vector<float> ms;
+        launch_all(exec, &ms);
+        for (size_t i = 0; i < ms.size(); ++i) out[i].ms += ms[i] / (double)iterations;
+    }
+    return out;
+}
+
+GraphStats Environment::stats(const Graph& graph) { return prepare(graph).stats; }
+std::string Environment::kernel_source(const Graph& graph) {
+    CodegenOptions opt;
+    opt.sm_count = sm_count_;
+    opt.dp_rank = dp_.rank;
+    return generate_graph_source(graph, opt, nullptr);
+}
+
+// average total + the five most expensive kernels by label (timestamp.rs:155-179)
+void Environment::print_timings(const std::string& label) {
+    if (timing_runs_ == 0) return;
+    double total = 0;
+    for (auto& p : timing_totals_) total += p.second;
+    std::printf("%s: %.3f ms/run over %d runs\n", label.c_str(), total / timing_runs_, timing_runs_);
+    auto sorted = timing_totals_;
+    std::sort(sorted.begin(), sorted.end(), [](auto& a, auto& b) { return a.second > b.second; });
+    for (size_t i = 0; i < sorted.size() && i < 5; ++i) std::printf("  %8.3f ms  %s\n", sorted[i].second / timing_runs_, sorted[i].first.c_str());
+    timing_totals_.clear();
+    timing_runs_ = 0;
+}
+
+}  // namespace descent

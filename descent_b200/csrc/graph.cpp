@@ -1,0 +1,581 @@
+// Graph passes and clustering (reference: src/graph.rs).  See graph.hpp for the design notes.
+#include "graph.hpp"
+
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <numeric>
+#include <queue>
+#include <unordered_map>
+
+namespace descent {
+
+// ---- small helpers ----------------------------------------------------------------------------
+
+std::string Op::name() const {
+    static const char* un[] = {"Mov", "Neg", "Sqrt", "Exp", "Log", "Sin", "Cos", "FloatToUint", "UintToFloat"};
+    static const char* bi[] = {"Add", "Sub", "Mul", "Div", "Pow", "UAdd", "UMul", "URem", "UBitXor"};
+    std::ostringstream os;
+    switch (kind) {
+        case OpKind::Input: os << "Input(" << parameter_id << ")"; break;
+        case OpKind::Output: os << "Output(" << parameter_id << ")"; break;
+        case OpKind::Literal:
+            if (literal_is_u32) os << "U32(" << literal_bits << ")";
+            else os << "F32(" << literal_f32_value() << ")";
+            break;
+        case OpKind::BuiltIn: os << (built_in == BuiltInOp::Coord ? "Coord" : "Rand"); break;
+        case OpKind::Unary: os << un[(int)unary]; break;
+        case OpKind::Binary: os << bi[(int)binary]; break;
+        case OpKind::CompareAndSelect: os << (compare == CompareMode::Eq ? "SelectEq" : "SelectGt"); break;
+        case OpKind::MatMul: os << "MatMul"; break;
+        case OpKind::Reduce: os << (reduce == ReduceOp::Max ? "ReduceMax(" : "ReduceSum(") << axis << ")"; break;
+        case OpKind::Unpad: os << "Unpad" << pad << "(" << axis << ")"; break;
+        case OpKind::WindowsToImage: os << "WindowsToImage"; break;
+        case OpKind::Gather: os << "Gather(" << axis << ")"; break;
+        case OpKind::ScatterAdd: os << "ScatterAdd(" << axis << ")"; break;
+        case OpKind::AllReduce: os << "AllReduce"; break;
+    }
+    return os.str();
+}
+
+Initializer Initializer::for_relu(int64_t fan_in) { return rand_normal(std::sqrt(2.0f / (float)fan_in)); }
+Initializer Initializer::for_siren(int64_t fan_in, bool first) {
+    return rand_uniform(std::sqrt(6.0f / (float)fan_in) * (first ? 30.0f : 1.0f));
+}
+
+std::vector<int> OpGraph::topo_order() const {
+    int n = (int)nodes.size();
+    std::vector<int> indeg(n, 0);
+    auto cons = consumers();
+    for (int i = 0; i < n; ++i)
+        if (nodes[i].alive) indeg[i] = (int)nodes[i].in.size();
+    std::priority_queue<int, std::vector<int>, std::greater<int>> ready;
+    for (int i = 0; i < n; ++i)
+        if (nodes[i].alive && indeg[i] == 0) ready.push(i);
+    std::vector<int> order;
+    while (!ready.empty()) {
+        int i = ready.top();
+        ready.pop();
+        order.push_back(i);
+        for (auto [d, k] : cons[i]) {
+            (void)k;
+            if (--indeg[d] == 0) ready.push(d);
+        }
+    }
+    int live = 0;
+    for (const auto& nd : nodes) live += nd.alive;
+    DSC_CHECK((int)order.size() == live, "op graph has a cycle");
+    return order;
+}
+
+static void json_shape(std::ostringstream& os, const Shape& s) {
+    os << "[";
+    for (int i = 0; i < s.len(); ++i) os << (i ? "," : "") << s[i];
+    os << "]";
+}
+static void json_chain(std::ostringstream& os, const ViewChain& c) {
+    os << "{\"input_count\":" << c.input_count << ",\"output_count\":" << c.output_count << ",\"views\":[";
+    for (size_t vi = 0; vi < c.views.size(); ++vi) {
+        const View& v = c.views[vi];
+        os << (vi ? "," : "") << "{\"input_shape\":";
+        json_shape(os, v.input_shape);
+        os << ",\"input_offsets\":[";
+        for (size_t i = 0; i < v.input_offsets.size(); ++i) os << (i ? "," : "") << v.input_offsets[i];
+        os << "],\"mapping\":[";
+        for (size_t i = 0; i < v.output_mapping.size(); ++i) {
+            const auto& m = v.output_mapping[i];
+            os << (i ? "," : "");
+            if (m.is_source) os << "[" << m.axis << "," << m.step << "]";
+            else os << "null";
+        }
+        os << "],\"output_shape\":";
+        json_shape(os, v.output_shape);
+        os << "}";
+    }
+    os << "]}";
+}
+
+std::string export_ops_json(const OpGraph& ops, const std::vector<ParameterStorage>& parameters, const std::vector<Cluster>* clusters) {
+    static const char* un[] = {"Mov", "Neg", "Sqrt", "Exp", "Log", "Sin", "Cos", "FloatToUint", "UintToFloat"};
+    static const char* bi[] = {"Add", "Sub", "Mul", "Div", "Pow", "UAdd", "UMul", "URem", "UBitXor"};
+    std::ostringstream os;
+    os << "{\"parameters\":[";
+    for (size_t i = 0; i < parameters.size(); ++i) {
+        os << (i ? "," : "") << "{\"id\":" << i << ",\"name\":\"" << parameters[i].name << "\",\"shape\":";
+        json_shape(os, parameters[i].shape);
+        os << ",\"trainable\":" << (parameters[i].reset_to.has_value() ? "true" : "false") << "}";
+    }
+    os << "],\"nodes\":[";
+    bool first = true;
+    for (int id : ops.topo_order()) {
+        const OpNode& n = ops.nodes[id];
+        os << (first ? "" : ",") << "{\"id\":" << id << ",\"colour\":" << n.colour << ",\"shape\":";
+        first = false;
+        json_shape(os, n.shape);
+        const Op& op = n.op;
+        os << ",\"op\":\"";
+        switch (op.kind) {
+            case OpKind::Input: os << "Input\",\"parameter\":" << op.parameter_id; break;
+            case OpKind::Output: os << "Output\",\"parameter\":" << op.parameter_id; break;
+            case OpKind::Literal: os << "Literal\",\"is_u32\":" << (op.literal_is_u32 ? "true" : "false") << ",\"bits\":" << op.literal_bits; break;
+            case OpKind::BuiltIn:
+                if (op.built_in == BuiltInOp::Coord) os << "Coord\"";
+                else os << "Rand\",\"uid\":" << op.rand_uid;
+                break;
+            case OpKind::Unary: os << "Unary\",\"kind\":\"" << un[(int)op.unary] << "\""; break;
+            case OpKind::Binary: os << "Binary\",\"kind\":\"" << bi[(int)op.binary] << "\""; break;
+            case OpKind::CompareAndSelect: os << "Select\",\"kind\":\"" << (op.compare == CompareMode::Eq ? "Eq" : "Gt") << "\""; break;
+            case OpKind::MatMul: os << "MatMul\",\"mode\":\"" << (op.output_mode == MatMulOutputMode::Batches ? "Batches" : "Rows") << "\""; break;
+            case OpKind::Reduce: os << "Reduce\",\"kind\":\"" << (op.reduce == ReduceOp::Max ? "Max" : "Sum") << "\",\"axis\":" << op.axis; break;
+            case OpKind::Unpad: os << "Unpad\",\"axis\":" << op.axis << ",\"pad\":" << op.pad; break;
+            case OpKind::WindowsToImage: os << "WindowsToImage\",\"stride_w\":" << op.stride_w << ",\"stride_h\":" << op.stride_h; break;
+            case OpKind::Gather: os << "Gather\",\"axis\":" << op.axis; break;
+            case OpKind::ScatterAdd: os << "ScatterAdd\",\"axis\":" << op.axis; break;
+            case OpKind::AllReduce: os << "AllReduce\""; break;
+        }
+        os << ",\"cluster\":" << n.cluster_id << ",\"args\":[";
+        for (int a = 0; a < n.arg_count(); ++a) {
+            const OpEdge* e = n.arg_edge(a);
+            DSC_CHECK(e != nullptr, "node " << id << " (" << op.name() << ") is missing argument " << a);
+            os << (a ? "," : "") << "{\"src\":" << e->src << ",\"arg_shape\":";
+            json_shape(os, e->arg_shape);
+            os << ",\"chain\":";
+            json_chain(os, e->chain);
+            os << "}";
+        }
+        os << "]}";
+    }
+    os << "]";
+    if (clusters) {
+        os << ",\"clusters\":[";
+        for (size_t i = 0; i < clusters->size(); ++i) {
+            const Cluster& c = (*clusters)[i];
+            os << (i ? "," : "") << "{\"kind\":" << (int)c.kind << ",\"level\":" << c.level << ",\"label\":\"" << c.label << "\",\"members\":[";
+            for (size_t k = 0; k < c.members.size(); ++k) os << (k ? "," : "") << c.members[k];
+            os << "],\"inputs\":[";
+            for (size_t k = 0; k < c.inputs.size(); ++k) os << (k ? "," : "") << c.inputs[k].node_id;
+            os << "],\"outputs\":[";
+            for (size_t k = 0; k < c.outputs.size(); ++k) os << (k ? "," : "") << c.outputs[k];
+            os << "]}";
+        }
+        os << "]";
+    }
+    os << "}";
+    return os.str();
+}
+
+std::string Scope::export_json() const { return export_ops_json(ops_, *parameters_, nullptr); }
+std::string Graph::export_json() const { return export_ops_json(ops_, *parameters_, &clusters_); }
+
+// ---- Graph ------------------------------------------------------------------------------------
+
+Graph::Graph(SharedParameters parameters, const OpGraph& ops, DataParallel dp)
+    : parameters_(std::move(parameters)), ops_(ops), dp_(dp) {
+    eliminate_dead_code();
+    eliminate_moves();
+    simplify_arithmetic();
+    eliminate_common_subgraphs();
+    eliminate_dead_code();
+    build_clusters();
+}
+
+std::vector<int> Graph::input_nodes() const {
+    std::vector<int> v;
+    for (int i = 0; i < (int)ops_.nodes.size(); ++i)
+        if (ops_.nodes[i].alive && ops_.nodes[i].op.kind == OpKind::Input) v.push_back(i);
+    return v;
+}
+std::vector<int> Graph::output_nodes() const {
+    std::vector<int> v;
+    for (int i = 0; i < (int)ops_.nodes.size(); ++i)
+        if (ops_.nodes[i].alive && ops_.nodes[i].op.kind == OpKind::Output) v.push_back(i);
+    return v;
+}
+
+// keep only what an Output depends on (graph.rs:150-165)
+void Graph::eliminate_dead_code() {
+    int n = (int)ops_.nodes.size();
+    std::vector<char> live(n, 0);
+    std::vector<int> stack;
+    for (int i = 0; i < n; ++i)
+        if (ops_.nodes[i].alive && ops_.nodes[i].op.kind == OpKind::Output) { live[i] = 1; stack.push_back(i); }
+    while (!stack.empty()) {
+        int i = stack.back();
+        stack.pop_back();
+        for (const auto& e : ops_.nodes[i].in)
+            if (!live[e.src]) { live[e.src] = 1; stack.push_back(e.src); }
+    }
+    for (int i = 0; i < n; ++i)
+        if (ops_.nodes[i].alive && !live[i]) ops_.remove_node(i);
+}
+
+// Fold every Mov into the chains of its consumers.  A Mov that feeds an Output stays, because the
+// Output takes over its producer's buffer (graph.rs:276-279).
+void Graph::eliminate_moves() {
+    auto order = ops_.topo_order();
+    auto cons = ops_.consumers();
+    for (int id : order) {
+        OpNode& node = ops_.nodes[id];
+        if (!node.alive || !node.op.is_mov()) continue;
+        DSC_CHECK(node.in.size() == 1, "a value or gradient is used but nothing was ever written to it (node " << id << ", shape "
+                                           << node.shape.str() << ")");
+        const OpEdge in_edge = node.in[0];
+        bool feeds_output = false;
+        for (auto [dst, k] : cons[id]) {
+            OpNode& d = ops_.nodes[dst];
+            if (!d.alive) continue;
+            OpEdge& out_edge = d.in[k];
+            if (d.op.kind == OpKind::Output) {
+                // a pure reshape of a computed value needs no copy: the executor writes the producer
+                // straight into the parameter's buffer
+                const OpKind sk = ops_.nodes[in_edge.src].op.kind;
+                const bool computed = sk != OpKind::Input && sk != OpKind::Literal && sk != OpKind::BuiltIn;
+                if (!(in_edge.chain.is_identity() && computed)) { feeds_output = true; continue; }
+            }
+            DSC_CHECK(out_edge.src == id, "consumer table out of date");
+            ViewChain chain = in_edge.chain;
+            chain.append(out_edge.chain);
+            out_edge.src = in_edge.src;
+            out_edge.chain = chain;
+            cons[in_edge.src].push_back({dst, k});
+        }
+        if (!feeds_output) ops_.remove_node(id);
+    }
+}
+
+// x*1, x+0 (and the u32 forms) become moves, which then fold (graph.rs:221-253)
+void Graph::simplify_arithmetic() {
+    bool mov_added = false;
+    for (int id : ops_.topo_order()) {
+        OpNode& node = ops_.nodes[id];
+        if (node.op.kind != OpKind::Binary) continue;
+        auto is_skip = [&](const Op& lit) {
+            switch (node.op.binary) {
+                case BinaryOp::Mul: return lit.is_literal_f32(1.0f);
+                case BinaryOp::Add: return lit.is_literal_f32(0.0f);
+                case BinaryOp::UMul: return lit.is_literal_u32(1);
+                case BinaryOp::UAdd: return lit.is_literal_u32(0);
+                default: return false;
+            }
+        };
+        int skip = -1;
+        for (int a = 0; a < 2 && skip < 0; ++a) {
+            const OpEdge* e = node.arg_edge(a);
+            if (e && is_skip(ops_.nodes[e->src].op)) skip = a;
+        }
+        if (skip < 0) continue;
+        OpEdge keep = *node.arg_edge(1 - skip);
+        keep.arg = 0;
+        node.in.clear();
+        node.in.push_back(keep);
+        node.op = Op::mov();
+        mov_added = true;
+    }
+    if (mov_added) eliminate_moves();
+}
+
+// merge structurally identical nodes (graph.rs:167-203)
+void Graph::eliminate_common_subgraphs() {
+    std::vector<int> remap(ops_.nodes.size());
+    std::iota(remap.begin(), remap.end(), 0);
+    std::unordered_map<std::string, std::vector<int>> by_key;
+    for (int id : ops_.topo_order()) {
+        OpNode& node = ops_.nodes[id];
+        for (auto& e : node.in) e.src = remap[e.src];
+        if (!node.op.can_merge()) continue;
+        std::sort(node.in.begin(), node.in.end(), [](const OpEdge& a, const OpEdge& b) { return a.arg < b.arg; });
+        std::ostringstream key;
+        key << node.op.name() << "|" << (int)node.op.kind << "|" << node.op.literal_bits << "|" << node.op.rand_uid << "|"
+            << (int)node.op.output_mode << "|" << node.op.stride_w << "," << node.op.stride_h << "|" << node.shape.str();
+        for (const auto& e : node.in) key << "|" << e.src << ":" << e.arg << ":" << e.chain.views.size();
+        auto& bucket = by_key[key.str()];
+        int found = -1;
+        for (int other : bucket) {
+            const OpNode& o = ops_.nodes[other];
+            if (o.op == node.op && o.shape == node.shape && o.in == node.in) { found = other; break; }
+        }
+        if (found >= 0) {
+            remap[id] = found;
+            ops_.remove_node(id);
+        } else {
+            bucket.push_back(id);
+        }
+    }
+}
+
+// ---- clustering -------------------------------------------------------------------------------
+
+static bool edge_is_fusable(const OpGraph& ops, int dst, const OpEdge& e) {
+    const OpNode& s = ops.nodes[e.src];
+    const OpNode& d = ops.nodes[dst];
+    return s.op.is_per_element() && d.op.is_per_element() && !d.op.is_gather_arg(e.arg) && e.chain.is_identity() &&
+           s.shape.element_count() == d.shape.element_count();
+}
+
+void Graph::build_per_element_program(Cluster& c) {
+    std::map<int, int> member_op_index;
+    auto find_input = [&](const ClusterInput& in) {
+        for (size_t i = 0; i < c.inputs.size(); ++i)
+            if (c.inputs[i] == in) return (int)i;
+        c.inputs.push_back(in);
+        return (int)c.inputs.size() - 1;
+    };
+    struct ArgKey { int src; ViewChain chain; Shape arg_shape; int op_index; };
+    std::vector<ArgKey> loaded;
+    auto cons = ops_.consumers();
+    for (int id : c.members) {
+        const OpNode& node = ops_.nodes[id];
+        PerElementOp pe;
+        pe.op = node.op;
+        pe.shape = node.shape;
+        for (int a = 0; a < node.arg_count(); ++a) {
+            const OpEdge* e = node.arg_edge(a);
+            DSC_CHECK(e != nullptr, "missing argument");
+            auto m = member_op_index.find(e->src);
+            if (m != member_op_index.end() && edge_is_fusable(ops_, id, *e)) { pe.args[a] = m->second; continue; }
+            const OpNode& src = ops_.nodes[e->src];
+            if (node.op.is_gather_arg(a)) {
+                DSC_CHECK(!src.op.is_inline_source(), "gather from a literal/built-in is not supported");
+                pe.input_index = find_input({e->src, e->chain, e->arg_shape});
+                pe.arg_shape = e->arg_shape;
+                continue;
+            }
+            int op_index = -1;
+            for (const auto& l : loaded)
+                if (l.src == e->src && l.chain == e->chain && l.arg_shape == e->arg_shape) op_index = l.op_index;
+            if (op_index < 0) {
+                PerElementOp ld;
+                if (src.op.kind == OpKind::Literal) {
+                    ld.kind = PerElementOp::Literal;
+                    ld.op = src.op;
+                } else if (src.op.kind == OpKind::BuiltIn) {
+                    ld.kind = PerElementOp::BuiltIn;
+                    ld.op = src.op;
+                    ld.chain = e->chain;
+                    ld.arg_shape = src.shape;
+                } else {
+                    ld.kind = PerElementOp::Load;
+                    ld.input_index = find_input({e->src, e->chain, e->arg_shape});
+                }
+                op_index = (int)c.ops.size();
+                c.ops.push_back(ld);
+                loaded.push_back({e->src, e->chain, e->arg_shape, op_index});
+            }
+            pe.args[a] = op_index;
+        }
+        switch (node.op.kind) {
+            case OpKind::Unary: pe.kind = PerElementOp::Unary; break;
+            case OpKind::Binary: pe.kind = PerElementOp::Binary; break;
+            case OpKind::CompareAndSelect: pe.kind = PerElementOp::Select; break;
+            case OpKind::Gather: pe.kind = PerElementOp::Gather; break;
+            default: fail("unexpected op in per-element cluster");
+        }
+        int op_index = (int)c.ops.size();
+        c.ops.push_back(pe);
+        member_op_index[id] = op_index;
+        bool needs_store = false;
+        for (auto [dst, k] : cons[id]) {
+            const OpNode& d = ops_.nodes[dst];
+            if (!d.alive) continue;
+            if (d.cluster_id != node.cluster_id || !edge_is_fusable(ops_, dst, d.in[k])) needs_store = true;
+        }
+        if (needs_store) {
+            c.outputs.push_back(id);
+            c.output_ops.push_back(op_index);
+        }
+    }
+    std::ostringstream label;
+    label << "PerElement (" << c.ops.size() << " ops) [" << c.element_count << "]";
+    c.label = label.str();
+}
+
+void Graph::build_clusters() {
+    auto order = ops_.topo_order();
+    auto cons = ops_.consumers();
+    int n = (int)ops_.nodes.size();
+
+    // MatMul -> Reduce(Sum, axis 0) pairs become one GEMM (the reduce is the split-K sum, array.rs:515)
+    std::vector<int> absorbed_by(n, -1);  // reduce node -> matmul node
+    for (int id : order) {
+        const OpNode& node = ops_.nodes[id];
+        if (node.op.kind != OpKind::Reduce || node.op.reduce != ReduceOp::Sum || node.op.axis != 0) continue;
+        const OpEdge& e = node.in[0];
+        const OpNode& src = ops_.nodes[e.src];
+        if (src.op.kind == OpKind::MatMul && e.chain.is_identity() && cons[e.src].size() == 1) absorbed_by[id] = e.src;
+    }
+
+    auto edge_cost = [&](int dst, const OpEdge& e) {
+        const OpNode& s = ops_.nodes[e.src];
+        if (s.op.kind == OpKind::Input || s.op.is_inline_source()) return 0;
+        if (absorbed_by[dst] == e.src) return 0;
+        if (ops_.nodes[dst].op.kind == OpKind::Output) return 0;
+        return edge_is_fusable(ops_, dst, e) ? 0 : 1;
+    };
+
+    // as-soon-as-possible levels; all AllReduce nodes share one level so they form one bucket
+    std::vector<int> asap(n, 0);
+    auto forward = [&](int ar_level) {
+        for (int id : order) {
+            int lv = 0;
+            for (const auto& e : ops_.nodes[id].in) lv = std::max(lv, asap[e.src] + edge_cost(id, e));
+            if (ops_.nodes[id].op.kind == OpKind::AllReduce) lv = std::max(lv, ar_level);
+            asap[id] = lv;
+        }
+    };
+    forward(0);
+    int ar_level = -1;
+    for (int id : order)
+        if (ops_.nodes[id].op.kind == OpKind::AllReduce) ar_level = std::max(ar_level, asap[id]);
+    if (ar_level >= 0) forward(ar_level);
+
+    // as-late-as-possible levels: producers move next to their first consumer
+    std::vector<int> level(n, 0);
+    for (auto it = order.rbegin(); it != order.rend(); ++it) {
+        int id = *it;
+        const OpNode& node = ops_.nodes[id];
+        int lv = INT32_MAX;
+        for (auto [dst, k] : cons[id])
+            if (ops_.nodes[dst].alive) lv = std::min(lv, level[dst] - edge_cost(dst, ops_.nodes[dst].in[k]));
+        if (lv == INT32_MAX || node.op.kind == OpKind::AllReduce || node.op.kind == OpKind::Input) lv = asap[id];
+        DSC_CHECK(lv >= asap[id], "level inversion");
+        level[id] = lv;
+    }
+
+    // per-element clusters: connected components of fusable edges within a level
+    std::vector<int> parent(n);
+    std::iota(parent.begin(), parent.end(), 0);
+    std::function<int(int)> find = [&](int x) { return parent[x] == x ? x : parent[x] = find(parent[x]); };
+    for (int id : order)
+        for (const auto& e : ops_.nodes[id].in)
+            if (edge_is_fusable(ops_, id, e) && level[id] == level[e.src]) parent[find(id)] = find(e.src);
+
+    std::map<int, int> root_to_cluster;
+    std::vector<Cluster> clusters;
+    for (int id : order) {
+        OpNode& node = ops_.nodes[id];
+        if (node.op.is_per_element()) {
+            int root = find(id);
+            auto it = root_to_cluster.find(root);
+            if (it == root_to_cluster.end()) {
+                Cluster c;
+                c.kind = ClusterKind::PerElement;
+                c.level = level[id];
+                c.element_count = node.shape.element_count();
+                clusters.push_back(c);
+                it = root_to_cluster.emplace(root, (int)clusters.size() - 1).first;
+            }
+            node.cluster_id = it->second;
+            clusters[it->second].members.push_back(id);
+            continue;
+        }
+        Cluster c;
+        c.level = level[id];
+        c.node_id = id;
+        std::ostringstream label;
+        auto add_input = [&](const OpEdge& e) { c.inputs.push_back({e.src, e.chain, e.arg_shape}); };
+        switch (node.op.kind) {
+            case OpKind::Reduce: {
+                if (absorbed_by[id] >= 0) {
+                    // joins the cluster of its MatMul, created earlier in topological order
+                    int mm_cluster = ops_.nodes[absorbed_by[id]].cluster_id;
+                    node.cluster_id = mm_cluster;
+                    clusters[mm_cluster].members.push_back(id);
+                    clusters[mm_cluster].outputs[0] = id;
+                    clusters[mm_cluster].matmul_absorbs_reduce = true;
+                    clusters[mm_cluster].level = level[id];
+                    continue;
+                }
+                c.kind = ClusterKind::Reduce;
+                add_input(node.in[0]);
+                label << "Reduce (k=" << node.in[0].arg_shape[node.op.axis] << ") " << node.shape.str();
+                break;
+            }
+            case OpKind::MatMul: {
+                c.kind = ClusterKind::MatMul;
+                add_input(*node.arg_edge(0));
+                add_input(*node.arg_edge(1));
+                label << "MatMul (k=" << node.arg_edge(0)->arg_shape.at(-1) << ") " << node.shape.str();
+                break;
+            }
+            case OpKind::Unpad:
+                c.kind = ClusterKind::Unpad;
+                add_input(node.in[0]);
+                label << "Unpad " << node.shape.str();
+                break;
+            case OpKind::WindowsToImage:
+                c.kind = ClusterKind::WindowsToImage;
+                add_input(node.in[0]);
+                label << "WindowsToImage " << node.shape.str();
+                break;
+            case OpKind::ScatterAdd: {
+                c.kind = ClusterKind::ScatterAdd;
+                const OpEdge* acc = node.arg_edge(0);
+                DSC_CHECK(acc->chain.is_identity() || ops_.nodes[acc->src].op.kind == OpKind::Literal,
+                          "scatter_add accumulator must be a plain array or a broadcast literal");
+                add_input(*node.arg_edge(1));
+                add_input(*node.arg_edge(2));
+                if (ops_.nodes[acc->src].op.kind != OpKind::Literal) add_input(*acc);
+                c.copy_from = acc->src;
+                label << "ScatterAdd " << node.arg_edge(1)->arg_shape.str();
+                break;
+            }
+            case OpKind::AllReduce:
+                c.kind = ClusterKind::AllReduce;
+                DSC_CHECK(node.in[0].chain.is_identity(), "all-reduce input must be a plain array");
+                add_input(node.in[0]);
+                label << "AllReduce " << node.shape.str();
+                break;
+            default: continue;  // Input / Output / Literal / BuiltIn own no kernel
+        }
+        c.members.push_back(id);
+        c.outputs.push_back(id);
+        c.label = label.str();
+        node.cluster_id = (int)clusters.size();
+        clusters.push_back(c);
+    }
+    for (auto& c : clusters)
+        if (c.kind == ClusterKind::PerElement) build_per_element_program(c);
+
+    // levels are a topological order of clusters: fusable edges stay inside a cluster, all others climb
+    std::vector<int> idx(clusters.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return clusters[a].level < clusters[b].level; });
+    std::vector<int> new_index(clusters.size());
+    for (size_t i = 0; i < idx.size(); ++i) new_index[idx[i]] = (int)i;
+    clusters_.clear();
+    for (int i : idx) clusters_.push_back(clusters[i]);
+    for (auto& node : ops_.nodes)
+        if (node.alive && node.cluster_id >= 0) node.cluster_id = new_index[node.cluster_id];
+}
+
+void Graph::write_dot_file(KernelDotOutput mode, const std::string& path) const {
+    std::ofstream w(path);
+    w << "digraph G {\n";
+    auto emit_node = [&](int id) {
+        const OpNode& n = ops_.nodes[id];
+        w << "n" << id << " [shape=box,label=\"" << n.op.name() << "\\n" << n.shape.str() << "\"";
+        if (mode == KernelDotOutput::Color) w << ",style=filled,fillcolor=\"/set312/" << (n.colour % 12) + 1 << "\"";
+        w << "];\n";
+    };
+    std::vector<char> done(ops_.nodes.size(), 0);
+    if (mode == KernelDotOutput::Cluster) {
+        for (size_t ci = 0; ci < clusters_.size(); ++ci) {
+            w << "subgraph cluster" << ci << " { style=filled; color=lightgrey; label=\"" << clusters_[ci].label << "\";\n";
+            for (int id : clusters_[ci].members) { emit_node(id); done[id] = 1; }
+            w << "}\n";
+        }
+    }
+    for (int id = 0; id < (int)ops_.nodes.size(); ++id)
+        if (ops_.nodes[id].alive && !done[id]) emit_node(id);
+    for (int id = 0; id < (int)ops_.nodes.size(); ++id) {
+        if (!ops_.nodes[id].alive) continue;
+        for (const auto& e : ops_.nodes[id].in)
+            w << "n" << e.src << " -> n" << id << " [label=\"" << (e.chain.is_identity() ? "" : "V") << "\"];\n";
+    }
+    w << "}\n";
+}
+
+}  // namespace descent

@@ -1,0 +1,95 @@
+// Graph compiler: optimisation passes over the op graph and partitioning into kernels ("clusters").
+//
+// The pass list follows the reference's `Graph::new` (src/graph.rs:111-139): dead-code elimination,
+// move elimination, x*1 / x+0 simplification, common-subgraph elimination, clustering.  What differs
+// is B200-first:
+//   * every Mov folds into its consumers' ViewChain (no materialised im2col / window / permute
+//     copies; the reference keeps a copy whenever a reshape cannot fold, graph.rs:262-284),
+//   * a MatMul followed by its split-K Reduce (array.rs:515) is one GEMM cluster, the K split is
+//     chosen by the backend rather than by MATMUL_MAX_K_SIZE,
+//   * per-element clusters are connected components of fusable edges inside one dependency level,
+//     which is cycle-free by construction (the reference re-checks reachability per candidate,
+//     graph.rs:366-435),
+//   * all gradient AllReduce nodes sit on one level so they form a single bucket.
+// Results never depend on clustering.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "array.hpp"
+
+namespace descent {
+
+enum class ClusterKind { PerElement, Reduce, MatMul, Unpad, WindowsToImage, ScatterAdd, AllReduce };
+
+// one buffer argument of a kernel: a producer node read through a chain
+struct ClusterInput {
+    int node_id = -1;
+    ViewChain chain;
+    Shape arg_shape;
+    bool operator==(const ClusterInput& o) const { return node_id == o.node_id && chain == o.chain && arg_shape == o.arg_shape; }
+};
+
+// straight-line program of a per-element kernel (reference: PerElementKernelOp, kernel.rs:8-35)
+struct PerElementOp {
+    enum Kind { Load, Literal, BuiltIn, Unary, Binary, Select, Gather } kind = Load;
+    int input_index = -1;        // Load / Gather: index into Cluster::inputs
+    Op op;                       // Literal / BuiltIn / Unary / Binary / Select / Gather payload
+    ViewChain chain;             // BuiltIn: chain from the built-in's own index space
+    Shape arg_shape;             // BuiltIn / Gather
+    int args[MAX_OP_ARGS] = {-1, -1, -1, -1};
+    Shape shape;                 // Gather: shape of the gather node
+};
+
+struct Cluster {
+    ClusterKind kind = ClusterKind::PerElement;
+    int level = 0;
+    std::vector<int> members;          // op nodes computed by this kernel, in topological order
+    std::vector<ClusterInput> inputs;  // buffers read
+    std::vector<int> outputs;          // op nodes whose values are written to memory
+    // PerElement
+    int64_t element_count = 0;
+    std::vector<PerElementOp> ops;
+    std::vector<int> output_ops;       // op index stored to outputs[i]
+    // single-node kernels
+    int node_id = -1;                  // the Reduce / MatMul / Unpad / WindowsToImage / ScatterAdd / AllReduce node
+    bool matmul_absorbs_reduce = false;  // outputs[0] is the Reduce(axis 0) node that followed the MatMul
+    int copy_from = -1;                // ScatterAdd: accumulator node taken in place (graph.rs:601-621)
+    std::string label;                 // as the reference's Kernel::label_name (kernel.rs)
+};
+
+class Graph {
+public:
+    Graph(SharedParameters parameters, const OpGraph& ops, DataParallel dp);
+
+    const OpGraph& ops() const { return ops_; }
+    const std::vector<Cluster>& clusters() const { return clusters_; }  // already in execution order
+    const SharedParameters& parameters() const { return parameters_; }
+    const DataParallel& dp() const { return dp_; }
+    std::vector<int> input_nodes() const;
+    std::vector<int> output_nodes() const;
+
+    enum class KernelDotOutput { None, Cluster, Color };
+    void write_dot_file(KernelDotOutput mode, const std::string& path) const;  // graph.rs:656
+    std::string export_json() const;  // optimised graph + clusters (tests, debugging)
+
+    // opaque per-graph state owned by the executor (compiled module, memory plan, CUDA graph)
+    mutable std::shared_ptr<void> executor_state;
+
+private:
+    void eliminate_dead_code();
+    void eliminate_moves();
+    void simplify_arithmetic();
+    void eliminate_common_subgraphs();
+    void build_clusters();
+    void build_per_element_program(Cluster& c);
+
+    SharedParameters parameters_;
+    OpGraph ops_;
+    DataParallel dp_;
+    std::vector<Cluster> clusters_;
+};
+
+std::string export_ops_json(const OpGraph& ops, const std::vector<ParameterStorage>& parameters, const std::vector<Cluster>* clusters);
+
+}  // namespace descent

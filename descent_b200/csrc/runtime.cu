@@ -1,0 +1,498 @@
+// Device layer behind include/descent_cuda.h: context, stream-ordered buffers, pinned staging,
+// NVRTC JIT for sm_100a, launches, CUDA-graph replay, events, NCCL data parallel.
+// Replaces the reference's Vulkan runtime (src/device/*.rs) and shader-module creation
+// (src/kernel.rs:946-1034); nothing here is a translation of it -- the mechanisms are CUDA's own
+// (memory pools instead of a buddy heap, graphs instead of command buffers, events instead of
+// timestamp query pools).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <nvrtc.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/descent_cuda.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) return set_error(DSC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// Driver entry points come through the runtime so the library never links libcuda directly
+// (it must load on a GPU-less build box for the symbol/compile checks).
+struct DriverApi {
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+    bool loaded = false;
+};
+DriverApi g_drv;
+
+int load_driver_api() {
+    if (g_drv.loaded) return DSC_OK;
+    auto get = [](const char* name, void** fn) -> int {
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || *fn == nullptr)
+            return set_error(DSC_ERR_CUDA, "driver entry point %s unavailable: %s", name, cudaGetErrorString(e));
+        return DSC_OK;
+    };
+    int rc;
+    if ((rc = get("cuModuleLoadData", (void**)&g_drv.ModuleLoadData))) return rc;
+    if ((rc = get("cuModuleUnload", (void**)&g_drv.ModuleUnload))) return rc;
+    if ((rc = get("cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction))) return rc;
+    if ((rc = get("cuLaunchKernel", (void**)&g_drv.LaunchKernel))) return rc;
+    if ((rc = get("cuFuncSetAttribute", (void**)&g_drv.FuncSetAttribute))) return rc;
+    if ((rc = get("cuGetErrorString", (void**)&g_drv.GetErrorString))) return rc;
+    if ((rc = get("cuTensorMapEncodeTiled", (void**)&g_drv.TensorMapEncodeTiled))) return rc;
+    g_drv.loaded = true;
+    return DSC_OK;
+}
+
+int cu_error(CUresult r, const char* what) {
+    const char* msg = nullptr;
+    if (g_drv.GetErrorString) g_drv.GetErrorString(r, &msg);
+    return set_error(DSC_ERR_CUDA, "%s failed: %s", what, msg ? msg : "unknown driver error");
+}
+#define CU_TRY(expr)                                 \
+    do {                                             \
+        CUresult r_ = (expr);                        \
+        if (r_ != CUDA_SUCCESS) return cu_error(r_, #expr); \
+    } while (0)
+
+// NCCL is optional (N=1 never touches it) and is resolved at run time so that importing torch first
+// and this library second share one libnccl.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+    if (g_nccl.handle) return DSC_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return set_error(DSC_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
+        return set_error(DSC_ERR_NCCL, "libnccl.so.2 is missing expected symbols");
+    g_nccl.handle = h;
+    return DSC_OK;
+}
+#define NCCL_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        ncclResult_t r_ = (expr);                                                                       \
+        if (r_ != ncclSuccess) return set_error(DSC_ERR_NCCL, "%s failed: %s", #expr, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+__global__ void dsc_set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
+__global__ void dsc_fill_u32_kernel(unsigned* p, unsigned v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+constexpr size_t kStagingSlotBytes = 16u << 20;
+constexpr int kStagingSlots = 2;
+
+}  // namespace
+
+struct dsc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    unsigned* step_params = nullptr;  // device: [0] rand_seed
+    char* staging[kStagingSlots] = {nullptr, nullptr};
+    cudaEvent_t staging_done[kStagingSlots] = {nullptr, nullptr};
+    int staging_next = 0;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    bool capturing = false;
+};
+struct dsc_module {
+    dsc_ctx* ctx;
+    CUmodule module;
+};
+struct dsc_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+};
+
+extern "C" {
+
+const char* dsc_last_error(void) { return g_last_error.c_str(); }
+
+int dsc_device_count(int* count) {
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return set_error(DSC_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return DSC_OK;
+}
+
+int dsc_ctx_create(int device, dsc_ctx** out) {
+    *out = nullptr;
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return set_error(DSC_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(nullptr));  // create the primary context
+    int rc = load_driver_api();
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return set_error(DSC_ERR_UNSUPPORTED, "device %d is sm_%d%d; this backend is written for sm_100a (B200)", device, prop.major, prop.minor);
+    dsc_ctx* ctx = new dsc_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;  // keep freed memory cached in the pool: alloc/free cost no driver calls
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    CUDA_TRY(cudaMalloc(&ctx->step_params, 4 * sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(ctx->step_params, 0, 4 * sizeof(unsigned)));
+    for (int i = 0; i < kStagingSlots; ++i) {
+        CUDA_TRY(cudaHostAlloc(&ctx->staging[i], kStagingSlotBytes, cudaHostAllocDefault));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->staging_done[i], cudaEventDisableTiming));
+    }
+    *out = ctx;
+    return DSC_OK;
+}
+
+int dsc_ctx_destroy(dsc_ctx* ctx) {
+    if (!ctx) return DSC_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    for (int i = 0; i < kStagingSlots; ++i) {
+        if (ctx->staging[i]) cudaFreeHost(ctx->staging[i]);
+        if (ctx->staging_done[i]) cudaEventDestroy(ctx->staging_done[i]);
+    }
+    cudaFree(ctx->step_params);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DSC_OK;
+}
+
+int dsc_ctx_device(dsc_ctx* ctx, int* device) { *device = ctx->device; return DSC_OK; }
+int dsc_ctx_stream(dsc_ctx* ctx, void** s) { *s = (void*)ctx->stream; return DSC_OK; }
+int dsc_ctx_sm_count(dsc_ctx* ctx, int* count) { *count = ctx->sm_count; return DSC_OK; }
+
+int dsc_alloc(dsc_ctx* ctx, size_t bytes, uint64_t* id) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CUDA_TRY(cudaMallocAsync(&p, bytes ? bytes : 4, ctx->stream));
+    *id = (uint64_t)p;
+    return DSC_OK;
+}
+int dsc_free(dsc_ctx* ctx, uint64_t id) {
+    if (!id) return DSC_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaFreeAsync((void*)id, ctx->stream));
+    return DSC_OK;
+}
+int dsc_fill_u32(dsc_ctx* ctx, uint64_t id, size_t offset_bytes, uint32_t value, size_t count) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (count == 0) return DSC_OK;
+    unsigned* p = (unsigned*)(id + offset_bytes);
+    if (value == 0) {
+        CUDA_TRY(cudaMemsetAsync(p, 0, count * 4, ctx->stream));
+    } else {
+        unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, (size_t)ctx->sm_count * 8);
+        dsc_fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>(p, value, count);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return DSC_OK;
+}
+int dsc_copy(dsc_ctx* ctx, uint64_t dst, uint64_t src, size_t bytes) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync((void*)dst, (const void*)src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DSC_OK;
+}
+
+int dsc_upload(dsc_ctx* ctx, uint64_t id, size_t offset, const void* src, size_t n, size_t zero_tail_to, int src_is_pinned) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    char* dst = (char*)id + offset;
+    if (src_is_pinned) {
+        if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        const char* s = (const char*)src;
+        size_t done = 0;
+        while (done < n) {
+            int slot = ctx->staging_next;
+            ctx->staging_next = (slot + 1) % kStagingSlots;
+            CUDA_TRY(cudaEventSynchronize(ctx->staging_done[slot]));
+            size_t chunk = std::min(kStagingSlotBytes, n - done);
+            memcpy(ctx->staging[slot], s + done, chunk);
+            CUDA_TRY(cudaMemcpyAsync(dst + done, ctx->staging[slot], chunk, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaEventRecord(ctx->staging_done[slot], ctx->stream));
+            done += chunk;
+        }
+    }
+    if (zero_tail_to > offset + n) CUDA_TRY(cudaMemsetAsync(dst + n, 0, zero_tail_to - offset - n, ctx->stream));
+    return DSC_OK;
+}
+int dsc_download(dsc_ctx* ctx, uint64_t id, size_t offset, void* dst, size_t n) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n) CUDA_TRY(cudaMemcpyAsync(dst, (const char*)id + offset, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
+}
+int dsc_host_alloc(size_t bytes, void** out) {
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 4, cudaHostAllocDefault));
+    return DSC_OK;
+}
+int dsc_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return DSC_OK;
+}
+
+int dsc_nvrtc_compile(const char* cuda_source, const char* const* options, int num_options, void** cubin, size_t* bytes) {
+    *cubin = nullptr;
+    *bytes = 0;
+    nvrtcProgram prog;
+    nvrtcResult r = nvrtcCreateProgram(&prog, cuda_source, "descent_kernels.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return set_error(DSC_ERR_NVRTC, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--extra-device-vectorization"};
+    for (int i = 0; i < num_options; ++i) opts.push_back(options[i]);
+    r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    if (r != NVRTC_SUCCESS) {
+        size_t log_size = 0;
+        nvrtcGetProgramLogSize(prog, &log_size);
+        std::string log(log_size, '\0');
+        nvrtcGetProgramLog(prog, log.data());
+        nvrtcDestroyProgram(&prog);
+        if (log.size() > 3500) log.resize(3500);
+        return set_error(DSC_ERR_NVRTC, "NVRTC compilation failed (%s):\n%s", nvrtcGetErrorString(r), log.c_str());
+    }
+    size_t size = 0;
+    r = nvrtcGetCUBINSize(prog, &size);
+    if (r != NVRTC_SUCCESS || size == 0) {
+        nvrtcDestroyProgram(&prog);
+        return set_error(DSC_ERR_NVRTC, "nvrtcGetCUBINSize: %s", nvrtcGetErrorString(r));
+    }
+    void* data = malloc(size);
+    nvrtcGetCUBIN(prog, (char*)data);
+    nvrtcDestroyProgram(&prog);
+    *cubin = data;
+    *bytes = size;
+    return DSC_OK;
+}
+int dsc_host_buffer_free(void* p) { free(p); return DSC_OK; }
+
+int dsc_module_load_cubin(dsc_ctx* ctx, const void* cubin, size_t bytes, dsc_module** out) {
+    (void)bytes;
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = load_driver_api();
+    if (rc) return rc;
+    CUmodule m;
+    CU_TRY(g_drv.ModuleLoadData(&m, cubin));
+    *out = new dsc_module{ctx, m};
+    return DSC_OK;
+}
+int dsc_module_jit(dsc_ctx* ctx, const char* cuda_source, const char* const* options, int num_options, dsc_module** out) {
+    void* cubin = nullptr;
+    size_t bytes = 0;
+    int rc = dsc_nvrtc_compile(cuda_source, options, num_options, &cubin, &bytes);
+    if (rc) return rc;
+    rc = dsc_module_load_cubin(ctx, cubin, bytes, out);
+    free(cubin);
+    return rc;
+}
+int dsc_module_get_kernel(dsc_module* module, const char* entry, dsc_kernel* out) {
+    CUfunction f;
+    CUDA_TRY(cudaSetDevice(module->ctx->device));
+    CUresult r = g_drv.ModuleGetFunction(&f, module->module, entry);
+    if (r != CUDA_SUCCESS) return set_error(DSC_ERR_INVALID, "kernel '%s' not found in module", entry);
+    *out = (dsc_kernel)f;
+    return DSC_OK;
+}
+int dsc_module_destroy(dsc_module* module) {
+    if (!module) return DSC_OK;
+    cudaSetDevice(module->ctx->device);
+    g_drv.ModuleUnload(module->module);
+    delete module;
+    return DSC_OK;
+}
+int dsc_kernel_set_max_dynamic_smem(dsc_kernel kernel, int bytes) {
+    CU_TRY(g_drv.FuncSetAttribute((CUfunction)kernel, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, bytes));
+    return DSC_OK;
+}
+
+int dsc_launch(dsc_ctx* ctx, dsc_kernel kernel, uint32_t gx, uint32_t gy, uint32_t gz, uint32_t block_x, uint32_t smem,
+               const uint64_t* buffers, int num_buffers) {
+    if (num_buffers < 0 || num_buffers > 62) return set_error(DSC_ERR_INVALID, "too many kernel buffers (%d)", num_buffers);
+    if (gx == 0 || gy == 0 || gz == 0) return DSC_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    uint64_t values[64];
+    void* params[64];
+    for (int i = 0; i < num_buffers; ++i) {
+        values[i] = buffers[i];
+        params[i] = &values[i];
+    }
+    values[num_buffers] = (uint64_t)ctx->step_params;
+    params[num_buffers] = &values[num_buffers];
+    CU_TRY(g_drv.LaunchKernel((CUfunction)kernel, gx, gy, gz, block_x, 1, 1, smem, (CUstream)ctx->stream, params, nullptr));
+    return DSC_OK;
+}
+int dsc_set_rand_seed(dsc_ctx* ctx, uint32_t rand_seed) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    dsc_set_u32_kernel<<<1, 1, 0, ctx->stream>>>(ctx->step_params, rand_seed);
+    CUDA_TRY(cudaGetLastError());
+    return DSC_OK;
+}
+
+int dsc_graph_begin_capture(dsc_ctx* ctx) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    return DSC_OK;
+}
+int dsc_graph_end_capture(dsc_ctx* ctx, dsc_graph** out) {
+    *out = nullptr;
+    ctx->capturing = false;
+    cudaGraph_t g = nullptr;
+    CUDA_TRY(cudaStreamEndCapture(ctx->stream, &g));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(g);
+        return set_error(DSC_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    dsc_graph* gr = new dsc_graph();
+    gr->graph = g;
+    gr->exec = exec;
+    *out = gr;
+    return DSC_OK;
+}
+int dsc_graph_launch(dsc_ctx* ctx, dsc_graph* graph, uint32_t rand_seed) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    dsc_set_u32_kernel<<<1, 1, 0, ctx->stream>>>(ctx->step_params, rand_seed);
+    CUDA_TRY(cudaGraphLaunch(graph->exec, ctx->stream));
+    return DSC_OK;
+}
+int dsc_graph_destroy(dsc_graph* graph) {
+    if (!graph) return DSC_OK;
+    if (graph->exec) cudaGraphExecDestroy(graph->exec);
+    if (graph->graph) cudaGraphDestroy(graph->graph);
+    delete graph;
+    return DSC_OK;
+}
+
+int dsc_event_create(void** event) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    *event = (void*)e;
+    return DSC_OK;
+}
+int dsc_event_record(dsc_ctx* ctx, void* event) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaEventRecord((cudaEvent_t)event, ctx->stream));
+    return DSC_OK;
+}
+int dsc_event_elapsed_ms(void* start, void* end, float* ms) {
+    CUDA_TRY(cudaEventSynchronize((cudaEvent_t)end));
+    CUDA_TRY(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)end));
+    return DSC_OK;
+}
+int dsc_event_destroy(void* event) {
+    if (event) CUDA_TRY(cudaEventDestroy((cudaEvent_t)event));
+    return DSC_OK;
+}
+int dsc_sync(dsc_ctx* ctx) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DSC_OK;
+}
+
+int dsc_dp_unique_id(void* out128) {
+    int rc = load_nccl();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, 128);
+    return DSC_OK;
+}
+int dsc_dp_init(dsc_ctx* ctx, const void* unique_id128, int world, int rank) {
+    if (world < 1 || rank < 0 || rank >= world) return set_error(DSC_ERR_INVALID, "bad data-parallel world/rank %d/%d", world, rank);
+    ctx->world = world;
+    ctx->rank = rank;
+    if (world == 1) return DSC_OK;
+    int rc = load_nccl();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, 128);
+    NCCL_TRY(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+    return DSC_OK;
+}
+int dsc_dp_allreduce_sum_f32(dsc_ctx* ctx, uint64_t id, size_t count) {
+    if (ctx->world == 1 || count == 0) return DSC_OK;
+    if (!ctx->comm) return set_error(DSC_ERR_NCCL, "data-parallel communicator not initialised");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    NCCL_TRY(g_nccl.AllReduce((const void*)id, (void*)id, count, ncclFloat32, ncclSum, ctx->comm, ctx->stream));
+    return DSC_OK;
+}
+int dsc_dp_world(dsc_ctx* ctx, int* world, int* rank) {
+    *world = ctx->world;
+    *rank = ctx->rank;
+    return DSC_OK;
+}
+
+}  // extern "C"
+
+// shared with gemm_tcgen05.cu
+extern "C" int dsc_internal_encode_tiled_2d_f32(void* tensor_map, uint64_t base, uint64_t dim0, uint64_t dim1, uint64_t row_stride_bytes,
+                                                uint32_t box0, uint32_t box1) {
+    int rc = load_driver_api();
+    if (rc) return rc;
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t elem[2] = {1, 1};
+    CU_TRY(g_drv.TensorMapEncodeTiled((CUtensorMap*)tensor_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, elem,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    return DSC_OK;
+}
+extern "C" void* dsc_internal_stream(dsc_ctx* ctx) { return (void*)ctx->stream; }
+extern "C" int dsc_internal_set_error(int code, const char* msg) { return set_error(code, "%s", msg); }
