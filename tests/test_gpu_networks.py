@@ -8,26 +8,35 @@ from oracle import run_graph
 
 pytestmark = pytest.mark.gpu
 
-# network, mini-batch, tolerance on every output tensor after one step (relative to the tensor's max |value|).
-# The oracle accumulates sums in float64; the CUDA path in float32 (fixed order), so long reductions
-# (K = m*h*w for conv filter gradients) carry ~sqrt(K)*2^-24 relative error: 1e-5 is the strict-FP32 bar
-# of BASELINE.json, 5e-5 is allowed where K >= 1e5 feeds an Adam step (sign-sensitive near zero gradients).
+# network, mini-batch, tolerance after one step, relative to each tensor's max |value| (BASELINE.json: 1e-5 for
+# strict-FP32 paths).  Every output of the step is checked against the oracle: loss/accuracy sums, Adam's
+# t/m/v state (linear / quadratic in the gradients, so they carry every gradient at full precision) and, for
+# SGD, the updated parameters.  Adam-updated parameters are checked differently, because the first Adam step
+# is theta -= alpha*m/(sqrt(v)+eps) ~ alpha*sign(g): for gradient entries that are cancellation residues
+# (|g| ~ eps) the sign depends on summation order, which no f32 implementation shares with the f64-accumulating
+# oracle (nor with the reference's own sequential order).  So theta is compared (a) against the oracle's Adam
+# formula evaluated on the backend's own m, v, t outputs at 2e-6 -- this pins the Adam arithmetic -- and (b)
+# against the oracle's theta on the well-conditioned entries (|g| > 1e-3 max|g|) at ADAM_THETA_TOL.
+ADAM_THETA_TOL = 2e-4
 CASES = [
     ("linear", 64, 1e-5),
     ("single-layer", 64, 1e-5),
     ("single-layer-dropout", 64, 1e-5),
-    ("conv-net", 16, 5e-5),
-    ("conv-blur-net", 8, 5e-5),
+    ("conv-net", 16, 1e-5),
+    ("conv-blur-net", 8, 1e-5),
     ("relu", 256, 1e-5),
-    ("relu-pe", 256, 2e-5),
-    ("siren", 256, 5e-5),
+    ("relu-pe", 256, 1e-5),
+    ("siren", 256, 1e-5),
     ("multi-hash", 512, 1e-5),
 ]
 
 
+@pytest.mark.parametrize("optimizer", ["adam", "descent"])
 @pytest.mark.parametrize("network,m,tol", CASES, ids=[c[0] for c in CASES])
-def test_one_training_step_matches_oracle(env, network, m, tol):
-    ex = env.example(network, m)
+def test_one_training_step_matches_oracle(env, network, m, tol, optimizer):
+    if optimizer == "descent" and network in ("relu", "relu-pe", "siren", "multi-hash"):
+        pytest.skip("image_fit always trains with Adam (examples/image_fit/main.rs:319)")
+    ex = env.example(network, m, optimizer=optimizer)
     rng = np.random.default_rng(SEED_BASE + len(network))
     params = init_example_params(ex, rng, siren=(network == "siren"))
     params[ex.x.id], params[ex.y.id] = synthetic_batch(ex, rng)
@@ -39,8 +48,29 @@ def test_one_training_step_matches_oracle(env, network, m, tol):
     worst = {}
     for pid, w in want.items():
         worst[env.parameter(pid).name() + "#%d" % pid] = max_rel_err(env.read(env.parameter(pid)), w)
-    bad = {k: v for k, v in worst.items() if not v <= tol}
-    assert not bad, "outputs beyond %g: %s" % (tol, bad)
+    theta = {p.name() + "#%d" % p.id for p in ex.parameters} if optimizer == "adam" else set()
+    bad = {k: v for k, v in worst.items() if k not in theta and not v <= tol}
+    assert not bad, "outputs beyond tolerance: %s (all: %s)" % (bad, worst)
+    if optimizer == "adam":
+        check_adam_update(env, ex, params, want)
+
+
+def check_adam_update(env, ex, params, want):
+    """optimizer.rs:83-97 on the backend's own state; state order is [t, m0, v0, m1, v1, ...] (optimizer.rs:79-95)."""
+    f32 = np.float32
+    beta1, beta2, eps = f32(0.9), f32(0.99 if ex.accuracy_sum is None else 0.999), f32(1e-8)
+    lr = f32(0.02 if ex.accuracy_sum is None else 0.005) * f32(params[ex.learning_rate_scale.id][0])
+    t = f32(env.read_parameter_scalar(ex.optimizer_state[0]))
+    alpha = lr * np.sqrt(f32(1) - np.exp(np.log(beta2) * t, dtype=f32), dtype=f32) / (f32(1) - np.exp(np.log(beta1) * t, dtype=f32))
+    for i, p in enumerate(ex.parameters):
+        m, v = env.read(ex.optimizer_state[1 + 2 * i]), env.read(ex.optimizer_state[2 + 2 * i])
+        expected = params[p.id] - (alpha * m) / (np.sqrt(v) + eps)
+        got = env.read(p)
+        assert max_rel_err(got, expected) <= 2e-6, (p.name(), p.id)
+        g = np.abs(want[ex.optimizer_state[1 + 2 * i].id])
+        ok = g > 1e-3 * g.max()
+        if ok.any():
+            assert max_rel_err(got[ok], want[p.id][ok]) <= ADAM_THETA_TOL, (p.name(), p.id)
 
 
 def test_multi_step_loss_tracks_oracle(env):
