@@ -31,30 +31,91 @@ std::string unum(int64_t v) { return std::to_string(v) + "u"; }
 int64_t pow2_ceil(int64_t v) { int64_t p = 1; while (p < v) p <<= 1; return p; }
 int64_t pow2_floor(int64_t v) { int64_t p = 1; while (p * 2 <= v) p <<= 1; return p; }
 
-// Emits statements that turn the consumer element index `e` (an unsigned expression) into the
+// An index kept symbolically as a sum of non-overlapping mixed-radix fields: value = sum(expr_t * stride_t)
+// with expr_t in [0, range_t) and stride_t * range_t <= stride of the next larger term.  Decoding such a sum
+// into the coordinates of a shape is done field by field whenever the fields line up with the shape's digits,
+// which keeps e.g. the row part (image, y, x) and the column part (fy, fx, channel) of conv2d's im2col index
+// separate, so the compiler hoists each out of the loop over the other.
+struct Term {
+    std::string expr;
+    int64_t stride;
+    int64_t range;
+};
+std::vector<Term> linear_term(const std::string& e, int64_t count) { return {{e, 1, count}}; }
+
+// Emits statements that map a consumer element (given as terms over the chain's output index space) to the
 // producer buffer index, view by view from the consumer side (offset + sum(step*coord),
-// clamped only where the view can leave the axis).  Returns the name of the resulting expression.
-std::string emit_chain(std::ostringstream& os, const ViewChain& chain, const std::string& e, int& uniq, const char* indent = "    ") {
-    std::string cur = e;
+// clamped only where the view can leave the axis).  Returns the resulting index expression.
+std::string emit_chain(std::ostringstream& os, const ViewChain& chain, std::vector<Term> terms, int& uniq, const char* indent = "    ") {
+    auto materialize = [&](const std::vector<Term>& ts) {
+        std::ostringstream sum;
+        bool any = false;
+        for (const auto& t : ts) {
+            if (t.range <= 1 && t.expr == "0") continue;
+            sum << (any ? " + " : "") << "(unsigned)(" << t.expr << ")";
+            if (t.stride != 1) sum << " * " << unum(t.stride);
+            any = true;
+        }
+        return any ? sum.str() : std::string("0u");
+    };
     for (int vi = (int)chain.views.size() - 1; vi >= 0; --vi) {
         const View& v = chain.views[vi];
         const int id = uniq++;
         auto ostr = v.output_shape.strides();
         auto istr = v.input_shape.strides();
-        int64_t lead = 1;  // product of output extents before axis i
+        // 1. coordinates of the needed output axes, term-wise when the fields align with the digits
+        std::vector<std::string> coord(v.output_shape.len());
+        bool aligned = true;
+        for (int i = 0; i < v.output_shape.len() && aligned; ++i) {
+            const auto& m = v.output_mapping[i];
+            if (!(m.is_source && v.output_shape[i] > 1)) continue;
+            const int64_t lo = ostr[i], hi = ostr[i] * v.output_shape[i];
+            std::ostringstream parts;
+            bool any = false;
+            for (const auto& t : terms) {
+                if (t.range <= 1 && t.expr == "0") continue;
+                const int64_t flo = t.stride, fhi = t.stride * t.range;
+                if (fhi <= lo) continue;  // entirely below this digit: no carry because fields do not overlap
+                if (flo >= hi) {
+                    if (flo % hi != 0) aligned = false;  // would leak into this digit
+                    continue;
+                }
+                std::string e;
+                if (flo >= lo && flo % lo == 0 && fhi <= hi) {
+                    e = flo == lo ? t.expr : "(" + t.expr + ") * " + num(flo / lo);
+                } else if (flo <= lo && lo % flo == 0 && (fhi <= hi || hi % flo == 0)) {
+                    e = lo == flo ? "(" + t.expr + ")" : "(" + t.expr + ") / " + num(lo / flo);
+                    if (fhi > hi) e = "(" + e + ") % " + num(v.output_shape[i]);
+                } else {
+                    aligned = false;
+                    break;
+                }
+                parts << (any ? " + " : "") << e;
+                any = true;
+            }
+            coord[i] = any ? parts.str() : "0";
+        }
+        if (!aligned) {
+            os << indent << "const unsigned l" << id << " = " << materialize(terms) << ";\n";
+            int64_t lead = 1;
+            for (int i = 0; i < v.output_shape.len(); ++i) {
+                const auto& m = v.output_mapping[i];
+                if (m.is_source && v.output_shape[i] > 1) {
+                    std::ostringstream e;
+                    e << "l" << id;
+                    if (ostr[i] != 1) e << " / " << unum(ostr[i]);
+                    if (lead != 1) e << " % " << unum(v.output_shape[i]);
+                    coord[i] = e.str();
+                }
+                lead *= v.output_shape[i];
+            }
+        }
         for (int i = 0; i < v.output_shape.len(); ++i) {
             const auto& m = v.output_mapping[i];
-            if (m.is_source && v.output_shape[i] > 1) {
-                os << indent << "const int c" << id << "_" << i << " = (int)(" << cur;
-                if (ostr[i] != 1) os << " / " << unum(ostr[i]);
-                if (lead != 1) os << " % " << unum(v.output_shape[i]);
-                os << ");\n";
-            }
-            lead *= v.output_shape[i];
+            if (m.is_source && v.output_shape[i] > 1) os << indent << "const int c" << id << "_" << i << " = (int)(" << coord[i] << ");\n";
         }
-        std::ostringstream sum;
-        int64_t constant = 0;
-        bool any = false;
+        // 2. one term per input axis
+        std::vector<Term> next;
         for (int a = 0; a < v.input_shape.len(); ++a) {
             std::ostringstream t;
             bool has_terms = false;
@@ -69,23 +130,26 @@ std::string emit_chain(std::ostringstream& os, const ViewChain& chain, const std
             }
             const int64_t off = v.input_offsets[a], len = v.input_shape[a];
             if (!has_terms) {
-                constant += std::min<int64_t>(std::max<int64_t>(off, 0), len - 1) * istr[a];
+                const int64_t fixed = std::min<int64_t>(std::max<int64_t>(off, 0), len - 1);
+                if (fixed != 0) next.push_back({num(fixed), istr[a], len});
                 continue;
             }
             std::string expr = t.str();
             if (off != 0) expr = expr + " + (" + num(off) + ")";
             if (v.input_needs_clamp(a)) expr = "min(max(" + expr + ", 0), " + num(len - 1) + ")";
-            sum << (any ? " + " : "") << "(" << expr << ")";
-            if (istr[a] != 1) sum << "*" << istr[a];
-            any = true;
+            os << indent << "const int a" << id << "_" << a << " = " << expr << ";\n";
+            next.push_back({"a" + num(id) + "_" + num(a), istr[a], len});
         }
-        os << indent << "const unsigned x" << id << " = (unsigned)(";
-        if (any) os << sum.str();
-        if (constant != 0 || !any) os << (any ? " + " : "") << constant;
-        os << ");\n";
-        cur = "x" + num(id);
+        std::sort(next.begin(), next.end(), [](const Term& x, const Term& y) { return x.stride > y.stride; });
+        terms = next;
     }
-    return cur;
+    const int id = uniq++;
+    os << indent << "const unsigned x" << id << " = " << materialize(terms) << ";\n";
+    return "x" + num(id);
+}
+std::string emit_chain(std::ostringstream& os, const ViewChain& chain, const std::string& e, int& uniq, const char* indent = "    ") {
+    if (chain.views.empty()) return e;
+    return emit_chain(os, chain, linear_term(e, chain.output_count), uniq, indent);
 }
 
 double chain_bytes(const Graph& g, const ClusterInput& in) {
@@ -331,80 +395,145 @@ ClusterCode gen_reduce(const Graph& g, const Cluster& c, int ci, const CodegenOp
 }
 
 // ---- matmul (reference: MatMulKernel + kernel_matmul.glsl) ---------------------------------------
-// Strict-FP32 SIMT GEMM, JIT-specialised per shape.  Operands are fetched through their chains
-// directly into k-major shared tiles (zero fill outside M/N/K, kernel.rs:461-487), so the im2col
-// "matrix" of conv2d and every transpose exist only as index arithmetic.  Register tile TMxTN per
-// thread; explicit fmaf (products are accumulated in ascending k inside a split, splits summed in
-// ascending order: SURVEY.md A.6).
+// Strict-FP32 SIMT GEMM, JIT-specialised per shape.  Operands are fetched through their chains into
+// registers, then into double-buffered k-major shared tiles (zero fill outside M/N/K,
+// kernel.rs:461-487), so the im2col "matrix" of conv2d and every transpose exist only as index
+// arithmetic and the next tile's loads overlap the current tile's FMAs.  TMxTN register tile per
+// thread, 128-bit shared loads, explicit fmaf.  Products are accumulated in ascending k inside a
+// split and splits are summed in ascending order.
 
 const char* kMatMulTemplate = R"(
 // {{LABEL}}
 extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, const float* B, float* C, const unsigned* dsc_step) {
     constexpr int BM = {{BM}}, BN = {{BN}}, BK = {{BK}}, TM = {{TM}}, TN = {{TN}}, NT = {{NT}};
+    constexpr int TX = BN / TN, TY = BM / TM, NC = TX * TY;
     constexpr int M = {{M}}, N = {{N}}, K = {{K}}, KC = {{KC}}, BC = {{BC}};
     constexpr int TILES_N = (N + BN - 1) / BN;
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
+    constexpr int AS = BM + 4, BS = BN + 4;
+    constexpr int LA = (BM * BK + NT - 1) / NT, LB = (BK * BN + NT - 1) / NT;
+    __shared__ __align__(16) float As[2][BK * AS];
+    __shared__ __align__(16) float Bs[2][BK * BS];
     const int tid = threadIdx.x;
     const int tile_m = blockIdx.x / TILES_N, tile_n = blockIdx.x % TILES_N;
     const int batch = blockIdx.y, split = blockIdx.z;
     const int m0 = tile_m * BM, n0 = tile_n * BN;
     const int k_begin = split * KC;
     const int k_end = min(K, k_begin + KC);
-    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int tx = tid % TX, ty = tid / TX;
     float acc[TM][TN];
     #pragma unroll
     for (int i = 0; i < TM; ++i)
         #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    float ra[LA], rb[LB];
+    auto load_tile = [&](int k0) {
         #pragma unroll
-        for (int i = tid; i < BM * BK; i += NT) {
+        for (int j = 0; j < LA; ++j) {
+            const int i = tid + j * NT;
             {{A_DECODE}}
             const int gm = m0 + lm, gk = k0 + lk;
             float v = 0.f;
-            if (gm < M && gk < k_end) {
-                const unsigned e = ((unsigned)batch * M + gm) * K + gk;
+            if ((BM * BK % NT == 0 || i < BM * BK) && gm < M && gk < k_end) {
 {{A_CHAIN}}
                 v = A[{{A_IDX}}];
             }
-            As[lk][lm] = v;
+            ra[j] = v;
         }
         #pragma unroll
-        for (int i = tid; i < BK * BN; i += NT) {
+        for (int j = 0; j < LB; ++j) {
+            const int i = tid + j * NT;
             {{B_DECODE}}
             const int gk = k0 + lk, gn = n0 + ln;
             float v = 0.f;
-            if (gn < N && gk < k_end) {
-                const unsigned e = ((unsigned)batch * K + gk) * N + gn;
+            if ((BK * BN % NT == 0 || i < BK * BN) && gn < N && gk < k_end) {
 {{B_CHAIN}}
                 v = B[{{B_IDX}}];
             }
-            Bs[lk][ln] = v;
+            rb[j] = v;
         }
-        __syncthreads();
+    };
+    auto store_tile = [&](int buf) {
         #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            float a[TM], b[TN];
-            #pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
-            #pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
-            #pragma unroll
-            for (int i = 0; i < TM; ++i)
-                #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < LA; ++j) {
+            const int i = tid + j * NT;
+            {{A_DECODE}}
+            if (BM * BK % NT == 0 || i < BM * BK) As[buf][lk * AS + lm] = ra[j];
         }
+        #pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const int i = tid + j * NT;
+            {{B_DECODE}}
+            if (BK * BN % NT == 0 || i < BK * BN) Bs[buf][lk * BS + ln] = rb[j];
+        }
+    };
+    load_tile(k_begin);
+    store_tile(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        const bool more = k0 + BK < k_end;
+        if (more) load_tile(k0 + BK);
+        if (NC == NT || tid < NC) {
+            const float* as = As[buf] + ty * TM;
+            const float* bs = Bs[buf] + tx * TN;
+            #pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                float a[TM], b[TN];
+                if (TM % 4 == 0) {
+                    #pragma unroll
+                    for (int i = 0; i < TM; i += 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(as + kk * AS + i);
+                        a[i] = q.x; a[i + 1] = q.y; a[i + 2] = q.z; a[i + 3] = q.w;
+                    }
+                } else {
+                    #pragma unroll
+                    for (int i = 0; i < TM; ++i) a[i] = as[kk * AS + i];
+                }
+                if (TN % 4 == 0) {
+                    #pragma unroll
+                    for (int j = 0; j < TN; j += 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(bs + kk * BS + j);
+                        b[j] = q.x; b[j + 1] = q.y; b[j + 2] = q.z; b[j + 3] = q.w;
+                    }
+                } else if (TN % 2 == 0) {
+                    #pragma unroll
+                    for (int j = 0; j < TN; j += 2) {
+                        const float2 q = *reinterpret_cast<const float2*>(bs + kk * BS + j);
+                        b[j] = q.x; b[j + 1] = q.y;
+                    }
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < TN; ++j) b[j] = bs[kk * BS + j];
+                }
+                #pragma unroll
+                for (int i = 0; i < TM; ++i)
+                    #pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+        }
+        if (more) store_tile(buf ^ 1);
         __syncthreads();
+        buf ^= 1;
     }
+    if (NC != NT && tid >= NC) return;
     #pragma unroll
     for (int i = 0; i < TM; ++i) {
         const int gm = m0 + ty * TM + i;
         if (gm >= M) continue;
-        #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            const int gn = n0 + tx * TN + j;
-            if (gn < N) C[{{C_INDEX}}] = acc[i][j];
+        const int gn0 = n0 + tx * TN;
+        float* crow = C + {{C_ROW}};
+        if (TN % 4 == 0 && N % 4 == 0) {
+            #pragma unroll
+            for (int j = 0; j < TN; j += 4)
+                if (gn0 + j < N) *reinterpret_cast<float4*>(crow + gn0 + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+        } else if (TN % 2 == 0 && N % 2 == 0) {
+            #pragma unroll
+            for (int j = 0; j < TN; j += 2)
+                if (gn0 + j < N) *reinterpret_cast<float2*>(crow + gn0 + j) = make_float2(acc[i][j], acc[i][j + 1]);
+        } else {
+            #pragma unroll
+            for (int j = 0; j < TN; ++j)
+                if (gn0 + j < N) crow[gn0 + j] = acc[i][j];
         }
     }
 }
@@ -417,25 +546,28 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws, floa
     const unsigned i = blockIdx.x * 256u + threadIdx.x;
     if (i >= COUNT) return;
     float acc = ws[i];
-    #pragma unroll 4
+    #pragma unroll 8
     for (unsigned s = 1; s < S; ++s) acc += ws[s * COUNT + i];
     out0[i] = acc;
 }
 )";
 
-struct GemmTile { int bm, bn, bk, tm, tn; };
+struct GemmTile { int bm, bn, bk, tm, tn, nt; };
 
 GemmTile choose_gemm_tile(int64_t M, int64_t N) {
     GemmTile t;
-    t.bn = N <= 8 ? 8 : N <= 16 ? 16 : N <= 32 ? 32 : 64;
-    t.bm = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
-    t.bk = 16;
-    int per_thread = std::max(1, t.bm * t.bn / 256);
-    t.tn = std::min(4, std::min(per_thread, t.bn / 8));
-    t.tn = std::max(1, t.tn);
-    t.tm = std::max(1, per_thread / t.tn);
-    while (t.tm > 8) { t.tm /= 2; }
-    while (t.bm % t.tm) t.tm /= 2;
+    t.tn = N > 64 ? 8 : N > 16 ? 4 : N > 8 ? 2 : 1;
+    t.bn = (int)std::min<int64_t>(div_round_up(N, t.tn) * t.tn, 128);
+    const int tx = t.bn / t.tn;
+    t.tm = (t.tn == 4 && t.bn <= 32) ? 4 : 8;
+    int ty = std::min(256 / tx, 256 / t.tm);
+    if (M < (int64_t)ty * t.tm) {  // short output: cover M with as few thread rows as possible
+        ty = (int)div_round_up(M, 8);
+        t.tm = (int)div_round_up(M, ty);
+    }
+    t.bm = ty * t.tm;
+    t.nt = (int)div_round_up(ty * tx, 32) * 32;
+    t.bk = (t.bm + t.bn + 8) * 32 * 8 <= 48 * 1024 ? 32 : 16;
     return t;
 }
 
@@ -447,14 +579,20 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     const int64_t r_graph = mm.shape[0];
     const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
     GemmTile t = choose_gemm_tile(M, N);
-    const int nt = (t.bm / t.tm) * (t.bn / t.tn);
     const int64_t tiles = div_round_up(M, t.bm) * div_round_up(N, t.bn) * BC;
+    const int64_t out_count = BC * M * N;
 
     int64_t S, KC;
     if (c.matmul_absorbs_reduce || r_graph == 1) {
-        // the backend owns the K split: enough CTAs to fill the machine, chunks of at least 8 k-tiles
+        // the backend owns the K split (the reference fixes it at ceil(K/1024), op.rs:74): enough CTAs to
+        // fill the machine, at least 4 k-tiles per split, partial-sum traffic well under the operand traffic
+        const int64_t target = (int64_t)opt.sm_count * std::max(2, std::min(8, 1024 / t.nt));
+        const int64_t in_elems = a.chain.addressed_count() + b.chain.addressed_count();
         S = 1;
-        if (tiles < opt.sm_count && K >= 16 * t.bk) S = std::min<int64_t>(div_round_up(2 * opt.sm_count, tiles), K / (8 * t.bk));
+        if (tiles * 2 <= target && K >= 8 * t.bk) {
+            S = std::min<int64_t>(div_round_up(target, tiles), K / (4 * t.bk));
+            S = std::min<int64_t>(S, std::max<int64_t>(1, in_elems / (4 * out_count)));
+        }
         S = std::max<int64_t>(S, 1);
         KC = div_round_up(div_round_up(K, S), t.bk) * t.bk;
         S = div_round_up(K, KC);
@@ -476,28 +614,38 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     };
     const bool a_m_fast = fast_axis(a, M, K);   // A element (m,k): rows = m
     const bool b_k_fast = fast_axis(b, K, N);   // B element (k,n): rows = k
+    // tile element i = tid + j*NT -> (fast coordinate, slow coordinate); written so that the fast coordinate is
+    // visibly independent of j whenever the thread count allows, which lets its index math leave the loops
+    auto decode = [&](const char* x, const char* bx, int bxv, const char* y, const char* by, int byv, bool x_fast) {
+        const char *f = x_fast ? x : y, *bf = x_fast ? bx : by, *s = x_fast ? y : x;
+        const int bfv = x_fast ? bxv : byv;
+        std::ostringstream d;
+        if (t.nt % bfv == 0) d << "const int " << f << " = tid % " << bf << ", " << s << " = tid / " << bf << " + j * (NT / " << bf << ");";
+        else if (bfv % t.nt == 0) d << "const int " << f << " = tid + (j % (" << bf << " / NT)) * NT, " << s << " = j / (" << bf << " / NT);";
+        else d << "const int " << f << " = i % " << bf << ", " << s << " = i / " << bf << ";";
+        return d.str();
+    };
     int uniq = 0;
     std::ostringstream ca, cb;
-    std::string ia = emit_chain(ca, a.chain, "e", uniq, "                ");
-    std::string ib = emit_chain(cb, b.chain, "e", uniq, "                ");
+    std::string ia = emit_chain(ca, a.chain, {{"batch", M * K, BC}, {"gm", K, M}, {"gk", 1, K}}, uniq, "                ");
+    std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, BC}, {"gk", N, K}, {"gn", 1, N}}, uniq, "                ");
     const std::string name = "k" + num(ci);
-    std::string c_index = rows_mode ? "(((unsigned)split * M + gm) * BC + batch) * N + gn" : "(((unsigned)split * BC + batch) * M + gm) * N + gn";
+    std::string c_row = rows_mode ? "(((size_t)split * M + gm) * BC + batch) * N" : "(((size_t)split * BC + batch) * M + gm) * N";
     ClusterCode code;
     code.source = subst(kMatMulTemplate,
-                        {{"LABEL", c.label}, {"NAME", name}, {"NT", num(nt)}, {"BM", num(t.bm)}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"TM", num(t.tm)},
+                        {{"LABEL", c.label}, {"NAME", name}, {"NT", num(t.nt)}, {"BM", num(t.bm)}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"TM", num(t.tm)},
                          {"TN", num(t.tn)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"KC", num(KC)}, {"BC", num(BC)},
-                         {"A_DECODE", a_m_fast ? "const int lm = i % BM, lk = i / BM;" : "const int lk = i % BK, lm = i / BK;"},
-                         {"B_DECODE", b_k_fast ? "const int lk = i % BK, ln = i / BK;" : "const int ln = i % BN, lk = i / BN;"},
-                         {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_INDEX", c_index}});
+                         {"A_DECODE", decode("lm", "BM", t.bm, "lk", "BK", t.bk, a_m_fast)},
+                         {"B_DECODE", decode("ln", "BN", t.bn, "lk", "BK", t.bk, !b_k_fast)},
+                         {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
     KernelLaunch l;
     l.entry = name;
     l.grid_x = (uint32_t)(div_round_up(M, t.bm) * div_round_up(N, t.bn));
     l.grid_y = (uint32_t)BC;
     l.grid_z = (uint32_t)S;
-    l.block = nt;
+    l.block = t.nt;
     l.label = c.label;
     l.cluster = ci;
-    const int64_t out_count = BC * M * N;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
     if (via_scratch) l.args.push_back({KernelArg::Scratch, -1, 0});
     else l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});

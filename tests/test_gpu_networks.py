@@ -15,9 +15,11 @@ pytestmark = pytest.mark.gpu
 # is theta -= alpha*m/(sqrt(v)+eps) ~ alpha*sign(g): for gradient entries that are cancellation residues
 # (|g| ~ eps) the sign depends on summation order, which no f32 implementation shares with the f64-accumulating
 # oracle (nor with the reference's own sequential order).  So theta is compared (a) against the oracle's Adam
-# formula evaluated on the backend's own m, v, t outputs at 2e-6 -- this pins the Adam arithmetic -- and (b)
+# formula evaluated on the backend's own m, v, t outputs at ADAM_FORMULA_TOL -- this pins the Adam arithmetic; the
+# bias correction 1 - exp(ln(beta2)*t) cancels to 1e-3 at t = 1, so one ulp of expf is 6e-5 of alpha -- and (b)
 # against the oracle's theta on the well-conditioned entries (|g| > 1e-3 max|g|) at ADAM_THETA_TOL.
 ADAM_THETA_TOL = 2e-4
+ADAM_FORMULA_TOL = 1e-4
 CASES = [
     ("linear", 64, 1e-5),
     ("single-layer", 64, 1e-5),
@@ -66,7 +68,7 @@ def check_adam_update(env, ex, params, want):
         m, v = env.read(ex.optimizer_state[1 + 2 * i]), env.read(ex.optimizer_state[2 + 2 * i])
         expected = params[p.id] - (alpha * m) / (np.sqrt(v) + eps)
         got = env.read(p)
-        assert max_rel_err(got, expected) <= 2e-6, (p.name(), p.id)
+        assert max_rel_err(got - params[p.id], expected - params[p.id]) <= ADAM_FORMULA_TOL, (p.name(), p.id)
         g = np.abs(want[ex.optimizer_state[1 + 2 * i].id])
         ok = g > 1e-3 * g.max()
         if ok.any():
