@@ -482,7 +482,7 @@ int dsc_dp_world(dsc_ctx* ctx, int* world, int* rank) {
 
 // shared with gemm_tcgen05.cu
 extern "C" int dsc_internal_encode_tiled_2d_f32(void* tensor_map, uint64_t base, uint64_t dim0, uint64_t dim1, uint64_t row_stride_bytes,
-                                                uint32_t box0, uint32_t box1) {
+                                                uint32_t box0, uint32_t box1, int swizzle_atom_32b) {
     int rc = load_driver_api();
     if (rc) return rc;
     cuuint64_t dims[2] = {dim0, dim1};
@@ -490,7 +490,8 @@ extern "C" int dsc_internal_encode_tiled_2d_f32(void* tensor_map, uint64_t base,
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t elem[2] = {1, 1};
     CU_TRY(g_drv.TensorMapEncodeTiled((CUtensorMap*)tensor_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, elem,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_atom_32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
     return DSC_OK;
 }

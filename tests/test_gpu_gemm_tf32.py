@@ -1,0 +1,48 @@
+"""dsc_gemm_tf32 (TMA + tcgen05 + TMEM) against an exact float64 product, all four operand layouts.
+Tolerance: TF32 keeps 10 explicit mantissa bits, so every product carries at most 2^-10 relative error
+(2^-11 per operand); FP32 accumulation adds ~K*2^-24.  |err| <= 2^-10 * (|A|.|B|) elementwise."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def device_gemm(d, env, a_store, b_store, m, n, k, a_is_mk, b_is_kn):
+    lib, ctx = d.lib, env.ctx()
+    bufs = []
+    for arr in (a_store, b_store, np.zeros((m, n), np.float32)):
+        h = ctypes.c_uint64(0)
+        assert lib.dsc_alloc(ctx, ctypes.c_size_t(arr.nbytes), ctypes.byref(h)) == 0
+        assert lib.dsc_upload(ctx, h, ctypes.c_size_t(0), arr.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arr.nbytes), ctypes.c_size_t(0), 0) == 0
+        bufs.append(h)
+    rc = lib.dsc_gemm_tf32(ctx, bufs[0], bufs[1], bufs[2], ctypes.c_int64(m), ctypes.c_int64(n), ctypes.c_int64(k), a_is_mk, b_is_kn)
+    assert rc == 0, lib.dsc_last_error().decode()
+    out = np.empty((m, n), np.float32)
+    assert lib.dsc_download(ctx, bufs[2], ctypes.c_size_t(0), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.nbytes)) == 0, lib.dsc_last_error().decode()
+    for h in bufs:
+        lib.dsc_free(ctx, h)
+    return out
+
+
+@pytest.mark.parametrize("a_is_mk", [1, 0])
+@pytest.mark.parametrize("b_is_kn", [0, 1])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 32), (256, 384, 160), (1024, 256, 4096)])
+def test_gemm_tf32_layouts(built_library, env, m, n, k, a_is_mk, b_is_kn):
+    rng = np.random.default_rng(m + 3 * n + 7 * k + 2 * a_is_mk + b_is_kn)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    b = rng.standard_normal((k, n)).astype(np.float32)
+    a_store = np.ascontiguousarray(a if a_is_mk else a.T)
+    b_store = np.ascontiguousarray(b if b_is_kn else b.T)
+    got = device_gemm(built_library, env, a_store, b_store, m, n, k, a_is_mk, b_is_kn)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    bound = 2.0 ** -10 * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)) + 1e-6
+    err = np.abs(got - exact)
+    assert (err <= bound).all(), "max err/bound %.3g at %s" % ((err / bound).max(), np.unravel_index((err / bound).argmax(), err.shape))
+
+
+def test_gemm_tf32_rejects_unaligned(built_library, env):
+    lib, ctx = built_library.lib, env.ctx()
+    rc = lib.dsc_gemm_tf32(ctx, ctypes.c_uint64(256), ctypes.c_uint64(256), ctypes.c_uint64(256), ctypes.c_int64(100), ctypes.c_int64(128), ctypes.c_int64(32), 1, 1)
+    assert rc == 5  # DSC_ERR_UNSUPPORTED: the caller falls back to the JIT SIMT GEMM
