@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--workload", default="conv-net")
     ap.add_argument("--mini-batch", type=int, default=0, help="per-GPU mini-batch (0 = workload default)")
     ap.add_argument("--optimizer", default="adam")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "strict"],
+                    help="tf32: plain dense GEMMs on tcgen05 tensor cores (TF32 operands, FP32 accumulate); strict: all FP32 SIMT")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-kernel event timings here")
     args = ap.parse_args()
@@ -184,6 +186,7 @@ def main():
         uid = [d.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         env.init_data_parallel(world, rank, uid[0])
+    env.set_tf32(args.precision == "tf32")
     ex = env.example(args.workload, m, optimizer=args.optimizer)
     rng = np.random.default_rng(0x5EED5EED + 2)       # same initial weights on every rank
     params, _, _ = make_inputs(ex, rng, args.workload)
@@ -290,10 +293,13 @@ def main():
 
     out = {
         "metric": "train samples/s", "value": global_batch / (ms_per_step * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 storage; tf32 tensor-core operands on dense GEMMs" if args.precision == "tf32" else "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "mini_batch_per_gpu": m, "global_batch": global_batch, "optimizer": args.optimizer,
-                   "parallelism": "dp%d" % world, "gemm_path": "strict-fp32 simt", "cuda_graph": True,
+                   "parallelism": "dp%d" % world,
+                   "gemm_path": "dense: tcgen05 tf32 (fp32 accumulate); view-chain/conv GEMMs: strict-fp32 simt" if args.precision == "tf32" else "strict-fp32 simt",
+                   "cuda_graph": True,
                    "l2_policy": "working set per step (%.0f MB arena) exceeds the 126 MB L2" % (stats["arena_bytes"] / 1e6)
                    if stats["arena_bytes"] > 126e6 else "working set %.0f MB fits L2; no flush" % (stats["arena_bytes"] / 1e6)},
         "e2e": {"value": global_batch / (e2e_ms / args.steps * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(x.nbytes + y.nbytes),

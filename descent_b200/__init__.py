@@ -132,7 +132,7 @@ class Environment:
         self.device = device
 
     def close(self):
-        if self._h:
+        if getattr(self, "_h", None):
             lib.dsc_env_destroy(self._h)
             self._h = None
 
@@ -216,6 +216,10 @@ class Environment:
 
     def set_options(self, use_cuda_graph=True, profile_runs=False):
         _check(lib.dsc_env_set_options(self._h, int(use_cuda_graph), int(profile_runs)))
+
+    def set_tf32(self, on):
+        """Tensor-core (tcgen05, TF32 operands, FP32 accumulate) path for plain dense MatMuls; default off = strict FP32."""
+        _check(lib.dsc_env_set_tf32(self._h, int(on)))
 
     def print_timings(self, label):
         _check(lib.dsc_env_print_timings(self._h, label.encode()))

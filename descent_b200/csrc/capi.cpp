@@ -149,6 +149,10 @@ int dsc_env_set_options(dsc_env* env, int use_cuda_graph, int profile_runs) {
     env->env->set_profile_runs(profile_runs != 0);
     return DSC_OK;
 }
+int dsc_env_set_tf32(dsc_env* env, int on) {
+    env->env->set_tf32(on != 0);
+    return DSC_OK;
+}
 int dsc_env_print_timings(dsc_env* env, const char* label) { return guarded([&] { env->env->print_timings(label); }); }
 int dsc_env_init_data_parallel(dsc_env* env, int world, int rank, const void* id) {
     return guarded([&] { env->env->init_data_parallel(world, rank, id); });

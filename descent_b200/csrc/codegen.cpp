@@ -578,9 +578,41 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     const int64_t BC = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
     const int64_t r_graph = mm.shape[0];
     const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
+    const int64_t out_count = BC * M * N;
+
+    // Plain dense operands (row-major or transposed whole buffers) take the TMA + tcgen05 TF32 kernel when the
+    // environment allows reduced operand precision; everything else stays on the strict-FP32 JIT path below.
+    if (opt.use_tf32 && BC == 1 && (c.matmul_absorbs_reduce || r_graph == 1) && M * N >= 128 * 128 && K >= 32) {
+        auto plain = [&](const ClusterInput& in, int64_t rows, int64_t cols, bool* row_major) {
+            if (in.chain.input_count != rows * cols || in.chain.views.size() > 1) return false;
+            if (!in.chain.views.empty() && in.chain.views[0].any_clamp()) return false;
+            if (eval_chain(in.chain, 0) != 0) return false;
+            const int64_t sr = eval_chain(in.chain, cols), sc = eval_chain(in.chain, 1);
+            if (sr == cols && sc == 1) { *row_major = true; return true; }
+            if (sr == 1 && sc == rows) { *row_major = false; return true; }
+            return false;
+        };
+        bool a_row_major = true, b_row_major = true;
+        if (plain(a, M, K, &a_row_major) && plain(b, K, N, &b_row_major) && (a_row_major ? K : M) % 4 == 0 && (b_row_major ? N : K) % 4 == 0) {
+            ClusterCode code;
+            KernelLaunch l;
+            l.kind = KernelLaunch::TensorGemm;
+            l.entry = "dsc_gemm_tf32";
+            l.label = "TensorCore" + c.label;
+            l.cluster = ci;
+            l.gemm_m = M; l.gemm_n = N; l.gemm_k = K;
+            l.gemm_a_is_mk = a_row_major;
+            l.gemm_b_is_kn = b_row_major;
+            l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+            l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)out_count;
+            l.flops = 2.0 * (double)M * (double)N * (double)K;
+            code.launches.push_back(l);
+            return code;
+        }
+    }
+
     GemmTile t = choose_gemm_tile(M, N);
     const int64_t tiles = div_round_up(M, t.bm) * div_round_up(N, t.bn) * BC;
-    const int64_t out_count = BC * M * N;
 
     int64_t S, KC;
     if (c.matmul_absorbs_reduce || r_graph == 1) {

@@ -15,11 +15,13 @@ struct KernelArg {
 };
 
 struct KernelLaunch {
-    enum Kind { Kernel, ZeroScratch, AllReduce } kind = Kernel;
+    enum Kind { Kernel, ZeroScratch, AllReduce, TensorGemm } kind = Kernel;
     std::string entry;
     uint32_t grid_x = 1, grid_y = 1, grid_z = 1, block = 256, smem = 0;
     std::vector<KernelArg> args;
     int64_t zero_offset = 0, zero_bytes = 0;  // ZeroScratch
+    int64_t gemm_m = 0, gemm_n = 0, gemm_k = 0;  // TensorGemm: args = {A, B, C}
+    bool gemm_a_is_mk = true, gemm_b_is_kn = true;
     std::string label;
     int cluster = -1;
     double algorithmic_bytes = 0;  // 4*(sum of min(source, addressed) input elements + outputs)
@@ -35,6 +37,7 @@ struct ClusterCode {
 struct CodegenOptions {
     int sm_count = 148;
     int dp_rank = 0;
+    bool use_tf32 = false;  // plain dense MatMuls go to the tcgen05 TF32 kernel (dsc_gemm_tf32)
 };
 
 std::string kernel_prelude();

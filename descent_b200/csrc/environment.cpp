@@ -90,6 +90,8 @@ struct ResolvedLaunch {
     std::string label, entry;
     int cluster = -1;
     double algorithmic_bytes = 0, flops = 0;
+    int64_t gemm_m = 0, gemm_n = 0, gemm_k = 0;
+    bool gemm_a_is_mk = true, gemm_b_is_kn = true;
 };
 
 struct Environment::GraphExec {
@@ -228,6 +230,7 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
     CodegenOptions opt;
     opt.sm_count = sm_count_;
     opt.dp_rank = dp_.rank;
+    opt.use_tf32 = use_tf32_;
     std::vector<ClusterCode> codes;
     exec.source = generate_graph_source(graph, opt, &codes);
 
@@ -384,6 +387,13 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
                 r.ptr = exec.arena;
                 r.bytes = (size_t)(bucket_bytes / 4);
                 r.label = "AllReduce bucket [" + std::to_string(bucket_bytes / 4) + "]";
+            } else if (l.kind == KernelLaunch::TensorGemm) {
+                for (const auto& a : l.args) r.buffers.push_back(device_address(a.node_id));
+                r.gemm_m = l.gemm_m; r.gemm_n = l.gemm_n; r.gemm_k = l.gemm_k;
+                r.gemm_a_is_mk = l.gemm_a_is_mk; r.gemm_b_is_kn = l.gemm_b_is_kn;
+                exec.stats.kernel_launches += 1;
+                exec.stats.algorithmic_bytes += l.algorithmic_bytes;
+                exec.stats.flops += l.flops;
             } else {
                 check(dsc_module_get_kernel(exec.module, l.entry.c_str(), &r.kernel));
                 r.gx = l.grid_x; r.gy = l.grid_y; r.gz = l.grid_z; r.block = l.block; r.smem = l.smem;
@@ -419,6 +429,8 @@ void Environment::launch_all(GraphExec& exec, std::vector<float>* per_launch_ms)
         else if (r.is_fill) check(dsc_fill_u32(ctx_, r.ptr, 0, r.fill_bits, r.bytes / 4));
         else if (r.kind == KernelLaunch::ZeroScratch) check(dsc_fill_u32(ctx_, r.ptr, 0, 0, r.bytes / 4));
         else if (r.kind == KernelLaunch::AllReduce) check(dsc_dp_allreduce_sum_f32(ctx_, r.ptr, r.bytes));
+        else if (r.kind == KernelLaunch::TensorGemm)
+            check(dsc_gemm_tf32(ctx_, r.buffers[0], r.buffers[1], r.buffers[2], r.gemm_m, r.gemm_n, r.gemm_k, r.gemm_a_is_mk, r.gemm_b_is_kn));
         else check(dsc_launch(ctx_, r.kernel, r.gx, r.gy, r.gz, r.block, r.smem, r.buffers.data(), (int)r.buffers.size()));
         if (per_launch_ms) check(dsc_event_record(ctx_, events[i + 1]));
     }
@@ -487,6 +499,7 @@ std::string Environment::kernel_source(const Graph& graph) {
     CodegenOptions opt;
     opt.sm_count = sm_count_;
     opt.dp_rank = dp_.rank;
+    opt.use_tf32 = use_tf32_;
     return generate_graph_source(graph, opt, nullptr);
 }
 

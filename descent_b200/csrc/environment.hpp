@@ -83,6 +83,9 @@ public:
     // --- backend controls (no counterpart in the reference) ---
     void set_use_cuda_graph(bool on) { use_cuda_graph_ = on; }
     void set_profile_runs(bool on) { profile_runs_ = on; }  // time every kernel of every run with events
+    // false (default): every GEMM is strict FP32 (SIMT).  true: plain dense MatMuls of graphs prepared afterwards run
+    // on the tensor cores with TF32 operands and FP32 accumulation (BASELINE.json north_star (b)).
+    void set_tf32(bool on) { use_tf32_ = on; }
     void init_data_parallel(int world, int rank, const void* nccl_unique_id128);
     void set_data_parallel_for_tracing(int world, int rank) {  // host-only environments: rank-specific graphs without NCCL
         DSC_CHECK(ctx_ == nullptr, "use init_data_parallel on a device environment");
@@ -110,6 +113,7 @@ private:
     DataParallel dp_;
     bool use_cuda_graph_ = true;
     bool profile_runs_ = false;
+    bool use_tf32_ = false;
     std::vector<std::pair<std::string, double>> timing_totals_;  // label -> accumulated ms
     int timing_runs_ = 0;
     std::vector<std::shared_ptr<void>> live_execs_;

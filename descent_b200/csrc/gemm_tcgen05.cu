@@ -116,7 +116,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     Storage& s = *reinterpret_cast<Storage*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int tiles_m = m / BM, tiles_n = n / BN, num_tiles = tiles_m * tiles_n, k_blocks = k / BK;
+    const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN, num_tiles = tiles_m * tiles_n, k_blocks = (k + BK - 1) / BK;  // TMA zero-fills out-of-range boxes
     constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 4;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
 
@@ -205,9 +205,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&s.tmem_full[acc_stage], acc_phase);
             tcgen05_fence_after();
-            float* row = c + (size_t)(m0 + quad * 32 + lane) * n + n0;
+            const int grow = m0 + quad * 32 + lane;
+            float* row = c + (size_t)grow * n + n0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < BN && n0 + c0 < n; c0 += 32) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_stage * BN + c0;
                 asm volatile(
@@ -220,10 +221,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                       "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (grow < m) {
+                    if ((n & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(row + c0 + j) =
-                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        for (int j = 0; j < 32; j += 4)
+                            if (n0 + c0 + j < n)
+                                *reinterpret_cast<float4*>(row + c0 + j) =
+                                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + c0 + j < n) row[c0 + j] = __uint_as_float(v[j]);
+                    }
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -245,7 +255,7 @@ int launch(dsc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, float* c,
     const int smem = (int)sizeof(SharedStorage<BN, STAGES>) + 1024;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return dsc_internal_set_error(DSC_ERR_CUDA, cudaGetErrorString(e));
-    const int tiles = (m / BM) * (n / BN);
+    const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
     const int grid = tiles < sm_count ? tiles : sm_count;
     kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)dsc_internal_stream(ctx)>>>(ma, mb, c, m, n, k);
     e = cudaGetLastError();
@@ -256,8 +266,11 @@ int launch(dsc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, float* c,
 }  // namespace
 
 extern "C" int dsc_gemm_tf32(dsc_ctx* ctx, uint64_t a, uint64_t b, uint64_t c, int64_t m, int64_t n, int64_t k, int a_is_mk, int b_is_kn) {
-    if (m <= 0 || n <= 0 || k <= 0 || m % BM != 0 || n % 128 != 0 || k % BK != 0 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX)
-        return dsc_internal_set_error(DSC_ERR_UNSUPPORTED, "dsc_gemm_tf32 needs M % 128 == 0, N % 128 == 0, K % 32 == 0");
+    if (m <= 0 || n <= 0 || k <= 0 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX)
+        return dsc_internal_set_error(DSC_ERR_UNSUPPORTED, "dsc_gemm_tf32: bad shape");
+    // TMA needs 16-byte row pitches: the contiguous extent of each operand must be a multiple of 4 floats
+    if ((a_is_mk ? k : m) % 4 != 0 || (b_is_kn ? n : k) % 4 != 0)
+        return dsc_internal_set_error(DSC_ERR_UNSUPPORTED, "dsc_gemm_tf32 needs the contiguous extent of A and of B to be a multiple of 4");
     if ((a | b | c) & 15) return dsc_internal_set_error(DSC_ERR_UNSUPPORTED, "dsc_gemm_tf32 needs 16-byte aligned operands");
     int device = 0, sm_count = 148;
     dsc_ctx_device(ctx, &device);

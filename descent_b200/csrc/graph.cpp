@@ -179,6 +179,7 @@ Graph::Graph(SharedParameters parameters, const OpGraph& ops, DataParallel dp)
     simplify_arithmetic();
     eliminate_common_subgraphs();
     eliminate_dead_code();
+    hoist_all_reduce_views();
     build_clusters();
 }
 
@@ -302,6 +303,27 @@ void Graph::eliminate_common_subgraphs() {
             ops_.remove_node(id);
         } else {
             bucket.push_back(id);
+        }
+    }
+}
+
+// A cross-rank sum is elementwise, so it commutes with any view: all-reduce the producer's buffer as it is
+// (e.g. the raw output of a filter-gradient GEMM) and let the consumers read the result through the view.
+void Graph::hoist_all_reduce_views() {
+    auto cons = ops_.consumers();
+    for (int id = 0; id < (int)ops_.nodes.size(); ++id) {
+        OpNode& node = ops_.nodes[id];
+        if (!node.alive || node.op.kind != OpKind::AllReduce || node.in[0].chain.is_identity()) continue;
+        const ViewChain view = node.in[0].chain;
+        const Shape src_shape = ops_.nodes[node.in[0].src].shape;
+        node.shape = src_shape;
+        node.in[0].chain = ViewChain::identity(src_shape.element_count());
+        node.in[0].arg_shape = src_shape;
+        for (auto [dst, k] : cons[id]) {
+            OpEdge& e = ops_.nodes[dst].in[k];
+            ViewChain chain = view;
+            chain.append(e.chain);
+            e.chain = chain;
         }
     }
 }

@@ -81,6 +81,7 @@ private:
     void eliminate_moves();
     void simplify_arithmetic();
     void eliminate_common_subgraphs();
+    void hoist_all_reduce_views();
     void build_clusters();
     void build_per_element_program(Cluster& c);
 

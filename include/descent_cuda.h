@@ -100,8 +100,9 @@ int dsc_sync(dsc_ctx* ctx);
  * operands, kernel.rs:385-557): C[M,N] (row-major, ldc=N) = A * B with FP32 storage, TF32 operands and
  * FP32 accumulation in TMEM.  a_is_mk != 0: A is row-major [M,K]; else A is stored [K,M] (i.e. the
  * transpose view the reference's dW = a^T * dc uses, array.rs:875).  b_is_kn != 0: B is row-major
- * [K,N]; else B is stored [N,K].  Requirements: M,N,K multiples of 128/128/32 resp. -> otherwise
- * DSC_ERR_UNSUPPORTED and the caller uses the JIT SIMT path. */
+ * [K,N]; else B is stored [N,K].  Any M, N, K (edge tiles are zero-filled by TMA and masked in the
+ * epilogue); the contiguous extent of A and of B must be a multiple of 4 floats and all three buffers
+ * 16-byte aligned, otherwise DSC_ERR_UNSUPPORTED and the caller uses the JIT strict-FP32 path. */
 int dsc_gemm_tf32(dsc_ctx* ctx, uint64_t a, uint64_t b, uint64_t c, int64_t m, int64_t n, int64_t k, int a_is_mk, int b_is_kn);
 
 /* Data parallel (new): one NCCL communicator per context/rank. */

@@ -1,0 +1,67 @@
+"""Rank body for test_two_gpu_data_parallel_matches_single_gpu (launched by torchrun)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from helpers import init_example_params, max_rel_err, synthetic_batch
+    workload = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import descent_b200 as d
+    m = 16
+    # reference run: one GPU, full batch
+    ref_env = d.Environment(local)
+    ref = ref_env.example(workload, m)
+    rng = np.random.default_rng(77)
+    params = init_example_params(ref, rng)
+    batches = [synthetic_batch(ref, rng) for _ in range(3)]
+    seeds = [int(s) for s in rng.integers(0, 2 ** 32, 3)]
+    for pid, v in params.items():
+        ref_env.write(ref_env.parameter(pid), v)
+    for (x, y), s in zip(batches, seeds):
+        ref_env.write(ref.x, x)
+        ref_env.write(ref.y, y)
+        ref_env.run(ref.train_graph, s)
+    want = [ref_env.read(p) for p in ref.parameters]
+    want_loss = ref_env.read_parameter_scalar(ref.loss_sum)
+    # data-parallel run
+    env = d.Environment(local)
+    uid = [d.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    env.init_data_parallel(world, rank, uid[0])
+    ex = env.example(workload, m // world)
+    for p_ref, p in zip(ref.parameters + ref.optimizer_state + [ref.loss_sum, ref.accuracy_sum, ref.learning_rate_scale],
+                        ex.parameters + ex.optimizer_state + [ex.loss_sum, ex.accuracy_sum, ex.learning_rate_scale]):
+        env.write(p, params[p_ref.id])
+    lo, hi = rank * m // world, (rank + 1) * m // world
+    for (x, y), s in zip(batches, seeds):
+        env.write(ex.x, x[lo:hi])
+        env.write(ex.y, y[lo:hi])
+        env.run(ex.train_graph, s)
+    got = [env.read(p) for p in ex.parameters]
+    loss = torch.tensor([env.read_parameter_scalar(ex.loss_sum)], device="cuda")
+    dist.all_reduce(loss)
+    worst = max(max_rel_err(g, w) for g, w in zip(got, want))
+    ok = worst <= 1e-3 and abs(float(loss.item()) - want_loss) <= 1e-4 * abs(want_loss)
+    flags = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("worst parameter deviation %.3g, loss %g vs %g" % (worst, float(loss.item()), want_loss))
+        print("DP_OK" if flags.item() == 1.0 else "DP_MISMATCH")
+    env.close()
+    ref_env.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
