@@ -250,7 +250,7 @@ def main():
     e2e_ms = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    profile = env.profile(ex.train_graph, 1, 5) if rank == 0 else None
+    profile = env.profile(ex.train_graph, 1, 5)  # every rank: the step contains the gradient all-reduce
     barrier()
     if rank != 0:
         env.close()

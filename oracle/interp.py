@@ -139,13 +139,24 @@ def _reduce(kind, a, arg_shape, axis):
     return np.sum(x.astype(np.float64), axis=axis, keepdims=True).astype(F32).reshape(-1)  # kernel.rs:606,619
 
 
-def _matmul(a, b, a_shape, b_shape, out_shape, mode):
+def tf32_operand(x, rounding):
+    """FP32 -> TF32 operand as the tensor core sees it: 10 explicit mantissa bits.  `rounding`: "trunc" drops the
+    low 13 bits, "rna" rounds to nearest (ties away).  Used only when a test asks for the TF32-emulating oracle."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    if rounding == "rna":
+        u = u + np.uint32(0x1000)
+    return (u & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _matmul(a, b, a_shape, b_shape, out_shape, mode, tf32=None):
     """array.rs:492-520, kernel.rs:385-557: [r, b, m, n] (Batches) or [r, m, b, n] (Rows); chunk c covers
     k in [c*chunk, (c+1)*chunk) with chunk = ceil(ceil(K/16)/r)*16 (kernel.rs:436)."""
     bc, m, k = a_shape
     _, _, n = b_shape
     r = out_shape[0]
     chunk = -(-(-(-k // 16)) // r) * 16
+    if tf32:
+        a, b = tf32_operand(a, tf32), tf32_operand(b, tf32)
     A = a.reshape(a_shape).astype(np.float64)
     B = b.reshape(b_shape).astype(np.float64)
     out = np.zeros((r, bc, m, n), dtype=F32)
@@ -201,8 +212,8 @@ def _scatter_add(acc, values, idx_bits, shape, values_shape, axis):
 
 
 class _Interp:
-    def __init__(self, graph, params, rand_seed, dp_rank):
-        self.graph, self.params, self.seed, self.rank = graph, params, rand_seed, dp_rank
+    def __init__(self, graph, params, rand_seed, dp_rank, tf32=None):
+        self.graph, self.params, self.seed, self.rank, self.tf32 = graph, params, rand_seed, dp_rank, tf32
         self.nodes = graph["nodes"]
         self.by_id = {n["id"]: n for n in self.nodes}
         self.values = {}
@@ -245,7 +256,8 @@ class _Interp:
         if op == "Reduce":
             return _reduce(node["kind"], self.arg(node, 0), node["args"][0]["arg_shape"], node["axis"])
         if op == "MatMul":
-            return _matmul(self.arg(node, 0), self.arg(node, 1), node["args"][0]["arg_shape"], node["args"][1]["arg_shape"], node["shape"], node["mode"])
+            return _matmul(self.arg(node, 0), self.arg(node, 1), node["args"][0]["arg_shape"], node["args"][1]["arg_shape"], node["shape"], node["mode"],
+                           self.tf32)
         if op == "Unpad":
             return _unpad(self.arg(node, 0), node["args"][0]["arg_shape"], node["axis"], node["pad"])
         if op == "WindowsToImage":
@@ -271,16 +283,17 @@ def _live_nodes(graph):
     return live
 
 
-def run_graph(graph, params, rand_seed=0):
+def run_graph(graph, params, rand_seed=0, tf32=None):
     """Evaluate one run of `graph` (Environment::run, environment.rs:326-516).  `params`: {parameter id:
-    array}.  Returns {parameter id: new value} for every Output."""
-    return run_graph_data_parallel([graph], [params], rand_seed)[0]
+    array}.  Returns {parameter id: new value} for every Output.  `tf32` ("trunc" / "rna"): emulate TF32
+    operand precision in every MatMul (for checking the tensor-core path); default None = strict FP32."""
+    return run_graph_data_parallel([graph], [params], rand_seed, tf32)[0]
 
 
-def run_graph_data_parallel(graphs, params_per_rank, rand_seed=0):
+def run_graph_data_parallel(graphs, params_per_rank, rand_seed=0, tf32=None):
     """Lock-step evaluation of one graph per rank; AllReduce nodes sum their input over ranks
     (float64, rounded once).  With a single rank AllReduce is the identity."""
-    interps = [_Interp(g, p, rand_seed, r) for r, (g, p) in enumerate(zip(graphs, params_per_rank))]
+    interps = [_Interp(g, p, rand_seed, r, tf32) for r, (g, p) in enumerate(zip(graphs, params_per_rank))]
     live = _live_nodes(graphs[0])
     for pos, node0 in enumerate(graphs[0]["nodes"]):
         if node0["id"] not in live:

@@ -46,3 +46,22 @@ def test_gemm_tf32_rejects_unaligned(built_library, env):
     lib, ctx = built_library.lib, env.ctx()
     rc = lib.dsc_gemm_tf32(ctx, ctypes.c_uint64(256), ctypes.c_uint64(256), ctypes.c_uint64(256), ctypes.c_int64(100), ctypes.c_int64(128), ctypes.c_int64(30), 1, 1)
     assert rc == 5  # DSC_ERR_UNSUPPORTED: the caller falls back to the JIT SIMT GEMM
+
+
+def test_tf32_operand_rounding_mode(built_library, env, capsys):
+    """Which FP32 -> TF32 conversion does tcgen05 kind::tf32 apply to its shared-memory operands?  The oracle's TF32
+    emulation (oracle.interp.tf32_operand) must use the same one; asserted: truncation matches to FP32 accumulation noise."""
+    from oracle.interp import tf32_operand
+    m, n, k = 256, 256, 512
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    b = rng.standard_normal((k, n)).astype(np.float32)
+    got = device_gemm(built_library, env, a, np.ascontiguousarray(b.T), m, n, k, 1, 0)
+    errs = {}
+    for mode in ("trunc", "rna"):
+        exact = tf32_operand(a, mode).astype(np.float64) @ tf32_operand(b, mode).astype(np.float64)
+        errs[mode] = float(np.abs(got - exact).max() / np.abs(exact).max())
+    with capsys.disabled():
+        print("\ntf32 operand conversion: max rel err vs truncation %.3g, vs round-to-nearest-away %.3g" % (errs["trunc"], errs["rna"]))
+    assert min(errs.values()) < 5e-6, errs
+    assert errs["trunc"] < errs["rna"], errs
