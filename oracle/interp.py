@@ -219,6 +219,14 @@ class _Interp:
         self.values = {}
         self.outputs = {}
 
+    def tf32_mode_for(self, node_id):
+        """`tf32` is None (strict), a rounding mode applied to every MatMul, or (mode, {node ids}) to emulate TF32 only
+        on the MatMuls the backend actually ran on tensor cores."""
+        if self.tf32 is None or isinstance(self.tf32, str):
+            return self.tf32
+        mode, nodes = self.tf32
+        return mode if node_id in nodes else None
+
     def arg(self, node, k):
         e = node["args"][k]
         src = self.by_id[e["src"]]
@@ -257,7 +265,7 @@ class _Interp:
             return _reduce(node["kind"], self.arg(node, 0), node["args"][0]["arg_shape"], node["axis"])
         if op == "MatMul":
             return _matmul(self.arg(node, 0), self.arg(node, 1), node["args"][0]["arg_shape"], node["args"][1]["arg_shape"], node["shape"], node["mode"],
-                           self.tf32)
+                           self.tf32_mode_for(node["id"]))
         if op == "Unpad":
             return _unpad(self.arg(node, 0), node["args"][0]["arg_shape"], node["axis"], node["pad"])
         if op == "WindowsToImage":

@@ -22,6 +22,16 @@ TF32_PARAM_TOL = 3e-2
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def tensor_core_nodes(env, ex):
+    """Op-node ids of the MatMuls the executor sent to the tcgen05 kernel (launch label 'TensorCore...')."""
+    clusters = ex.train_graph.export_json()["clusters"]
+    nodes = set()
+    for t in env.profile(ex.train_graph, 0, 1):
+        if t["label"].startswith("TensorCore"):
+            nodes.update(clusters[t["cluster"]]["members"])
+    return nodes
+
+
 def test_tf32_training_drift_within_stated_tolerance(env):
     env.set_tf32(True)
     ex = env.example("single-layer", 1024)
@@ -53,9 +63,11 @@ def test_tf32_single_step_gradients(env):
     rng = np.random.default_rng(4)
     params = init_example_params(ex, rng)
     params[ex.x.id], params[ex.y.id] = synthetic_batch(ex, rng)
+    nodes = tensor_core_nodes(env, ex)
+    assert len(nodes) >= 2
     upload(env, params)
     env.run(ex.train_graph, 1)
-    want = run_graph(ex.train_graph_json, params, 1, tf32="trunc")
+    want = run_graph(ex.train_graph_json, params, 1, tf32=("trunc", nodes))
     strict = run_graph(ex.train_graph_json, params, 1)
     for i, p in enumerate(ex.parameters):
         m_state = ex.optimizer_state[1 + 2 * i]
