@@ -250,6 +250,19 @@ Array Array::image_to_windows(int64_t filter_w, int64_t filter_h, int64_t stride
 }
 Array Array::windows_to_image(int64_t stride_w, int64_t stride_h) const {
     Shape s = shape().windows_to_image(stride_w, stride_h);
+    {
+        // Non-overlapping windows (stride == filter, e.g. the 2x2/2 max-pool backward): every image element
+        // comes from exactly one window element, so col2im is a pure permutation and can be a view
+        // ([.., oh, ow, g, fh, fw, c] -> [.., oh, fh, ow, fw, g, c] -> reshape) instead of a kernel.
+        const Shape w = shape();
+        const int n = w.len();
+        if (w[n - 3] == stride_h && w[n - 2] == stride_w) {
+            std::vector<int> perm;
+            for (int i = 0; i < n - 6; ++i) perm.push_back(i);
+            for (int i : {n - 6, n - 3, n - 5, n - 2, n - 4, n - 1}) perm.push_back(i);
+            return permute_axes(perm).reshape(s);
+        }
+    }
     return Array(scope_->ops().new_node(scope_->colour(), s, Op::windows_to_image(stride_w, stride_h), {node_id_}), scope_);
 }
 

@@ -36,7 +36,7 @@ def test_tf32_training_drift_within_stated_tolerance(env):
     env.set_tf32(True)
     ex = env.example("single-layer", 1024)
     labels = [t["label"] for t in env.profile(ex.train_graph, 0, 1)]
-    assert sum(l.startswith("TensorCore") for l in labels) >= 4, labels  # fc1/fc2 forward, dW, dX on tcgen05
+    assert sum(l.startswith("TensorCore") for l in labels) >= 2, labels  # fc1 forward and dW1 (N = 10 operands are not TMA-aligned)
     rng = np.random.default_rng(21)
     params = init_example_params(ex, rng)
     upload(env, params)
