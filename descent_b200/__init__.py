@@ -108,9 +108,9 @@ class Graph:
         _check(lib.dsc_graphdef_export_json(self._h, ctypes.byref(out)))
         return json.loads(_take_string(out))
 
-    def kernel_source(self, sm_count=148, dp_rank=0):
+    def kernel_source(self, sm_count=148, dp_rank=0, tf32=False):
         out = ctypes.c_void_p()
-        _check(lib.dsc_graphdef_kernel_source(self._h, sm_count, dp_rank, ctypes.byref(out)))
+        _check(lib.dsc_graphdef_kernel_source_ex(self._h, sm_count, dp_rank, int(tf32), ctypes.byref(out)))
         return _take_string(out)
 
     def write_dot_file(self, mode, path):

@@ -183,10 +183,14 @@ int dsc_env_graph_stats(dsc_env* env, dsc_graphdef* graph, char** json_out) {
 int dsc_scope_export_json(dsc_scope* scope, char** json_out) { return guarded([&] { *json_out = dup_string(scope->scope->export_json()); }); }
 int dsc_graphdef_export_json(dsc_graphdef* graph, char** json_out) { return guarded([&] { *json_out = dup_string(graph->graph->export_json()); }); }
 int dsc_graphdef_kernel_source(dsc_graphdef* graph, int sm_count, int dp_rank, char** out) {
+    return dsc_graphdef_kernel_source_ex(graph, sm_count, dp_rank, 0, out);
+}
+int dsc_graphdef_kernel_source_ex(dsc_graphdef* graph, int sm_count, int dp_rank, int use_tf32, char** out) {
     return guarded([&] {
         CodegenOptions opt;
         opt.sm_count = sm_count > 0 ? sm_count : 148;
         opt.dp_rank = dp_rank;
+        opt.use_tf32 = use_tf32 != 0;
         *out = dup_string(generate_graph_source(*graph->graph, opt, nullptr));
     });
 }

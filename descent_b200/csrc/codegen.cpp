@@ -539,6 +539,186 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
 }
 )";
 
+// Tensor-core variant of the same GEMM for operands that need index arithmetic (conv2d's im2col view, grouped
+// and transposed views): all 256 threads gather the A/B tiles through their chains (4 consecutive k per thread,
+// one 128-bit shared store) into the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices),
+// one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into a TMEM accumulator and commits to an
+// mbarrier; the gather of tile i+1 overlaps the MMAs of tile i (two smem stages).  Epilogue: tcgen05.ld.
+const char* kMatMulTcTemplate = R"(
+// {{LABEL}}  [tcgen05 tf32]
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* A, const float* B, float* C, const unsigned* dsc_step) {
+    constexpr int BM = 128, BN = {{BN}}, BK = {{BK}}, NT = 256;
+    constexpr int M = {{M}}, N = {{N}}, K = {{K}}, KC = {{KC}}, BC = {{BC}};
+    constexpr int TILES_N = (N + BN - 1) / BN;
+    constexpr int KQ = BK / 4;                              // 16-byte k-chunks per tile row
+    constexpr int A_UNITS = BM * KQ, B_UNITS = BN * KQ;     // one unit = 4 consecutive k of one row
+    constexpr int LA = (A_UNITS + NT - 1) / NT, LB = (B_UNITS + NT - 1) / NT;
+    constexpr unsigned A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr unsigned A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128, SBO = 128;  // k-chunk stride, 8-row-group stride
+    constexpr unsigned TMEM_COLS = {{TMEM_COLS}};
+    constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+    extern __shared__ __align__(128) unsigned char dsc_smem[];
+    unsigned char* sa = dsc_smem;                 // 2 stages of A
+    unsigned char* sb = dsc_smem + 2 * A_BYTES;   // 2 stages of B
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(dsc_smem + 2 * A_BYTES + 2 * B_BYTES);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile_m = blockIdx.x / TILES_N, tile_n = blockIdx.x % TILES_N;
+    const int batch = blockIdx.y, split = blockIdx.z;
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
+    const int k_begin = split * KC;
+    const int k_end = min(K, k_begin + KC);
+    const unsigned sa_addr = (unsigned)__cvta_generic_to_shared(sa), sb_addr = (unsigned)__cvta_generic_to_shared(sb);
+    const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(bars);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_d = *tmem_slot;
+
+    float4 ra[LA], rb[LB];
+    auto load_tile = [&](int k0) {
+        #pragma unroll
+        for (int j = 0; j < LA; ++j) {
+            const int u = tid + j * NT;
+            const int lm = tid % BM, lq = tid / BM + j * (NT / BM);
+            const int gm = m0 + lm;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if ((A_UNITS % NT == 0 || u < A_UNITS) && gm < M) {
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int gk = k0 + lq * 4 + q;
+                    if (gk < k_end) {
+{{A_CHAIN}}
+                        v[q] = A[{{A_IDX}}];
+                    }
+                }
+            }
+            ra[j] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        #pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const int u = tid + j * NT;
+            const int ln = u % BN, lq = u / BN;
+            const int gn = n0 + ln;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if ((B_UNITS % NT == 0 || u < B_UNITS) && gn < N) {
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int gk = k0 + lq * 4 + q;
+                    if (gk < k_end) {
+{{B_CHAIN}}
+                        v[q] = B[{{B_IDX}}];
+                    }
+                }
+            }
+            rb[j] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    };
+    auto store_tile = [&](int buf) {
+        #pragma unroll
+        for (int j = 0; j < LA; ++j) {
+            const int u = tid + j * NT;
+            const int lm = tid % BM, lq = tid / BM + j * (NT / BM);
+            if (A_UNITS % NT == 0 || u < A_UNITS)
+                *reinterpret_cast<float4*>(sa + buf * A_BYTES + lq * A_LBO + (lm >> 3) * SBO + (lm & 7) * 16) = ra[j];
+        }
+        #pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const int u = tid + j * NT;
+            const int ln = u % BN, lq = u / BN;
+            if (B_UNITS % NT == 0 || u < B_UNITS)
+                *reinterpret_cast<float4*>(sb + buf * B_BYTES + lq * B_LBO + (ln >> 3) * SBO + (ln & 7) * 16) = rb[j];
+        }
+    };
+    auto wait_bar = [&](int buf, unsigned parity) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "DSC_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DSC_DONE;\n"
+            "bra DSC_WAIT;\n"
+            "DSC_DONE:\n"
+            "}\n" ::"r"(bar_addr + 8u * buf), "r"(parity) : "memory");
+    };
+    const int num_tiles = (k_end - k_begin + BK - 1) / BK;
+    for (int it = 0; it < num_tiles; ++it) {
+        const int buf = it & 1;
+        load_tile(k_begin + it * BK);
+        if (it >= 2) wait_bar(buf, (unsigned)((it >> 1) - 1) & 1u);  // the MMAs that read this stage have retired
+        store_tile(buf);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            #pragma unroll
+            for (int kk = 0; kk < BK / 8; ++kk) {
+                const unsigned a_addr = sa_addr + buf * A_BYTES + kk * 2 * A_LBO;
+                const unsigned b_addr = sb_addr + buf * B_BYTES + kk * 2 * B_LBO;
+                const unsigned long long adesc = (unsigned long long)((a_addr >> 4) & 0x3fff) | ((unsigned long long)((A_LBO >> 4) & 0x3fff) << 16) |
+                                                 ((unsigned long long)((SBO >> 4) & 0x3fff) << 32) | (1ull << 46);
+                const unsigned long long bdesc = (unsigned long long)((b_addr >> 4) & 0x3fff) | ((unsigned long long)((B_LBO >> 4) & 0x3fff) << 16) |
+                                                 ((unsigned long long)((SBO >> 4) & 0x3fff) << 32) | (1ull << 46);
+                const unsigned accumulate = (it | kk) != 0 ? 1u : 0u;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    "setp.ne.b32 p, %4, 0;\n"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+                    "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr + 8u * buf) : "memory");
+        }
+    }
+    if (num_tiles > 0) wait_bar((num_tiles - 1) & 1, (unsigned)((num_tiles - 1) >> 1) & 1u);  // the last commit covers every MMA
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // epilogue: warp w reads the 32 TMEM lanes of quadrant w%4, 16 columns at a time
+    const int quad = warp & 3;
+    const int gm = m0 + quad * 32 + lane;
+    for (int c0 = (warp >> 2) * 16; c0 < BN; c0 += 32) {
+        unsigned v[16];
+        const unsigned taddr = tmem_d + ((unsigned)(quad * 32) << 16) + (unsigned)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+              "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (gm < M && num_tiles > 0) {
+            float* crow = C + {{C_ROW}};
+            const int gn0 = n0 + c0;
+            if (N % 4 == 0) {
+                #pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    if (gn0 + j < N)
+                        *reinterpret_cast<float4*>(crow + gn0 + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (gn0 + j < N) crow[gn0 + j] = __uint_as_float(v[j]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+    }
+}
+)";
+
 const char* kSplitSumTemplate = R"(
 // split-K partial sums of {{LABEL}}, added in ascending split order
 extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws, float* out0, const unsigned* dsc_step) {
@@ -611,14 +791,28 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
         }
     }
 
+    // Operands behind view chains (conv2d's im2col, grouped / transposed views) use the gathered tcgen05 kernel
+    // when TF32 is allowed and the GEMM is big enough to matter; otherwise the strict-FP32 SIMT kernel.
+    const bool tc = opt.use_tf32 && 2.0 * (double)BC * (double)M * (double)N * (double)K >= 5e7 && N >= 8;
     GemmTile t = choose_gemm_tile(M, N);
+    if (tc) {
+        t.bm = 128;
+        t.bn = (int)std::min<int64_t>(div_round_up(N, 16) * 16, 256);
+        t.nt = 256;
+        t.tm = t.tn = 0;
+        int64_t best_padded = INT64_MAX;
+        for (int bk = 8; bk <= 64; bk += 8) {  // least zero padding of K, then the deepest tile
+            const int64_t padded = div_round_up(K, bk) * bk;
+            if (padded <= best_padded) { best_padded = padded; t.bk = bk; }
+        }
+    }
     const int64_t tiles = div_round_up(M, t.bm) * div_round_up(N, t.bn) * BC;
 
     int64_t S, KC;
     if (c.matmul_absorbs_reduce || r_graph == 1) {
         // the backend owns the K split (the reference fixes it at ceil(K/1024), op.rs:74): enough CTAs to
         // fill the machine, at least 4 k-tiles per split, partial-sum traffic well under the operand traffic
-        const int64_t target = (int64_t)opt.sm_count * std::max(2, std::min(8, 1024 / t.nt));
+        const int64_t target = (int64_t)opt.sm_count * (tc ? 4 : std::max(2, std::min(8, 1024 / t.nt)));
         const int64_t in_elems = a.chain.addressed_count() + b.chain.addressed_count();
         S = 1;
         if (tiles * 2 <= target && K >= 8 * t.bk) {
@@ -664,6 +858,14 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     const std::string name = "k" + num(ci);
     std::string c_row = rows_mode ? "(((size_t)split * M + gm) * BC + batch) * N" : "(((size_t)split * BC + batch) * M + gm) * N";
     ClusterCode code;
+    int64_t tmem_cols = 32;
+    while (tmem_cols < t.bn) tmem_cols *= 2;
+    if (tc)
+        code.source = subst(kMatMulTcTemplate,
+                            {{"LABEL", c.label}, {"NAME", name}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)},
+                             {"KC", num(KC)}, {"BC", num(BC)}, {"TMEM_COLS", num(tmem_cols)}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
+                             {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
+    else
     code.source = subst(kMatMulTemplate,
                         {{"LABEL", c.label}, {"NAME", name}, {"NT", num(t.nt)}, {"BM", num(t.bm)}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"TM", num(t.tm)},
                          {"TN", num(t.tn)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"KC", num(KC)}, {"BC", num(BC)},
@@ -676,7 +878,8 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     l.grid_y = (uint32_t)BC;
     l.grid_z = (uint32_t)S;
     l.block = t.nt;
-    l.label = c.label;
+    l.label = tc ? "TensorCore" + c.label : c.label;
+    if (tc) l.smem = (uint32_t)(2 * (t.bm + t.bn) * t.bk * 4 + 64);
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
     if (via_scratch) l.args.push_back({KernelArg::Scratch, -1, 0});

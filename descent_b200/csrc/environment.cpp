@@ -396,6 +396,7 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
                 exec.stats.flops += l.flops;
             } else {
                 check(dsc_module_get_kernel(exec.module, l.entry.c_str(), &r.kernel));
+                if (l.smem > 48 * 1024) check(dsc_kernel_set_max_dynamic_smem(r.kernel, (int)l.smem));
                 r.gx = l.grid_x; r.gy = l.grid_y; r.gz = l.grid_z; r.block = l.block; r.smem = l.smem;
                 for (const auto& a : l.args)
                     r.buffers.push_back(a.kind == KernelArg::NodeBuffer ? device_address(a.node_id)

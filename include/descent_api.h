@@ -63,6 +63,7 @@ int dsc_env_graph_stats(dsc_env* env, dsc_graphdef* graph, char** json_out);
 int dsc_scope_export_json(dsc_scope* scope, char** json_out);       /* raw op graph: what the oracle interprets */
 int dsc_graphdef_export_json(dsc_graphdef* graph, char** json_out); /* optimised graph + clusters */
 int dsc_graphdef_kernel_source(dsc_graphdef* graph, int sm_count, int dp_rank, char** cuda_source_out);
+int dsc_graphdef_kernel_source_ex(dsc_graphdef* graph, int sm_count, int dp_rank, int use_tf32, char** cuda_source_out);
 int dsc_graphdef_write_dot_file(dsc_graphdef* graph, int mode /*0 none,1 cluster,2 colour*/, const char* path); /* graph.rs:656 */
 
 /* ---- Scope (array.rs:1257-1441) ------------------------------------------------------------- */

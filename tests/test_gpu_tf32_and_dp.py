@@ -88,3 +88,28 @@ def test_two_gpu_data_parallel_matches_single_gpu(workload):
                           "--master-port", "29533", script, workload], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DP_OK" in out.stdout, out.stdout[-3000:]
+
+
+@pytest.mark.parametrize("network,m", [("conv-net", 64), ("conv-blur-net", 32), ("siren", 1024)])
+def test_tf32_view_chain_gemms_match_tf32_oracle(env, network, m):
+    """conv2d as implicit GEMM (im2col view chain, grouped, replicate padding) and transposed dense GEMMs on the
+    gathered tcgen05 kernel: one training step against the oracle with TF32 truncation on exactly those MatMuls."""
+    env.set_tf32(True)
+    ex = env.example(network, m)
+    rng = np.random.default_rng(8)
+    params = init_example_params(ex, rng, siren=(network == "siren"))
+    params[ex.x.id], params[ex.y.id] = synthetic_batch(ex, rng)
+    nodes = tensor_core_nodes(env, ex)
+    assert nodes, "no MatMul went to the tensor cores"
+    upload(env, params)
+    from helpers import fill_missing_inputs
+    fill_missing_inputs(env, ex.train_graph_json, params)
+    env.run(ex.train_graph, 5)
+    want = run_graph(ex.train_graph_json, params, 5, tf32=("trunc", nodes))
+    worst = {}
+    for i, p in enumerate(ex.parameters):
+        m_state = ex.optimizer_state[1 + 2 * i]
+        worst[p.name() + "#%d" % p.id] = max_rel_err(env.read(m_state), want[m_state.id])
+    print(network, worst)
+    assert max(worst.values()) <= 1e-4, worst
+    assert abs(env.read_parameter_scalar(ex.loss_sum) - float(want[ex.loss_sum.id][0])) <= 1e-5 * abs(float(want[ex.loss_sum.id][0]))
