@@ -90,8 +90,10 @@ def test_two_gpu_data_parallel_matches_single_gpu(workload):
     assert "DP_OK" in out.stdout, out.stdout[-3000:]
 
 
-@pytest.mark.parametrize("network,m", [("conv-net", 64), ("conv-blur-net", 32), ("siren", 1024)])
-def test_tf32_view_chain_gemms_match_tf32_oracle(env, network, m):
+# SIREN's first layer (x30 init) feeds sin() arguments of magnitude ~50: FP32 accumulation-order noise of the GEMM is
+# amplified by the oscillation, hence the wider bound there.
+@pytest.mark.parametrize("network,m,tol", [("conv-net", 64, 1e-4), ("conv-blur-net", 32, 1e-4), ("siren", 1024, 1e-3)])
+def test_tf32_view_chain_gemms_match_tf32_oracle(env, network, m, tol):
     """conv2d as implicit GEMM (im2col view chain, grouped, replicate padding) and transposed dense GEMMs on the
     gathered tcgen05 kernel: one training step against the oracle with TF32 truncation on exactly those MatMuls."""
     env.set_tf32(True)
@@ -111,5 +113,5 @@ def test_tf32_view_chain_gemms_match_tf32_oracle(env, network, m):
         m_state = ex.optimizer_state[1 + 2 * i]
         worst[p.name() + "#%d" % p.id] = max_rel_err(env.read(m_state), want[m_state.id])
     print(network, worst)
-    assert max(worst.values()) <= 1e-4, worst
+    assert max(worst.values()) <= tol, worst
     assert abs(env.read_parameter_scalar(ex.loss_sum) - float(want[ex.loss_sum.id][0])) <= 1e-5 * abs(float(want[ex.loss_sum.id][0]))
