@@ -553,8 +553,10 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* A, const
     constexpr int KQ = BK / 4;                              // 16-byte k-chunks per tile row
     constexpr int A_UNITS = BM * KQ, B_UNITS = BN * KQ;     // one unit = 4 consecutive k of one row
     constexpr int LA = (A_UNITS + NT - 1) / NT, LB = (B_UNITS + NT - 1) / NT;
-    constexpr unsigned A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-    constexpr unsigned A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128, SBO = 128;  // k-chunk stride, 8-row-group stride
+    // k-chunk stride (LBO) and 8-row-group stride (SBO); LBO carries 16 bytes of padding so that lanes storing
+    // consecutive k-chunks of one row hit different banks
+    constexpr unsigned A_LBO = (BM / 8) * 128 + 16, B_LBO = (BN / 8) * 128 + 16, SBO = 128;
+    constexpr unsigned A_BYTES = KQ * A_LBO, B_BYTES = KQ * B_LBO;
     constexpr unsigned TMEM_COLS = {{TMEM_COLS}};
     constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
     extern __shared__ __align__(128) unsigned char dsc_smem[];
@@ -585,56 +587,69 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* A, const
     const unsigned tmem_d = *tmem_slot;
 
     float4 ra[LA], rb[LB];
+    // One unit = 4 consecutive k of one row.  Lanes walk k first (consecutive 16-byte chunks of the same row are
+    // usually adjacent in memory: channels of one pixel, then the next pixel), and a unit whose four source
+    // addresses turn out contiguous and 16-byte aligned is fetched with a single 128-bit load.
     auto load_tile = [&](int k0) {
         #pragma unroll
         for (int j = 0; j < LA; ++j) {
             const int u = tid + j * NT;
-            const int lm = tid % BM, lq = tid / BM + j * (NT / BM);
+            const int lq = u % KQ, lm = u / KQ;
             const int gm = m0 + lm;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            unsigned ai[4] = {0u, 0u, 0u, 0u};
+            bool av[4] = {false, false, false, false};
             if ((A_UNITS % NT == 0 || u < A_UNITS) && gm < M) {
                 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int gk = k0 + lq * 4 + q;
                     if (gk < k_end) {
 {{A_CHAIN}}
-                        v[q] = A[{{A_IDX}}];
+                        ai[q] = {{A_IDX}};
+                        av[q] = true;
                     }
                 }
             }
-            ra[j] = make_float4(v[0], v[1], v[2], v[3]);
+            if (av[3] && ai[1] == ai[0] + 1u && ai[2] == ai[0] + 2u && ai[3] == ai[0] + 3u && (ai[0] & 3u) == 0u)
+                ra[j] = *reinterpret_cast<const float4*>(A + ai[0]);
+            else
+                ra[j] = make_float4(av[0] ? A[ai[0]] : 0.f, av[1] ? A[ai[1]] : 0.f, av[2] ? A[ai[2]] : 0.f, av[3] ? A[ai[3]] : 0.f);
         }
         #pragma unroll
         for (int j = 0; j < LB; ++j) {
             const int u = tid + j * NT;
-            const int ln = u % BN, lq = u / BN;
+            const int lq = u % KQ, ln = u / KQ;
             const int gn = n0 + ln;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            unsigned bi[4] = {0u, 0u, 0u, 0u};
+            bool bv[4] = {false, false, false, false};
             if ((B_UNITS % NT == 0 || u < B_UNITS) && gn < N) {
                 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int gk = k0 + lq * 4 + q;
                     if (gk < k_end) {
 {{B_CHAIN}}
-                        v[q] = B[{{B_IDX}}];
+                        bi[q] = {{B_IDX}};
+                        bv[q] = true;
                     }
                 }
             }
-            rb[j] = make_float4(v[0], v[1], v[2], v[3]);
+            if (bv[3] && bi[1] == bi[0] + 1u && bi[2] == bi[0] + 2u && bi[3] == bi[0] + 3u && (bi[0] & 3u) == 0u)
+                rb[j] = *reinterpret_cast<const float4*>(B + bi[0]);
+            else
+                rb[j] = make_float4(bv[0] ? B[bi[0]] : 0.f, bv[1] ? B[bi[1]] : 0.f, bv[2] ? B[bi[2]] : 0.f, bv[3] ? B[bi[3]] : 0.f);
         }
     };
     auto store_tile = [&](int buf) {
         #pragma unroll
         for (int j = 0; j < LA; ++j) {
             const int u = tid + j * NT;
-            const int lm = tid % BM, lq = tid / BM + j * (NT / BM);
+            const int lq = u % KQ, lm = u / KQ;
             if (A_UNITS % NT == 0 || u < A_UNITS)
                 *reinterpret_cast<float4*>(sa + buf * A_BYTES + lq * A_LBO + (lm >> 3) * SBO + (lm & 7) * 16) = ra[j];
         }
         #pragma unroll
         for (int j = 0; j < LB; ++j) {
             const int u = tid + j * NT;
-            const int ln = u % BN, lq = u / BN;
+            const int lq = u % KQ, ln = u / KQ;
             if (B_UNITS % NT == 0 || u < B_UNITS)
                 *reinterpret_cast<float4*>(sb + buf * B_BYTES + lq * B_LBO + (ln >> 3) * SBO + (ln & 7) * 16) = rb[j];
         }
@@ -793,7 +808,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
 
     // Operands behind view chains (conv2d's im2col, grouped / transposed views) use the gathered tcgen05 kernel
     // when TF32 is allowed and the GEMM is big enough to matter; otherwise the strict-FP32 SIMT kernel.
-    const bool tc = opt.use_tf32 && 2.0 * (double)BC * (double)M * (double)N * (double)K >= 5e7 && N >= 8;
+    const bool tc = opt.use_tf32 && 2.0 * (double)BC * (double)M * (double)N * (double)K >= 5e7 && N >= 8 && M >= 128;
     GemmTile t = choose_gemm_tile(M, N);
     if (tc) {
         t.bm = 128;
@@ -879,7 +894,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     l.grid_z = (uint32_t)S;
     l.block = t.nt;
     l.label = tc ? "TensorCore" + c.label : c.label;
-    if (tc) l.smem = (uint32_t)(2 * (t.bm + t.bn) * t.bk * 4 + 64);
+    if (tc) l.smem = (uint32_t)(2 * (t.bk / 4) * ((t.bm / 8) * 128 + 16 + (t.bn / 8) * 128 + 16) + 64);
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
     if (via_scratch) l.args.push_back({KernelArg::Scratch, -1, 0});
