@@ -152,6 +152,35 @@ std::string emit_chain(std::ostringstream& os, const ViewChain& chain, const std
     return emit_chain(os, chain, linear_term(e, chain.output_count), uniq, indent);
 }
 
+// Largest power of two R <= 4 such that every R-aligned group of R consecutive consumer elements is read from
+// R consecutive, R-aligned producer elements.  Per view: the innermost output axis must walk the innermost input
+// axis with step 1 and without clamping, and every quantity that could break the alignment of a group (extents
+// of those axes, the offset, steps of other output axes onto the same input axis) must be a multiple of R.
+// Reshapes between views preserve linear indices, so the conditions compose.
+int64_t chain_vector_run(const ViewChain& chain, int64_t innermost_extent) {
+    auto pow2_divisor = [](int64_t r, int64_t v) {
+        v = v < 0 ? -v : v;
+        if (v == 0) return r;
+        while (r > 1 && v % r != 0) r /= 2;
+        return r;
+    };
+    int64_t run = pow2_divisor(4, innermost_extent);
+    for (const View& v : chain.views) {
+        int ao = v.output_shape.len() - 1, ai = v.input_shape.len() - 1;
+        while (ao > 0 && v.output_shape[ao] == 1) --ao;
+        while (ai > 0 && v.input_shape[ai] == 1) --ai;
+        const AxisMapping& m = v.output_mapping[ao];
+        if (!m.is_source || m.axis != ai || m.step != 1 || v.input_needs_clamp(ai)) return 1;
+        run = pow2_divisor(run, v.output_shape[ao]);
+        run = pow2_divisor(run, v.input_shape[ai]);
+        run = pow2_divisor(run, v.input_offsets[ai]);
+        for (int i = 0; i < v.output_shape.len(); ++i)
+            if (i != ao && v.output_mapping[i].is_source && v.output_mapping[i].axis == ai && v.output_shape[i] > 1)
+                run = pow2_divisor(run, v.output_mapping[i].step);
+    }
+    return run;
+}
+
 double chain_bytes(const Graph& g, const ClusterInput& in) {
     (void)g;
     return 4.0 * (double)in.chain.addressed_count();
@@ -558,6 +587,7 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* A, const
     constexpr unsigned A_LBO = (BM / 8) * 128 + 16, B_LBO = (BN / 8) * 128 + 16, SBO = 128;
     constexpr unsigned A_BYTES = KQ * A_LBO, B_BYTES = KQ * B_LBO;
     constexpr unsigned TMEM_COLS = {{TMEM_COLS}};
+    constexpr bool A_VEC = {{A_VEC}}, B_VEC = {{B_VEC}};  // aligned groups of 4 k are provably contiguous in memory
     constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
     extern __shared__ __align__(128) unsigned char dsc_smem[];
     unsigned char* sa = dsc_smem;                 // 2 stages of A
@@ -598,6 +628,17 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* A, const
             const int gm = m0 + lm;
             unsigned ai[4] = {0u, 0u, 0u, 0u};
             bool av[4] = {false, false, false, false};
+            if (A_VEC) {
+                const int gk = k0 + lq * 4;
+                ra[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((A_UNITS % NT == 0 || u < A_UNITS) && gm < M && gk < k_end) {
+{{A_CHAIN}}
+                    const float* src = A + {{A_IDX}};
+                    if (gk + 3 < k_end) ra[j] = *reinterpret_cast<const float4*>(src);
+                    else ra[j] = make_float4(src[0], gk + 1 < k_end ? src[1] : 0.f, gk + 2 < k_end ? src[2] : 0.f, 0.f);
+                }
+                continue;
+            }
             if ((A_UNITS % NT == 0 || u < A_UNITS) && gm < M) {
                 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -621,6 +662,17 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* A, const
             const int gn = n0 + ln;
             unsigned bi[4] = {0u, 0u, 0u, 0u};
             bool bv[4] = {false, false, false, false};
+            if (B_VEC) {
+                const int gk = k0 + lq * 4;
+                rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((B_UNITS % NT == 0 || u < B_UNITS) && gn < N && gk < k_end) {
+{{B_CHAIN}}
+                    const float* src = B + {{B_IDX}};
+                    if (gk + 3 < k_end) rb[j] = *reinterpret_cast<const float4*>(src);
+                    else rb[j] = make_float4(src[0], gk + 1 < k_end ? src[1] : 0.f, gk + 2 < k_end ? src[2] : 0.f, 0.f);
+                }
+                continue;
+            }
             if ((B_UNITS % NT == 0 || u < B_UNITS) && gn < N) {
                 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -878,7 +930,9 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     if (tc)
         code.source = subst(kMatMulTcTemplate,
                             {{"LABEL", c.label}, {"NAME", name}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)},
-                             {"KC", num(KC)}, {"BC", num(BC)}, {"TMEM_COLS", num(tmem_cols)}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
+                             {"KC", num(KC)}, {"BC", num(BC)}, {"TMEM_COLS", num(tmem_cols)},
+                             {"A_VEC", chain_vector_run(a.chain, K) == 4 && KC % 4 == 0 ? "true" : "false"},
+                             {"B_VEC", chain_vector_run(b.chain, N) == 4 && false ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
                              {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
     else
     code.source = subst(kMatMulTemplate,
