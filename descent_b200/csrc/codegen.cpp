@@ -343,6 +343,8 @@ const char* kReduceTemplate = R"(
 // {{LABEL}}
 extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, float* out0, const unsigned* dsc_step) {
     constexpr unsigned O = {{O}}u, K = {{K}}u, INNER = {{INNER}}u, G = {{G}}u, TO = 256u / G;
+    constexpr unsigned S = {{S}}u, KS = (K + S - 1u) / S;  // S > 1: blockIdx.y owns a slice of k and writes a partial
+    const unsigned k_lo = blockIdx.y * KS, k_hi = min(K, k_lo + KS);
     const unsigned tid = threadIdx.x;
     const unsigned g = {{G_OF_TID}};
     const unsigned ol = {{O_OF_TID}};
@@ -351,7 +353,7 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, flo
     if (o < O) {
         const unsigned oo = o / INNER, oi = o % INNER;
         {{UNROLL}}
-        for (unsigned k = g; k < K; k += G) {
+        for (unsigned k = k_lo + g; k < k_hi; k += G) {
             const unsigned e = (oo * K + k) * INNER + oi;
 {{CHAIN}}
             const float v = in0[{{IDX}}];
@@ -370,10 +372,26 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, flo
             }
             __syncthreads();
         }
-        if (g == 0 && o < O) out0[o] = red[tid];
+        if (g == 0 && o < O) out0[blockIdx.y * O + o] = red[tid];
     } else if (o < O) {
-        out0[o] = acc;
+        out0[blockIdx.y * O + o] = acc;
     }
+}
+)";
+
+const char* kReduceSplitTemplate = R"(
+// k-slice partials of {{LABEL}}, combined in ascending slice order
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws, float* out0, const unsigned* dsc_step) {
+    constexpr unsigned COUNT = {{COUNT}}u, S = {{S}}u;
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= COUNT) return;
+    float acc = ws[i];
+    #pragma unroll 8
+    for (unsigned s = 1; s < S; ++s) {
+        const float v = ws[s * COUNT + i];
+        acc = {{OP}};
+    }
+    out0[i] = acc;
 }
 )";
 
@@ -401,25 +419,45 @@ ClusterCode gen_reduce(const Graph& g, const Cluster& c, int ci, const CodegenOp
             kfast = dk != 0 && (d_o == 0 || dk < d_o);
         }
     }
+    // few outputs and a long axis: slice k across blockIdx.y as well, partials to scratch, combined in slice order
+    int64_t S = 1;
+    const int64_t blocks = div_round_up(O, 256 / G);
+    if (blocks < 2 * opt.sm_count && K / G >= 64) S = std::max<int64_t>(1, std::min<int64_t>(div_round_up(4 * opt.sm_count, blocks), K / (G * 16)));
     std::ostringstream chain;
     int uniq = 0;
     std::string idx = emit_chain(chain, in.chain, "e", uniq, "            ");
     const bool is_max = node.op.reduce == ReduceOp::Max;
     const std::string name = "k" + num(ci);
     ClusterCode code;
-    code.source = subst(kReduceTemplate, {{"LABEL", c.label}, {"NAME", name}, {"O", num(O)}, {"K", num(K)}, {"INNER", num(inner)}, {"G", num(G)},
+    code.source = subst(kReduceTemplate, {{"LABEL", c.label}, {"NAME", name}, {"O", num(O)}, {"K", num(K)}, {"INNER", num(inner)}, {"G", num(G)}, {"S", num(S)},
                                           {"G_OF_TID", kfast ? "tid % G" : "tid / TO"}, {"O_OF_TID", kfast ? "tid / G" : "tid % TO"},
                                           {"GSTRIDE", kfast ? "1u" : "TO"}, {"INIT", is_max ? "__uint_as_float(0xff800000u)" : "0.f"},
                                           {"UNROLL", K <= 16 ? "#pragma unroll" : "#pragma unroll 4"}, {"CHAIN", chain.str()}, {"IDX", idx},
                                           {"OP", is_max ? "fmaxf(acc, v)" : "acc + v"}, {"OP_AV", is_max ? "fmaxf(a, v)" : "a + v"}});
     KernelLaunch l;
     l.entry = name;
-    l.grid_x = (uint32_t)div_round_up(O, 256 / G);
+    l.grid_x = (uint32_t)blocks;
+    l.grid_y = (uint32_t)S;
     l.label = c.label;
     l.cluster = ci;
-    l.args = {{KernelArg::NodeBuffer, in.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+    l.args = {{KernelArg::NodeBuffer, in.node_id, 0}};
+    if (S > 1) l.args.push_back({KernelArg::Scratch, -1, 0});
+    else l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
     l.algorithmic_bytes = chain_bytes(g, in) + 4.0 * (double)O;
     code.launches.push_back(l);
+    if (S > 1) {
+        code.scratch_bytes = S * O * 4;
+        const std::string sname = name + "_slices";
+        code.source += subst(kReduceSplitTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(O)}, {"S", num(S)},
+                                                    {"OP", is_max ? "fmaxf(acc, v)" : "acc + v"}});
+        KernelLaunch sl;
+        sl.entry = sname;
+        sl.grid_x = (uint32_t)div_round_up(O, 256);
+        sl.label = "ReduceSlices " + c.label;
+        sl.cluster = ci;
+        sl.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+        code.launches.push_back(sl);
+    }
     return code;
 }
 
@@ -1084,21 +1122,15 @@ ClusterCode gen_w2i(const Graph& g, const Cluster& c, int ci) {
 // chunk partials to the accumulator in ascending chunk order.  Bitwise reproducible run to run.
 
 const char* kScatterTemplate = R"(
-// {{LABEL}}: per-chunk sorted partial sums
-extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part(const float* values, const float* indices, float* partial, const unsigned* dsc_step) {
-    constexpr unsigned CH = {{CH}}u, COUNT = {{COUNT}}u, ROWS = {{ROWS}}u, INNER = {{INNER}}u, OUTER = {{OUTER}}u, PER = CH / 256u;
+// {{LABEL}}: per-chunk sorted partial sums ({{NSRC}} chained source(s))
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part({{SRC_PARAMS}}float* partial, const unsigned* dsc_step) {
+    constexpr unsigned CH = {{CH}}u, ROWS = {{ROWS}}u, INNER = {{INNER}}u, OUTER = {{OUTER}}u, PER = CH / 256u;
     __shared__ unsigned keys[CH];
     __shared__ float vals[CH];
-    const unsigned tid = threadIdx.x, chunk = blockIdx.x, outer = blockIdx.y;
+    const unsigned tid = threadIdx.x, gchunk = blockIdx.x, outer = blockIdx.y;
     for (unsigned lp = tid; lp < CH; lp += 256u) {
-        const unsigned pos = chunk * CH + lp;
         unsigned key = 0xffffffffu;
-        if (pos < COUNT) {
-            const unsigned e = pos;
-{{IDX_CHAIN}}
-            const unsigned row = (unsigned)__float_as_int(indices[{{IDX_IDX}}]);
-            if (row < ROWS) key = row * CH + lp;
-        }
+{{LOAD_KEYS}}
         keys[lp] = key;
     }
     __syncthreads();
@@ -1121,9 +1153,8 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part(const float* val
             const unsigned key = keys[i];
             float v = 0.f;
             if (key != 0xffffffffu) {
-                const unsigned e = (outer * COUNT + chunk * CH + key % CH) * INNER + w;
-{{VAL_CHAIN}}
-                v = values[{{VAL_IDX}}];
+                const unsigned lp = key % CH;
+{{LOAD_VALUES}}
             }
             vals[i] = v;
         }
@@ -1150,7 +1181,7 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part(const float* val
             if (key == 0xffffffffu) continue;
             const unsigned row = key / CH;
             const bool tail = (i == CH - 1) || (keys[i + 1] / CH != row);
-            if (tail) partial[((chunk * OUTER + outer) * ROWS + row) * INNER + w] = vals[i];
+            if (tail) partial[((gchunk * OUTER + outer) * ROWS + row) * INNER + w] = vals[i];
         }
         __syncthreads();
     }
@@ -1163,70 +1194,93 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}_sum({{ACC_PARAM}}cons
     if (e >= TOTAL) return;
 {{ACC_CHAIN}}
     float acc = {{ACC_VALUE}};
+    #pragma unroll 4
     for (unsigned c = 0; c < NCHUNK; ++c) acc += partial[c * TOTAL + e];
     out0[e] = acc;
 }
 )";
 
 ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci) {
-    const OpNode& node = g.ops().nodes[c.node_id];
-    const ClusterInput& values = c.inputs[0];
-    const ClusterInput& indices = c.inputs[1];
+    const OpNode& node = g.ops().nodes[c.node_id];  // the first scatter of the chain: same table shape and axis as the rest
+    const int nsrc = (int)c.members.size();
     const int axis = node.op.axis;
-    const int64_t rows = node.shape[axis], count = values.arg_shape[axis];
+    const int64_t rows = node.shape[axis];
     int64_t inner = 1, outer = 1;
     for (int d = axis + 1; d < node.shape.len(); ++d) inner *= node.shape[d];
     for (int d = 0; d < axis; ++d) outer *= node.shape[d];
-    const int64_t ch = std::min<int64_t>(1024, std::max<int64_t>(256, pow2_ceil(count)));
+    int64_t max_count = 1;
+    for (int s = 0; s < nsrc; ++s) max_count = std::max(max_count, c.inputs[2 * s].arg_shape[axis]);
+    const int64_t ch = std::min<int64_t>(1024, std::max<int64_t>(256, pow2_ceil(max_count)));
     DSC_CHECK(rows * ch < (int64_t)0xffffffffLL, "scatter_add table too large for 32-bit sort keys");
-    const int64_t nchunk = div_round_up(count, ch);
     const int64_t total = node.shape.element_count();
     const OpNode& acc_node = g.ops().nodes[c.copy_from];
     const bool acc_literal = acc_node.op.kind == OpKind::Literal;
 
     int uniq = 0;
-    std::ostringstream ic, vc, ac;
-    std::string ii = emit_chain(ic, indices.chain, "e", uniq, "            ");
-    std::string vi = emit_chain(vc, values.chain, "e", uniq, "                ");
-    std::string acc_value;
-    if (acc_literal) {
-        acc_value = "__uint_as_float(" + num(acc_node.op.literal_bits) + "u)";
-    } else {
-        acc_value = "acc_in[" + emit_chain(ac, c.inputs[2].chain, "e", uniq, "    ") + "]";
+    std::ostringstream params, load_keys, load_values;
+    int64_t chunk_base = 0;
+    double bytes = 2.0 * 4.0 * (double)total;
+    for (int s = 0; s < nsrc; ++s) {
+        const ClusterInput& values = c.inputs[2 * s];
+        const ClusterInput& indices = c.inputs[2 * s + 1];
+        const int64_t count = values.arg_shape[axis];
+        const int64_t nchunk = div_round_up(count, ch);
+        params << "const float* values" << s << ", const float* indices" << s << ", ";
+        const std::string cond = "gchunk >= " + unum(chunk_base) + " && gchunk < " + unum(chunk_base + nchunk);
+        load_keys << "        if (" << cond << ") {\n            const unsigned pos = (gchunk - " << unum(chunk_base) << ") * CH + lp;\n"
+                  << "            if (pos < " << unum(count) << ") {\n                const unsigned e = pos;\n";
+        std::string ii = emit_chain(load_keys, indices.chain, "e", uniq, "                ");
+        load_keys << "                const unsigned row = (unsigned)__float_as_int(indices" << s << "[" << ii << "]);\n"
+                  << "                if (row < ROWS) key = row * CH + lp;\n            }\n        }\n";
+        load_values << "                if (" << cond << ") {\n                    const unsigned e = (outer * " << unum(count) << " + (gchunk - "
+                    << unum(chunk_base) << ") * CH + lp) * INNER + w;\n";
+        std::string vi = emit_chain(load_values, values.chain, "e", uniq, "                    ");
+        load_values << "                    v = values" << s << "[" << vi << "];\n                }\n";
+        chunk_base += nchunk;
+        bytes += chain_bytes(g, values) + chain_bytes(g, indices);
     }
+    const int64_t nchunk_total = chunk_base;
+    std::ostringstream ac;
+    std::string acc_value;
+    if (acc_literal) acc_value = "__uint_as_float(" + num(acc_node.op.literal_bits) + "u)";
+    else acc_value = "acc_in[" + emit_chain(ac, c.inputs[2 * nsrc].chain, "e", uniq, "    ") + "]";
     const std::string name = "k" + num(ci);
     ClusterCode code;
     code.source = subst(kScatterTemplate,
-                        {{"LABEL", c.label}, {"NAME", name}, {"CH", num(ch)}, {"COUNT", num(count)}, {"ROWS", num(rows)}, {"INNER", num(inner)},
-                         {"OUTER", num(outer)}, {"IDX_CHAIN", ic.str()}, {"IDX_IDX", ii}, {"VAL_CHAIN", vc.str()}, {"VAL_IDX", vi},
-                         {"ACC_PARAM", acc_literal ? "" : "const float* acc_in, "}, {"TOTAL", num(total)}, {"NCHUNK", num(nchunk)},
+                        {{"LABEL", c.label}, {"NAME", name}, {"NSRC", num(nsrc)}, {"SRC_PARAMS", params.str()}, {"CH", num(ch)}, {"ROWS", num(rows)},
+                         {"INNER", num(inner)}, {"OUTER", num(outer)}, {"LOAD_KEYS", load_keys.str()}, {"LOAD_VALUES", load_values.str()},
+                         {"ACC_PARAM", acc_literal ? "" : "const float* acc_in, "}, {"TOTAL", num(total)}, {"NCHUNK", num(nchunk_total)},
                          {"ACC_CHAIN", ac.str()}, {"ACC_VALUE", acc_value}});
-    code.scratch_bytes = nchunk * total * 4;
+    code.scratch_bytes = nchunk_total * total * 4;
     KernelLaunch z;
     z.kind = KernelLaunch::ZeroScratch;
     z.zero_offset = 0;
     z.zero_bytes = code.scratch_bytes;
-    z.label = "Fill(0) " + num(nchunk * total);
+    z.label = "Fill(0) " + num(nchunk_total * total);
     z.cluster = ci;
     code.launches.push_back(z);
     KernelLaunch p;
     p.entry = name + "_part";
-    p.grid_x = (uint32_t)nchunk;
+    p.grid_x = (uint32_t)nchunk_total;
     p.grid_y = (uint32_t)outer;
     p.label = c.label;
     p.cluster = ci;
-    p.args = {{KernelArg::NodeBuffer, values.node_id, 0}, {KernelArg::NodeBuffer, indices.node_id, 0}, {KernelArg::Scratch, -1, 0}};
-    p.algorithmic_bytes = chain_bytes(g, values) + chain_bytes(g, indices) + 2.0 * 4.0 * (double)total;
+    for (int s = 0; s < nsrc; ++s) {
+        p.args.push_back({KernelArg::NodeBuffer, c.inputs[2 * s].node_id, 0});
+        p.args.push_back({KernelArg::NodeBuffer, c.inputs[2 * s + 1].node_id, 0});
+    }
+    p.args.push_back({KernelArg::Scratch, -1, 0});
+    p.algorithmic_bytes = bytes;
     code.launches.push_back(p);
-    KernelLaunch s;
-    s.entry = name + "_sum";
-    s.grid_x = (uint32_t)div_round_up(total, 256);
-    s.label = "ScatterSum " + node.shape.str();
-    s.cluster = ci;
-    if (!acc_literal) s.args.push_back({KernelArg::NodeBuffer, c.copy_from, 0});
-    s.args.push_back({KernelArg::Scratch, -1, 0});
-    s.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
-    code.launches.push_back(s);
+    KernelLaunch sm;
+    sm.entry = name + "_sum";
+    sm.grid_x = (uint32_t)div_round_up(total, 256);
+    sm.label = "ScatterSum " + node.shape.str();
+    sm.cluster = ci;
+    if (!acc_literal) sm.args.push_back({KernelArg::NodeBuffer, c.copy_from, 0});
+    sm.args.push_back({KernelArg::Scratch, -1, 0});
+    sm.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
+    code.launches.push_back(sm);
     return code;
 }
 

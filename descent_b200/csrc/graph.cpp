@@ -537,6 +537,26 @@ void Graph::build_clusters() {
                 const OpEdge* acc = node.arg_edge(0);
                 DSC_CHECK(acc->chain.is_identity() || ops_.nodes[acc->src].op.kind == OpKind::Literal,
                           "scatter_add accumulator must be a plain array or a broadcast literal");
+                {
+                    // scatter_adds chained on one table (the four corners of a hash-grid cell,
+                    // examples/image_fit/main.rs:190-199) become one kernel: its chunk list is the concatenation of the
+                    // sources in chain order, so every row sees exactly the same addition order as the chained ops.
+                    const OpNode& acc_node = ops_.nodes[acc->src];
+                    if (acc_node.op.kind == OpKind::ScatterAdd && acc->chain.is_identity() && cons[acc->src].size() == 1 &&
+                        acc_node.cluster_id >= 0 && acc_node.op.axis == node.op.axis && acc_node.shape == node.shape) {
+                        Cluster& prev = clusters[acc_node.cluster_id];
+                        const size_t at = 2 * prev.members.size();
+                        const OpEdge* v = node.arg_edge(1);
+                        const OpEdge* ix = node.arg_edge(2);
+                        prev.inputs.insert(prev.inputs.begin() + at, ClusterInput{ix->src, ix->chain, ix->arg_shape});
+                        prev.inputs.insert(prev.inputs.begin() + at, ClusterInput{v->src, v->chain, v->arg_shape});
+                        prev.members.push_back(id);
+                        prev.outputs[0] = id;
+                        prev.level = level[id];
+                        node.cluster_id = acc_node.cluster_id;
+                        continue;
+                    }
+                }
                 add_input(*node.arg_edge(1));
                 add_input(*node.arg_edge(2));
                 if (ops_.nodes[acc->src].op.kind != OpKind::Literal) add_input(*acc);
