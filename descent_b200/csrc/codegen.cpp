@@ -1189,13 +1189,24 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part({{SRC_PARAMS}}fl
 
 // {{LABEL}}: accumulator + chunk partials in ascending chunk order
 extern "C" __global__ void __launch_bounds__(256) {{NAME}}_sum({{ACC_PARAM}}const float* partial, float* out0, const unsigned* dsc_step) {
+    // 32 table elements x 8 chunk lanes per CTA: lane g adds chunks g, g+8, ... in ascending order, then the eight
+    // lane sums are added to the accumulator in lane order -- a fixed order, independent of timing
     constexpr unsigned TOTAL = {{TOTAL}}u, NCHUNK = {{NCHUNK}}u;
-    const unsigned e = blockIdx.x * 256u + threadIdx.x;
-    if (e >= TOTAL) return;
+    __shared__ float red[8][32];
+    const unsigned tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+    const unsigned e = blockIdx.x * 32u + tx;
+    float part = 0.f;
+    if (e < TOTAL) {
+        #pragma unroll 4
+        for (unsigned c = ty; c < NCHUNK; c += 8u) part += partial[c * TOTAL + e];
+    }
+    red[ty][tx] = part;
+    __syncthreads();
+    if (ty != 0 || e >= TOTAL) return;
 {{ACC_CHAIN}}
     float acc = {{ACC_VALUE}};
-    #pragma unroll 4
-    for (unsigned c = 0; c < NCHUNK; ++c) acc += partial[c * TOTAL + e];
+    #pragma unroll
+    for (unsigned g = 0; g < 8u; ++g) acc += red[g][tx];
     out0[e] = acc;
 }
 )";
@@ -1274,7 +1285,7 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci) {
     code.launches.push_back(p);
     KernelLaunch sm;
     sm.entry = name + "_sum";
-    sm.grid_x = (uint32_t)div_round_up(total, 256);
+    sm.grid_x = (uint32_t)div_round_up(total, 32);
     sm.label = "ScatterSum " + node.shape.str();
     sm.cluster = ci;
     if (!acc_literal) sm.args.push_back({KernelArg::NodeBuffer, c.copy_from, 0});

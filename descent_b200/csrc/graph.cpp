@@ -9,6 +9,7 @@
 #include <map>
 #include <numeric>
 #include <queue>
+#include <set>
 #include <unordered_map>
 
 namespace descent {
@@ -466,13 +467,57 @@ void Graph::build_clusters() {
         level[id] = lv;
     }
 
-    // per-element clusters: connected components of fusable edges within a level
+    // per-element clusters: connected components of fusable edges within a level, then independent components of
+    // one level with the same element count are fused horizontally (they cannot depend on each other: any
+    // non-fusable edge climbs a level), which turns e.g. the ten hash-grid levels' identical index kernels into one
+    // launch.  Both level assignments are valid schedules; the one that yields fewer kernels is used.
     std::vector<int> parent(n);
-    std::iota(parent.begin(), parent.end(), 0);
     std::function<int(int)> find = [&](int x) { return parent[x] == x ? x : parent[x] = find(parent[x]); };
-    for (int id : order)
-        for (const auto& e : ops_.nodes[id].in)
-            if (edge_is_fusable(ops_, id, e) && level[id] == level[e.src]) parent[find(id)] = find(e.src);
+    auto cluster_with = [&](const std::vector<int>& lv) {
+        std::iota(parent.begin(), parent.end(), 0);
+        for (int id : order)
+            for (const auto& e : ops_.nodes[id].in)
+                if (edge_is_fusable(ops_, id, e) && lv[id] == lv[e.src]) parent[find(id)] = find(e.src);
+        // buffers a component binds: external producers + members someone outside reads
+        std::map<int, std::set<int>> ext_in, ext_out;
+        for (int id : order) {
+            const OpNode& node = ops_.nodes[id];
+            if (!node.op.is_per_element()) continue;
+            const int root = find(id);
+            for (const auto& e : node.in) {
+                const OpNode& s = ops_.nodes[e.src];
+                if (s.op.is_inline_source()) continue;
+                if (!(s.op.is_per_element() && find(e.src) == root && edge_is_fusable(ops_, id, e))) ext_in[root].insert(e.src);
+            }
+            for (auto [dst, k] : cons[id]) {
+                const OpNode& d = ops_.nodes[dst];
+                if (!(d.op.is_per_element() && find(dst) == root && edge_is_fusable(ops_, dst, d.in[k]))) ext_out[root].insert(id);
+            }
+        }
+        std::map<std::pair<int, int64_t>, std::pair<int, int>> open_group;  // (level, count) -> (root, buffers so far)
+        int kernels = 0;
+        for (int id : order) {
+            const OpNode& node = ops_.nodes[id];
+            if (!node.op.is_per_element() || find(id) != id) continue;
+            const int buffers = (int)(ext_in[id].size() + ext_out[id].size());
+            auto key = std::make_pair(lv[id], node.shape.element_count());
+            auto it = open_group.find(key);
+            if (it != open_group.end() && it->second.second + buffers <= 40) {
+                parent[id] = it->second.first;
+                it->second.second += buffers;
+            } else {
+                open_group[key] = {id, buffers};
+                kernels += 1;
+            }
+        }
+        return kernels;
+    };
+    {
+        const int with_alap = cluster_with(level);
+        const int with_asap = cluster_with(asap);
+        if (with_asap < with_alap) level = asap;
+        else cluster_with(level);
+    }
 
     std::map<int, int> root_to_cluster;
     std::vector<Cluster> clusters;
