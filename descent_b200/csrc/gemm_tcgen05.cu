@@ -283,14 +283,23 @@ extern "C" int dsc_gemm_tf32(dsc_ctx* ctx, uint64_t a, uint64_t b, uint64_t c, i
     if (a_mn) rc = dsc_internal_encode_tiled_2d_f32(&ma, a, (uint64_t)m, (uint64_t)k, (uint64_t)m * 4, 32, BK, 1);
     else rc = dsc_internal_encode_tiled_2d_f32(&ma, a, (uint64_t)k, (uint64_t)m, (uint64_t)k * 4, BK, BM, 0);
     if (rc) return rc;
-    constexpr int BN = 128;
+    // 128x256 tiles (4 stages, all 512 TMEM columns) halve the B-operand shared-memory traffic per MMA: with
+    // 128x128 tiles a tf32 MMA reads 8 KB per 64 cycles = the whole 128 B/clk of shared-memory bandwidth.
+    const bool wide = n >= 1024 && ((int64_t)((m + BM - 1) / BM) * ((n + 255) / 256)) >= sm_count;
+    const uint32_t bn = wide ? 256 : 128;
     if (b_mn) rc = dsc_internal_encode_tiled_2d_f32(&mb, b, (uint64_t)n, (uint64_t)k, (uint64_t)n * 4, 32, BK, 1);
-    else rc = dsc_internal_encode_tiled_2d_f32(&mb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 4, BK, BN, 0);
+    else rc = dsc_internal_encode_tiled_2d_f32(&mb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 4, BK, bn, 0);
     if (rc) return rc;
     float* cp = (float*)c;
-    constexpr int STAGES = 6;
-    if (!a_mn && !b_mn) return launch<BN, STAGES, false, false>(ctx, ma, mb, cp, (int)m, (int)n, (int)k, sm_count);
-    if (!a_mn && b_mn) return launch<BN, STAGES, false, true>(ctx, ma, mb, cp, (int)m, (int)n, (int)k, sm_count);
-    if (a_mn && !b_mn) return launch<BN, STAGES, true, false>(ctx, ma, mb, cp, (int)m, (int)n, (int)k, sm_count);
-    return launch<BN, STAGES, true, true>(ctx, ma, mb, cp, (int)m, (int)n, (int)k, sm_count);
+    const int mi = (int)m, ni = (int)n, ki = (int)k;
+    if (wide) {
+        if (!a_mn && !b_mn) return launch<256, 4, false, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
+        if (!a_mn && b_mn) return launch<256, 4, false, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
+        if (a_mn && !b_mn) return launch<256, 4, true, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
+        return launch<256, 4, true, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
+    }
+    if (!a_mn && !b_mn) return launch<128, 6, false, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
+    if (!a_mn && b_mn) return launch<128, 6, false, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
+    if (a_mn && !b_mn) return launch<128, 6, true, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
+    return launch<128, 6, true, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
 }

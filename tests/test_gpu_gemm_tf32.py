@@ -28,7 +28,7 @@ def device_gemm(d, env, a_store, b_store, m, n, k, a_is_mk, b_is_kn):
 
 @pytest.mark.parametrize("a_is_mk", [1, 0])
 @pytest.mark.parametrize("b_is_kn", [0, 1])
-@pytest.mark.parametrize("m,n,k", [(128, 128, 32), (256, 384, 160), (1024, 256, 4096), (1000, 300, 784), (1568, 128, 8192), (36, 12, 20)])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 32), (256, 384, 160), (1024, 256, 4096), (1000, 300, 784), (1568, 128, 8192), (36, 12, 20), (19072, 1024, 96)])
 def test_gemm_tf32_layouts(built_library, env, m, n, k, a_is_mk, b_is_kn):
     rng = np.random.default_rng(m + 3 * n + 7 * k + 2 * a_is_mk + b_is_kn)
     a = rng.standard_normal((m, k)).astype(np.float32)
