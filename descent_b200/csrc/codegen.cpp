@@ -181,6 +181,36 @@ int64_t chain_vector_run(const ViewChain& chain, int64_t innermost_extent) {
     return run;
 }
 
+// The same question for runs along another axis of the consumer's logical shape (e.g. along m of a GEMM operand
+// [b, m, k] whose memory is contiguous in m: the transposed operands of the weight-gradient GEMMs).  The
+// consumer-side view must have exactly that logical shape and must map the axis, with step 1, onto its innermost
+// input axis; from there on the innermost-axis conditions above apply.
+int64_t chain_vector_run_axis(const ViewChain& chain, const Shape& arg_shape, int axis) {
+    if (axis == arg_shape.len() - 1) return chain_vector_run(chain, arg_shape[axis]);
+    if (chain.views.empty()) return 1;  // row-major buffer: another axis is never the contiguous one
+    const View& v = chain.views.back();
+    if (v.output_shape != arg_shape) return 1;
+    auto pow2_divisor = [](int64_t r, int64_t x) {
+        x = x < 0 ? -x : x;
+        if (x == 0) return r;
+        while (r > 1 && x % r != 0) r /= 2;
+        return r;
+    };
+    int ai = v.input_shape.len() - 1;
+    while (ai > 0 && v.input_shape[ai] == 1) --ai;
+    const AxisMapping& m = v.output_mapping[axis];
+    if (!m.is_source || m.axis != ai || m.step != 1 || v.input_needs_clamp(ai)) return 1;
+    int64_t run = pow2_divisor(4, arg_shape[axis]);
+    run = pow2_divisor(run, v.input_shape[ai]);
+    run = pow2_divisor(run, v.input_offsets[ai]);
+    for (int i = 0; i < v.output_shape.len(); ++i)
+        if (i != axis && v.output_mapping[i].is_source && v.output_mapping[i].axis == ai && v.output_shape[i] > 1)
+            run = pow2_divisor(run, v.output_mapping[i].step);
+    ViewChain rest;
+    rest.views.assign(chain.views.begin(), chain.views.end() - 1);
+    return std::min(run, chain_vector_run(rest, v.input_shape[ai]));
+}
+
 double chain_bytes(const Graph& g, const ClusterInput& in) {
     (void)g;
     return 4.0 * (double)in.chain.addressed_count();
@@ -606,6 +636,9 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
 }
 )";
 
+#include "gemm_tc_template.inc"
+
+// (superseded by gemm_tc_template.inc; kept until the MN-major variant has soaked)
 // Tensor-core variant of the same GEMM for operands that need index arithmetic (conv2d's im2col view, grouped
 // and transposed views): all 256 threads gather the A/B tiles through their chains (4 consecutive k per thread,
 // one 128-bit shared store) into the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices),
@@ -898,7 +931,10 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
 
     // Operands behind view chains (conv2d's im2col, grouped / transposed views) use the gathered tcgen05 kernel
     // when TF32 is allowed and the GEMM is big enough to matter; otherwise the strict-FP32 SIMT kernel.
-    const bool tc = opt.use_tf32 && 2.0 * (double)BC * (double)M * (double)N * (double)K >= 5e7 && N >= 8 && M >= 128;
+    // shared-memory operand layout follows the direction that is contiguous in global memory
+    const bool a_mn = chain_vector_run_axis(a.chain, a.arg_shape, 2) < 4 && chain_vector_run_axis(a.chain, a.arg_shape, 1) == 4;
+    const bool b_mn = chain_vector_run_axis(b.chain, b.arg_shape, 1) < 4 && chain_vector_run_axis(b.chain, b.arg_shape, 2) == 4;
+    const bool tc = opt.use_tf32 && 2.0 * (double)BC * (double)M * (double)N * (double)K >= 5e7 && N >= 8 && (M >= 128 || (a_mn && K >= 1024));
     GemmTile t = choose_gemm_tile(M, N);
     if (tc) {
         t.bm = 128;
@@ -965,12 +1001,14 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     ClusterCode code;
     int64_t tmem_cols = 32;
     while (tmem_cols < t.bn) tmem_cols *= 2;
+    const bool a_vec = a_mn || (chain_vector_run_axis(a.chain, a.arg_shape, 2) == 4 && KC % 4 == 0);
+    const bool b_vec = b_mn || (chain_vector_run_axis(b.chain, b.arg_shape, 1) == 4 && KC % 4 == 0);
     if (tc)
-        code.source = subst(kMatMulTcTemplate,
+        code.source = subst(kMatMulTc2Template,
                             {{"LABEL", c.label}, {"NAME", name}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)},
-                             {"KC", num(KC)}, {"BC", num(BC)}, {"TMEM_COLS", num(tmem_cols)},
-                             {"A_VEC", chain_vector_run(a.chain, K) == 4 && KC % 4 == 0 ? "true" : "false"},
-                             {"B_VEC", chain_vector_run(b.chain, N) == 4 && false ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
+                             {"KC", num(KC)}, {"BC", num(BC)}, {"TMEM_COLS", num(tmem_cols)}, {"A_MN", a_mn ? "true" : "false"},
+                             {"B_MN", b_mn ? "true" : "false"}, {"A_LAYOUT", a_mn ? "MN-major" : "K-major"}, {"B_LAYOUT", b_mn ? "MN-major" : "K-major"},
+                             {"A_VEC", a_vec ? "true" : "false"}, {"B_VEC", b_vec ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
                              {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
     else
     code.source = subst(kMatMulTemplate,
@@ -986,7 +1024,13 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     l.grid_z = (uint32_t)S;
     l.block = t.nt;
     l.label = tc ? "TensorCore" + c.label : c.label;
-    if (tc) l.smem = (uint32_t)(2 * (t.bk / 4) * ((t.bm / 8) * 128 + 16 + (t.bn / 8) * 128 + 16) + 64);
+    if (tc) {  // mirrors A_BYTES / B_BYTES of the template: two stages each, barriers, 1 KB alignment slack
+        auto stage = [&](bool mn, int rows) {
+            const int64_t bytes = mn ? (int64_t)div_round_up(rows, 32) * t.bk * 128 : (int64_t)(t.bk / 4) * ((rows / 8) * 128 + 16);
+            return div_round_up(bytes, 1024) * 1024;
+        };
+        l.smem = (uint32_t)(2 * stage(a_mn, t.bm) + 2 * stage(b_mn, t.bn) + 64 + 1024);
+    }
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
     if (via_scratch) l.args.push_back({KernelArg::Scratch, -1, 0});
