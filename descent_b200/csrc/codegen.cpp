@@ -637,6 +637,7 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
 )";
 
 #include "gemm_tc_template.inc"
+#include "gemm_tc_async_template.inc"
 
 // (superseded by gemm_tc_template.inc; kept until the MN-major variant has soaked)
 // Tensor-core variant of the same GEMM for operands that need index arithmetic (conv2d's im2col view, grouped
@@ -1003,10 +1004,19 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     while (tmem_cols < t.bn) tmem_cols *= 2;
     const bool a_vec = a_mn || (chain_vector_run_axis(a.chain, a.arg_shape, 2) == 4 && KC % 4 == 0);
     const bool b_vec = b_mn || (chain_vector_run_axis(b.chain, b.arg_shape, 1) == 4 && KC % 4 == 0);
+    // shared-memory bytes of one pipeline stage (mirrors A_BYTES / B_BYTES of the templates)
+    auto stage_bytes = [&](bool mn, int rows) {
+        const int64_t bytes = mn ? (int64_t)div_round_up(rows, 32) * t.bk * 128 : (int64_t)(t.bk / 4) * ((rows / 8) * 128 + 16);
+        return div_round_up(bytes, 1024) * 1024;
+    };
+    const int64_t one_stage = tc ? stage_bytes(a_mn, t.bm) + stage_bytes(b_mn, t.bn) : 0;
+    const bool async_copy = tc && a_vec && b_vec;  // every unit is one aligned 16-byte run: cp.async pipeline
+    const int64_t k_tiles = div_round_up(std::min<int64_t>(KC, K), t.bk);
+    const int64_t stages = async_copy ? std::max<int64_t>(2, std::min<int64_t>({4, 196608 / std::max<int64_t>(one_stage, 1), k_tiles})) : 2;
     if (tc)
-        code.source = subst(kMatMulTc2Template,
+        code.source = subst(async_copy ? kMatMulTc3Template : kMatMulTc2Template,
                             {{"LABEL", c.label}, {"NAME", name}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)},
-                             {"KC", num(KC)}, {"BC", num(BC)}, {"TMEM_COLS", num(tmem_cols)}, {"A_MN", a_mn ? "true" : "false"},
+                             {"KC", num(KC)}, {"BC", num(BC)}, {"TMEM_COLS", num(tmem_cols)}, {"A_MN", a_mn ? "true" : "false"}, {"STAGES", num(stages)},
                              {"B_MN", b_mn ? "true" : "false"}, {"A_LAYOUT", a_mn ? "MN-major" : "K-major"}, {"B_LAYOUT", b_mn ? "MN-major" : "K-major"},
                              {"A_VEC", a_vec ? "true" : "false"}, {"B_VEC", b_vec ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
                              {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
@@ -1024,13 +1034,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     l.grid_z = (uint32_t)S;
     l.block = t.nt;
     l.label = tc ? "TensorCore" + c.label : c.label;
-    if (tc) {  // mirrors A_BYTES / B_BYTES of the template: two stages each, barriers, 1 KB alignment slack
-        auto stage = [&](bool mn, int rows) {
-            const int64_t bytes = mn ? (int64_t)div_round_up(rows, 32) * t.bk * 128 : (int64_t)(t.bk / 4) * ((rows / 8) * 128 + 16);
-            return div_round_up(bytes, 1024) * 1024;
-        };
-        l.smem = (uint32_t)(2 * stage(a_mn, t.bm) + 2 * stage(b_mn, t.bn) + 64 + 1024);
-    }
+    if (tc) l.smem = (uint32_t)(stages * one_stage + 64 + 1024);  // stages, barriers, 1 KB alignment slack
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
     if (via_scratch) l.args.push_back({KernelArg::Scratch, -1, 0});

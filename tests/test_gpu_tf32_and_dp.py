@@ -92,7 +92,7 @@ def test_two_gpu_data_parallel_matches_single_gpu(workload):
 
 # SIREN's first layer (x30 init) feeds sin() arguments of magnitude ~50: FP32 accumulation-order noise of the GEMM is
 # amplified by the oscillation, hence the wider bound there.
-@pytest.mark.parametrize("network,m,tol", [("conv-net", 64, 1e-4), ("conv-blur-net", 32, 1e-4), ("siren", 1024, 1e-3), ("multi-hash", 2048, 1e-4), ("relu-pe", 1024, 1e-4)])
+@pytest.mark.parametrize("network,m,tol", [("conv-net", 64, 1e-4), ("conv-blur-net", 32, 1e-4), ("siren", 1024, 1e-3), ("multi-hash", 2048, 3e-4), ("relu-pe", 1024, 1e-4)])
 def test_tf32_view_chain_gemms_match_tf32_oracle(env, network, m, tol):
     """conv2d as implicit GEMM (im2col view chain, grouped, replicate padding) and transposed dense GEMMs on the
     gathered tcgen05 kernel: one training step against the oracle with TF32 truncation on exactly those MatMuls."""
