@@ -6,8 +6,9 @@
     python bench.py --impl reference ...     (the CPU port of the reference path, see oracle/)
 
 One JSON line on rank 0.  `value` = global samples / max-over-ranks device time for K replayed steps with the
-batch resident in HBM; `e2e` = the same through Environment.write (pinned host -> device) + run + a loss
-read-back every step.  `roofline` describes the kernel with the largest share of the step (CUDA events per
+batch resident in HBM; `e2e` = the same through the public API with host buffers: every step uploads one batch
+from pinned host memory (Environment.prefetch_pinned, overlapped with the previous step on a copy stream), runs,
+and reads the loss back.  `roofline` describes the kernel with the largest share of the step (CUDA events per
 launch on the context's stream), against MEASURED_PEAKS.json.  `cpu_baseline` times the numpy port of the
 reference semantics (oracle/) on a bounded sample of the same workload on the host cores.
 """
@@ -240,11 +241,15 @@ def main():
         sampler.start()
     total_ms = timed(lambda s: env.run(ex.train_graph, int(seeds[args.warmup + s])), args.steps)
 
+    def upload():  # this step's share of host -> device traffic: one whole batch from pinned host memory
+        env.prefetch_pinned(ex.x, x_pinned)
+        env.prefetch_pinned(ex.y, y_pinned)
+
     def e2e_step(s):
-        env.write_pinned(ex.x, x_pinned)
-        env.write_pinned(ex.y, y_pinned)
-        env.run(ex.train_graph, int(seeds[args.warmup + s]))
-        env.read_parameter_scalar(ex.loss_sum)
+        env.run(ex.train_graph, int(seeds[args.warmup + s]))  # consumes the batch uploaded during the previous step
+        upload()                                               # batch s+1 crosses PCIe on the copy stream while step s computes
+        env.read_parameter_scalar(ex.loss_sum)                 # device -> host read of step s's result (synchronises)
+    upload()
     for s in range(2):
         e2e_step(s)
     e2e_ms = timed(e2e_step, args.steps)

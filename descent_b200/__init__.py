@@ -174,6 +174,10 @@ class Environment:
         a = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
         _check(lib.dsc_env_write_parameter(self._h, param.id, a.ctypes.data_as(c_f32_p), ctypes.c_size_t(a.size), 1 if pinned else 0))
 
+    def prefetch_pinned(self, param, pinned_array):
+        """Start copying the next batch while earlier runs execute; it lands in `param` at the next run()."""
+        _check(lib.dsc_env_prefetch_parameter(self._h, param.id, pinned_array.ctypes.data_as(c_f32_p), ctypes.c_size_t(pinned_array.size)))
+
     def write_pinned(self, param, pinned_array):
         _check(lib.dsc_env_write_parameter(self._h, param.id, pinned_array.ctypes.data_as(c_f32_p), ctypes.c_size_t(pinned_array.size), 1))
 

@@ -110,6 +110,9 @@ int dsc_env_parameter_info(dsc_env* env, int param, int64_t* shape7, int* ndim, 
 int dsc_env_write_parameter(dsc_env* env, int param, const float* data, size_t count, int pinned) {
     return guarded([&] { env->env->write_parameter(env->param(param), data, count, pinned != 0); });
 }
+int dsc_env_prefetch_parameter(dsc_env* env, int param, const float* pinned_data, size_t count) {
+    return guarded([&] { env->env->prefetch_parameter(env->param(param), pinned_data, count); });
+}
 int dsc_env_read_parameter(dsc_env* env, int param, float* dst, size_t count) {
     return guarded([&] { env->env->read_parameter(env->param(param), dst, count); });
 }
@@ -165,7 +168,8 @@ int dsc_env_profile(dsc_env* env, dsc_graphdef* graph, uint32_t rand_seed, int i
         for (size_t i = 0; i < timings.size(); ++i) {
             const auto& t = timings[i];
             os << (i ? "," : "") << "{\"label\":\"" << t.label << "\",\"entry\":\"" << t.entry << "\",\"cluster\":" << t.cluster << ",\"ms\":" << t.ms
-               << ",\"bytes\":" << t.algorithmic_bytes << ",\"flops\":" << t.flops << "}";
+               << ",\"bytes\":" << t.algorithmic_bytes << ",\"flops\":" << t.flops << ",\"grid\":[" << t.grid[0] << "," << t.grid[1] << "," << t.grid[2]
+               << "],\"block\":" << t.block << ",\"smem\":" << t.smem << "}";
         }
         os << "]";
         *json_out = dup_string(os.str());

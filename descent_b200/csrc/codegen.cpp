@@ -6,6 +6,7 @@
 #include "codegen.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 
 namespace descent {
@@ -639,225 +640,6 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
 #include "gemm_tc_template.inc"
 #include "gemm_tc_async_template.inc"
 
-// (superseded by gemm_tc_template.inc; kept until the MN-major variant has soaked)
-// Tensor-core variant of the same GEMM for operands that need index arithmetic (conv2d's im2col view, grouped
-// and transposed views): all 256 threads gather the A/B tiles through their chains (4 consecutive k per thread,
-// one 128-bit shared store) into the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices),
-// one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into a TMEM accumulator and commits to an
-// mbarrier; the gather of tile i+1 overlaps the MMAs of tile i (two smem stages).  Epilogue: tcgen05.ld.
-const char* kMatMulTcTemplate = R"(
-// {{LABEL}}  [tcgen05 tf32]
-extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* A, const float* B, float* C, const unsigned* dsc_step) {
-    constexpr int BM = 128, BN = {{BN}}, BK = {{BK}}, NT = 256;
-    constexpr int M = {{M}}, N = {{N}}, K = {{K}}, KC = {{KC}}, BC = {{BC}};
-    constexpr int TILES_N = (N + BN - 1) / BN;
-    constexpr int KQ = BK / 4;                              // 16-byte k-chunks per tile row
-    constexpr int A_UNITS = BM * KQ, B_UNITS = BN * KQ;     // one unit = 4 consecutive k of one row
-    constexpr int LA = (A_UNITS + NT - 1) / NT, LB = (B_UNITS + NT - 1) / NT;
-    // k-chunk stride (LBO) and 8-row-group stride (SBO); LBO carries 16 bytes of padding so that lanes storing
-    // consecutive k-chunks of one row hit different banks
-    constexpr unsigned A_LBO = (BM / 8) * 128 + 16, B_LBO = (BN / 8) * 128 + 16, SBO = 128;
-    constexpr unsigned A_BYTES = KQ * A_LBO, B_BYTES = KQ * B_LBO;
-    constexpr unsigned TMEM_COLS = {{TMEM_COLS}};
-    constexpr bool A_VEC = {{A_VEC}}, B_VEC = {{B_VEC}};  // aligned groups of 4 k are provably contiguous in memory
-    constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
-    extern __shared__ __align__(128) unsigned char dsc_smem[];
-    unsigned char* sa = dsc_smem;                 // 2 stages of A
-    unsigned char* sb = dsc_smem + 2 * A_BYTES;   // 2 stages of B
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(dsc_smem + 2 * A_BYTES + 2 * B_BYTES);
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile_m = blockIdx.x / TILES_N, tile_n = blockIdx.x % TILES_N;
-    const int batch = blockIdx.y, split = blockIdx.z;
-    const int m0 = tile_m * BM, n0 = tile_n * BN;
-    const int k_begin = split * KC;
-    const int k_end = min(K, k_begin + KC);
-    const unsigned sa_addr = (unsigned)__cvta_generic_to_shared(sa), sb_addr = (unsigned)__cvta_generic_to_shared(sb);
-    const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(bars);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr + 8));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(tmem_slot)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tmem_d = *tmem_slot;
-
-    float4 ra[LA], rb[LB];
-    // One unit = 4 consecutive k of one row.  Lanes walk k first (consecutive 16-byte chunks of the same row are
-    // usually adjacent in memory: channels of one pixel, then the next pixel), and a unit whose four source
-    // addresses turn out contiguous and 16-byte aligned is fetched with a single 128-bit load.
-    auto load_tile = [&](int k0) {
-        #pragma unroll
-        for (int j = 0; j < LA; ++j) {
-            const int u = tid + j * NT;
-            const int lq = u % KQ, lm = u / KQ;
-            const int gm = m0 + lm;
-            unsigned ai[4] = {0u, 0u, 0u, 0u};
-            bool av[4] = {false, false, false, false};
-            if (A_VEC) {
-                const int gk = k0 + lq * 4;
-                ra[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((A_UNITS % NT == 0 || u < A_UNITS) && gm < M && gk < k_end) {
-{{A_CHAIN}}
-                    const float* src = A + {{A_IDX}};
-                    if (gk + 3 < k_end) ra[j] = *reinterpret_cast<const float4*>(src);
-                    else ra[j] = make_float4(src[0], gk + 1 < k_end ? src[1] : 0.f, gk + 2 < k_end ? src[2] : 0.f, 0.f);
-                }
-                continue;
-            }
-            if ((A_UNITS % NT == 0 || u < A_UNITS) && gm < M) {
-                #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int gk = k0 + lq * 4 + q;
-                    if (gk < k_end) {
-{{A_CHAIN}}
-                        ai[q] = {{A_IDX}};
-                        av[q] = true;
-                    }
-                }
-            }
-            if (av[3] && ai[1] == ai[0] + 1u && ai[2] == ai[0] + 2u && ai[3] == ai[0] + 3u && (ai[0] & 3u) == 0u)
-                ra[j] = *reinterpret_cast<const float4*>(A + ai[0]);
-            else
-                ra[j] = make_float4(av[0] ? A[ai[0]] : 0.f, av[1] ? A[ai[1]] : 0.f, av[2] ? A[ai[2]] : 0.f, av[3] ? A[ai[3]] : 0.f);
-        }
-        #pragma unroll
-        for (int j = 0; j < LB; ++j) {
-            const int u = tid + j * NT;
-            const int lq = u % KQ, ln = u / KQ;
-            const int gn = n0 + ln;
-            unsigned bi[4] = {0u, 0u, 0u, 0u};
-            bool bv[4] = {false, false, false, false};
-            if (B_VEC) {
-                const int gk = k0 + lq * 4;
-                rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((B_UNITS % NT == 0 || u < B_UNITS) && gn < N && gk < k_end) {
-{{B_CHAIN}}
-                    const float* src = B + {{B_IDX}};
-                    if (gk + 3 < k_end) rb[j] = *reinterpret_cast<const float4*>(src);
-                    else rb[j] = make_float4(src[0], gk + 1 < k_end ? src[1] : 0.f, gk + 2 < k_end ? src[2] : 0.f, 0.f);
-                }
-                continue;
-            }
-            if ((B_UNITS % NT == 0 || u < B_UNITS) && gn < N) {
-                #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int gk = k0 + lq * 4 + q;
-                    if (gk < k_end) {
-{{B_CHAIN}}
-                        bi[q] = {{B_IDX}};
-                        bv[q] = true;
-                    }
-                }
-            }
-            if (bv[3] && bi[1] == bi[0] + 1u && bi[2] == bi[0] + 2u && bi[3] == bi[0] + 3u && (bi[0] & 3u) == 0u)
-                rb[j] = *reinterpret_cast<const float4*>(B + bi[0]);
-            else
-                rb[j] = make_float4(bv[0] ? B[bi[0]] : 0.f, bv[1] ? B[bi[1]] : 0.f, bv[2] ? B[bi[2]] : 0.f, bv[3] ? B[bi[3]] : 0.f);
-        }
-    };
-    auto store_tile = [&](int buf) {
-        #pragma unroll
-        for (int j = 0; j < LA; ++j) {
-            const int u = tid + j * NT;
-            const int lq = u % KQ, lm = u / KQ;
-            if (A_UNITS % NT == 0 || u < A_UNITS)
-                *reinterpret_cast<float4*>(sa + buf * A_BYTES + lq * A_LBO + (lm >> 3) * SBO + (lm & 7) * 16) = ra[j];
-        }
-        #pragma unroll
-        for (int j = 0; j < LB; ++j) {
-            const int u = tid + j * NT;
-            const int lq = u % KQ, ln = u / KQ;
-            if (B_UNITS % NT == 0 || u < B_UNITS)
-                *reinterpret_cast<float4*>(sb + buf * B_BYTES + lq * B_LBO + (ln >> 3) * SBO + (ln & 7) * 16) = rb[j];
-        }
-    };
-    auto wait_bar = [&](int buf, unsigned parity) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "DSC_WAIT:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-            "@p bra DSC_DONE;\n"
-            "bra DSC_WAIT;\n"
-            "DSC_DONE:\n"
-            "}\n" ::"r"(bar_addr + 8u * buf), "r"(parity) : "memory");
-    };
-    const int num_tiles = (k_end - k_begin + BK - 1) / BK;
-    for (int it = 0; it < num_tiles; ++it) {
-        const int buf = it & 1;
-        load_tile(k_begin + it * BK);
-        if (it >= 2) wait_bar(buf, (unsigned)((it >> 1) - 1) & 1u);  // the MMAs that read this stage have retired
-        store_tile(buf);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            #pragma unroll
-            for (int kk = 0; kk < BK / 8; ++kk) {
-                const unsigned a_addr = sa_addr + buf * A_BYTES + kk * 2 * A_LBO;
-                const unsigned b_addr = sb_addr + buf * B_BYTES + kk * 2 * B_LBO;
-                const unsigned long long adesc = (unsigned long long)((a_addr >> 4) & 0x3fff) | ((unsigned long long)((A_LBO >> 4) & 0x3fff) << 16) |
-                                                 ((unsigned long long)((SBO >> 4) & 0x3fff) << 32) | (1ull << 46);
-                const unsigned long long bdesc = (unsigned long long)((b_addr >> 4) & 0x3fff) | ((unsigned long long)((B_LBO >> 4) & 0x3fff) << 16) |
-                                                 ((unsigned long long)((SBO >> 4) & 0x3fff) << 32) | (1ull << 46);
-                const unsigned accumulate = (it | kk) != 0 ? 1u : 0u;
-                asm volatile(
-                    "{\n"
-                    ".reg .pred p;\n"
-                    "setp.ne.b32 p, %4, 0;\n"
-                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-                    "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr + 8u * buf) : "memory");
-        }
-    }
-    if (num_tiles > 0) wait_bar((num_tiles - 1) & 1, (unsigned)((num_tiles - 1) >> 1) & 1u);  // the last commit covers every MMA
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // epilogue: warp w reads the 32 TMEM lanes of quadrant w%4, 16 columns at a time
-    const int quad = warp & 3;
-    const int gm = m0 + quad * 32 + lane;
-    for (int c0 = (warp >> 2) * 16; c0 < BN; c0 += 32) {
-        unsigned v[16];
-        const unsigned taddr = tmem_d + ((unsigned)(quad * 32) << 16) + (unsigned)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-              "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (gm < M && num_tiles > 0) {
-            float* crow = C + {{C_ROW}};
-            const int gn0 = n0 + c0;
-            if (N % 4 == 0) {
-                #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    if (gn0 + j < N)
-                        *reinterpret_cast<float4*>(crow + gn0 + j) =
-                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            } else {
-                #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (gn0 + j < N) crow[gn0 + j] = __uint_as_float(v[j]);
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
-    }
-}
-)";
-
 const char* kSplitSumTemplate = R"(
 // split-K partial sums of {{LABEL}}, added in ascending split order
 extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws, float* out0, const unsigned* dsc_step) {
@@ -943,7 +725,8 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
         t.nt = 256;
         t.tm = t.tn = 0;
         int64_t best_padded = INT64_MAX;
-        for (int bk = 8; bk <= 64; bk += 8) {  // least zero padding of K, then the deepest tile
+        for (int bk = 8; bk <= 96; bk += 8) {  // least zero padding of K, then the deepest tile
+            if (bk > 64 && (128 + t.bn) * bk > 12 * 1024) break;  // staging registers: at most 12 float4 per thread beyond BK 64
             const int64_t padded = div_round_up(K, bk) * bk;
             if (padded <= best_padded) { best_padded = padded; t.bk = bk; }
         }
@@ -1010,8 +793,10 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
         return div_round_up(bytes, 1024) * 1024;
     };
     const int64_t one_stage = tc ? stage_bytes(a_mn, t.bm) + stage_bytes(b_mn, t.bn) : 0;
-    const bool async_copy = tc && a_vec && b_vec;  // every unit is one aligned 16-byte run: cp.async pipeline
     const int64_t k_tiles = div_round_up(std::min<int64_t>(KC, K), t.bk);
+    // every unit is one aligned 16-byte run and the k loop is long enough to fill a pipeline: cp.async stages;
+    // short-K GEMMs (convolution forward / backward-input) use the persistent register-staged kernel instead
+    const bool async_copy = tc && a_vec && b_vec && k_tiles >= 8;
     const int64_t stages = async_copy ? std::max<int64_t>(2, std::min<int64_t>({4, 196608 / std::max<int64_t>(one_stage, 1), k_tiles})) : 2;
     if (tc)
         code.source = subst(async_copy ? kMatMulTc3Template : kMatMulTc2Template,
@@ -1030,6 +815,16 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     KernelLaunch l;
     l.entry = name;
     l.grid_x = (uint32_t)(div_round_up(M, t.bm) * div_round_up(N, t.bn));
+    if (tc && !async_copy && t.bn <= 32) {
+        // Persistent over output tiles when the accumulator is narrow: each CTA loops over tiles blockIdx.x,
+        // blockIdx.x + gridDim.x, ... and gathers the next tile's operands while the previous accumulator drains.
+        // Measured on B200 (conv-net, m=8192): conv1 forward 0.29 -> 0.19 ms, conv2 forward 0.30 -> 0.26 ms.  Wide
+        // accumulators (conv2 backward-input, N=72) lose: the fence.proxy.async ahead of the next MMA then also
+        // waits for the previous tile's many global stores (0.31 -> 0.41 ms), so those stay one tile per CTA.
+        const int64_t smem = stages * one_stage + 64 + 1024;
+        const int64_t resident = std::max<int64_t>(1, std::min<int64_t>({8, (200 * 1024) / smem, 512 / tmem_cols}));
+        l.grid_x = (uint32_t)std::min<int64_t>(l.grid_x, (int64_t)opt.sm_count * resident);
+    }
     l.grid_y = (uint32_t)BC;
     l.grid_z = (uint32_t)S;
     l.block = t.nt;

@@ -8,6 +8,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 
 namespace descent {
@@ -130,6 +131,7 @@ Environment::~Environment() {
         live_execs_.clear();
         for (auto& p : *parameters_)
             if (p.buffer) dsc_free(ctx_, p.buffer);
+        for (auto& f : prefetches_) dsc_free(ctx_, f.staging);
         dsc_ctx_destroy(ctx_);
     }
 }
@@ -154,8 +156,34 @@ Parameter Environment::static_parameter_with_data(const Shape& shape, const std:
 }
 uint64_t Environment::parameter_buffer(const Parameter& p) const { return (*parameters_)[p.checked_id(parameters_)].buffer; }
 
+void Environment::prefetch_parameter(const Parameter& p, const float* pinned_data, size_t count) {
+    require_device("prefetch_parameter");
+    const int id = p.checked_id(parameters_);
+    const ParameterStorage& s = (*parameters_)[id];
+    DSC_CHECK(count == (size_t)s.shape.element_count(), "prefetch_parameter writes whole parameters: '" << s.name << "' has "
+                                                            << s.shape.element_count() << " elements, got " << count);
+    auto it = std::find_if(prefetches_.begin(), prefetches_.end(), [&](const Prefetch& f) { return f.param == id; });
+    if (it == prefetches_.end()) {
+        Prefetch f{id, 0, count * 4, false};
+        check(dsc_alloc(ctx_, f.bytes, &f.staging));
+        check(dsc_sync(ctx_));  // the allocation is ordered on the compute stream; the copy stream is about to use it
+        prefetches_.push_back(f);
+        it = prefetches_.end() - 1;
+    }
+    check(dsc_prefetch(ctx_, it->staging, pinned_data, it->bytes));
+    it->pending = true;
+}
+void Environment::commit_prefetches(int only_param) {
+    for (Prefetch& f : prefetches_) {
+        if (!f.pending || (only_param >= 0 && f.param != only_param)) continue;
+        check(dsc_prefetch_commit(ctx_, (*parameters_)[f.param].buffer, f.staging, f.bytes));
+        f.pending = false;
+    }
+}
+
 void Environment::write_parameter(const Parameter& p, const float* data, size_t count, bool pinned) {
     if (!ctx_) return;  // host-only tracing: module/optimizer constructors may "write" initial state; nothing can read it back
+    commit_prefetches(p.checked_id(parameters_));
     const ParameterStorage& s = (*parameters_)[p.checked_id(parameters_)];
     const size_t total = (size_t)s.shape.element_count();
     DSC_CHECK(count <= total, "writing " << count << " floats into parameter '" << s.name << "' of " << total);
@@ -163,6 +191,7 @@ void Environment::write_parameter(const Parameter& p, const float* data, size_t 
 }
 void Environment::read_parameter(const Parameter& p, float* dst, size_t count) {
     require_device("read_parameter");
+    commit_prefetches(p.checked_id(parameters_));
     const ParameterStorage& s = (*parameters_)[p.checked_id(parameters_)];
     DSC_CHECK(count <= (size_t)s.shape.element_count(), "reading past the end of parameter '" << s.name << "'");
     check(dsc_download(ctx_, s.buffer, 0, dst, count * 4));
@@ -444,6 +473,7 @@ void Environment::launch_all(GraphExec& exec, std::vector<float>* per_launch_ms)
 
 void Environment::run(const Graph& graph, uint32_t rand_seed) {
     GraphExec& exec = prepare(graph);
+    commit_prefetches();
     if (profile_runs_) {
         check(dsc_set_rand_seed(ctx_, rand_seed));
         std::vector<float> ms;
@@ -485,6 +515,8 @@ std::vector<KernelTiming> Environment::profile(const Graph& graph, uint32_t rand
         out[i].cluster = exec.launches[i].cluster;
         out[i].algorithmic_bytes = exec.launches[i].algorithmic_bytes;
         out[i].flops = exec.launches[i].flops;
+        out[i].grid[0] = exec.launches[i].gx; out[i].grid[1] = exec.launches[i].gy; out[i].grid[2] = exec.launches[i].gz;
+        out[i].block = exec.launches[i].block; out[i].smem = exec.launches[i].smem;
     }
     for (int it = 0; it < iterations; ++it) {
         check(dsc_set_rand_seed(ctx_, rand_seed + (uint32_t)it));

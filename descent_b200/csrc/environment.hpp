@@ -40,6 +40,7 @@ struct KernelTiming {
     std::string entry;
     int cluster = -1;
     double ms = 0;  // average per launch
+    uint32_t grid[3] = {0, 0, 0}, block = 0, smem = 0;
     double algorithmic_bytes = 0;
     double flops = 0;
 };
@@ -67,6 +68,10 @@ public:
     // ParameterWriter (environment.rs:42-61): write `count` floats from the start, zero-fill the rest
     void write_parameter(const Parameter& p, const float* data, size_t count, bool data_is_pinned = false);
     void zero_fill(const Parameter& p) { write_parameter(p, nullptr, 0); }
+    // Asynchronous whole-parameter write from pinned host memory: the host -> device copy runs on a second
+    // stream while earlier graphs execute, and lands in the parameter just before the next run() / read /
+    // write.  `data` must stay untouched until that run has been issued.
+    void prefetch_parameter(const Parameter& p, const float* pinned_data, size_t count);
     // ParameterReader
     void read_parameter(const Parameter& p, float* dst, size_t count);
     std::vector<float> read_parameter_to_vec(const Parameter& p);
@@ -106,6 +111,10 @@ private:
     GraphExec& prepare(const Graph& graph);
     void require_device(const char* what) const;
     void launch_all(GraphExec& exec, std::vector<float>* per_launch_ms);
+    void commit_prefetches(int only_param = -1);
+
+    struct Prefetch { int param; uint64_t staging; size_t bytes; bool pending; };
+    std::vector<Prefetch> prefetches_;  // one staging buffer per prefetched parameter, reused every step
 
     dsc_ctx* ctx_ = nullptr;
     int sm_count_ = 148;

@@ -139,6 +139,9 @@ struct dsc_ctx {
     char* staging[kStagingSlots] = {nullptr, nullptr};
     cudaEvent_t staging_done[kStagingSlots] = {nullptr, nullptr};
     int staging_next = 0;
+    cudaStream_t copy_stream = nullptr;   // host -> device prefetch of the next batch, overlapping the running graph
+    cudaEvent_t prefetch_done = nullptr;  // recorded on copy_stream after a prefetch
+    cudaEvent_t staged_read = nullptr;    // recorded on stream after a commit read the staging buffer
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
     bool capturing = false;
@@ -182,6 +185,9 @@ int dsc_ctx_create(int device, dsc_ctx** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->prefetch_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->staged_read, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;  // keep freed memory cached in the pool: alloc/free cost no driver calls
@@ -206,6 +212,10 @@ int dsc_ctx_destroy(dsc_ctx* ctx) {
         if (ctx->staging_done[i]) cudaEventDestroy(ctx->staging_done[i]);
     }
     cudaFree(ctx->step_params);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaEventDestroy(ctx->prefetch_done);
+    cudaEventDestroy(ctx->staged_read);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DSC_OK;
@@ -267,6 +277,20 @@ int dsc_upload(dsc_ctx* ctx, uint64_t id, size_t offset, const void* src, size_t
         }
     }
     if (zero_tail_to > offset + n) CUDA_TRY(cudaMemsetAsync(dst + n, 0, zero_tail_to - offset - n, ctx->stream));
+    return DSC_OK;
+}
+int dsc_prefetch(dsc_ctx* ctx, uint64_t staging, const void* pinned_src, size_t n) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->staged_read, 0));  // the last commit has finished reading the staging buffers
+    if (n) CUDA_TRY(cudaMemcpyAsync((void*)staging, pinned_src, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(cudaEventRecord(ctx->prefetch_done, ctx->copy_stream));
+    return DSC_OK;
+}
+int dsc_prefetch_commit(dsc_ctx* ctx, uint64_t dst, uint64_t staging, size_t n) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->prefetch_done, 0));
+    if (n) CUDA_TRY(cudaMemcpyAsync((void*)dst, (const void*)staging, n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->staged_read, ctx->stream));
     return DSC_OK;
 }
 int dsc_download(dsc_ctx* ctx, uint64_t id, size_t offset, void* dst, size_t n) {

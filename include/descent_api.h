@@ -41,6 +41,11 @@ int dsc_env_trainable_parameter(dsc_env* env, const int64_t* shape, int ndim, co
 int dsc_env_parameter_count(dsc_env* env, int* count);
 int dsc_env_parameter_info(dsc_env* env, int param, int64_t* shape7, int* ndim, char* name64, int* trainable);
 int dsc_env_write_parameter(dsc_env* env, int param, const float* data, size_t count, int data_is_pinned);  /* writer :160, zero-fills the tail */
+/* Asynchronous writer for the next mini-batch: `pinned_data` (from dsc_host_alloc, `count` = the whole parameter)
+ * is copied on a second stream while earlier runs execute and becomes the parameter's contents at the next
+ * dsc_env_run / read / write.  Plays the role of the reference's staging ring (staging.rs:100-140), which lets
+ * the host fill batch i+1 while the GPU consumes batch i. */
+int dsc_env_prefetch_parameter(dsc_env* env, int param, const float* pinned_data, size_t count);
 int dsc_env_read_parameter(dsc_env* env, int param, float* dst, size_t count);                               /* reader :175 */
 int dsc_env_reset_parameter(dsc_env* env, int param, uint64_t* rng_state);                                   /* reset_parameter :190 */
 int dsc_env_scope(dsc_env* env, dsc_scope** out);                                                            /* scope :231 */

@@ -56,6 +56,13 @@ int dsc_copy(dsc_ctx* ctx, uint64_t dst, uint64_t src, size_t bytes);
  * until dsc_sync or a later download); otherwise the bytes are staged through the context's pinned
  * ring and `src` is free on return. */
 int dsc_upload(dsc_ctx* ctx, uint64_t id, size_t offset, const void* src, size_t n, size_t zero_tail_to, int src_is_pinned);
+/* Double-buffered form of the StagingWriter for the next mini-batch (the reference's staging ring overlaps
+ * host writes with GPU work the same way, staging.rs:100-140).  dsc_prefetch copies n bytes of pinned host
+ * memory into the device buffer `staging` on the context's copy stream, concurrently with whatever runs on
+ * the compute stream; dsc_prefetch_commit makes the compute stream wait for every prefetch issued so far and
+ * copies staging -> dst device-side.  A later dsc_prefetch waits for the last commit before overwriting. */
+int dsc_prefetch(dsc_ctx* ctx, uint64_t staging, const void* pinned_src, size_t n);
+int dsc_prefetch_commit(dsc_ctx* ctx, uint64_t dst, uint64_t staging, size_t n);
 /* StagingReader (staging.rs:198-302): blocks until the bytes are on the host. */
 int dsc_download(dsc_ctx* ctx, uint64_t id, size_t offset, void* dst, size_t n);
 int dsc_host_alloc(size_t bytes, void** out); /* pinned host memory */

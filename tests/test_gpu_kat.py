@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+import descent_b200 as d
 from reference_kats import ALL_CASES, TEST_RAND_SEED, instantiate
 from test_oracle_kat import HASH_VECTORS, hash_indices_graph
 
@@ -21,6 +22,29 @@ def test_writer_zero_fills_tail(env):  # staging.rs:181-187
     env.write(a, np.ones(16, np.float32))
     env.zero_fill(a)
     np.testing.assert_array_equal(env.read_parameter_to_vec(a), np.zeros(16, np.float32))
+
+
+def test_prefetch_lands_at_the_next_run(env):
+    """Environment.prefetch_pinned: batch i+1 crosses PCIe on the copy stream while batch i is in use; the parameter
+    only changes at the next run (the staging ring of staging.rs:100-140 gives the reference the same overlap)."""
+    n = 1 << 20
+    x = env.static_parameter([n], "x")
+    y = env.static_parameter([n], "y")
+    scope = env.scope()
+    scope.write_parameter_value(y, scope.parameter_value(x) * 2.0 + 1.0)
+    g = scope.build_graph()
+    host = d.pinned_array(n)
+    first = np.arange(n, dtype=np.float32)
+    env.write(x, first)
+    for step in range(4):
+        host[:] = np.float32(step) - first
+        env.prefetch_pinned(x, host)
+        if step == 0:  # nothing ran yet: reading the parameter itself forces the pending copy to land
+            np.testing.assert_array_equal(env.read_parameter_to_vec(x), host)
+        env.run(g, TEST_RAND_SEED)
+        np.testing.assert_array_equal(env.read_parameter_to_vec(y), host * np.float32(2.0) + np.float32(1.0))
+    with pytest.raises(d.DescentError):
+        env.prefetch_pinned(x, d.pinned_array(n // 2))  # whole parameters only
 
 
 @pytest.mark.parametrize("use_cuda_graph", [True, False])
