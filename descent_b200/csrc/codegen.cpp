@@ -531,7 +531,7 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
             {{A_DECODE}}
             const int gm = m0 + lm, gk = k0 + lk;
             float v = 0.f;
-            if ((BM * BK % NT == 0 || i < BM * BK) && gm < M && gk < k_end) {
+            if ((BM * BK % NT == 0 || i < BM * BK) && gm < M && gk < k_end && ({{A_VALID}})) {
 {{A_CHAIN}}
                 v = A[{{A_IDX}}];
             }
@@ -639,6 +639,7 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
 
 #include "gemm_tc_template.inc"
 #include "gemm_tc_async_template.inc"
+#include "conv_bwd_input_template.inc"
 
 const char* kSplitSumTemplate = R"(
 // split-K partial sums of {{LABEL}}, added in ascending split order
@@ -672,14 +673,75 @@ GemmTile choose_gemm_tile(int64_t M, int64_t N) {
     return t;
 }
 
+
+// conv2d backward-input as a halo-tiled implicit GEMM (conv_bwd_input_template.inc); returns false when the shape
+// falls outside what that kernel covers and the gathered GEMM should be used instead
+bool gen_conv_backward_input(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, ClusterCode* out) {
+    const auto& cbi = c.conv_backward_input;
+    const ClusterInput& a = cbi.unfused[0];
+    const ClusterInput& b = cbi.unfused[1];
+    const int64_t G = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
+    const int64_t IH = cbi.in_h, IW = cbi.in_w, OH = cbi.out_h, OW = cbi.out_w, FH = cbi.filter_h, FW = cbi.filter_w;
+    const int64_t GC = N / (FH * FW), images = M / (OH * OW);
+    if (IW > 128 || 128 % IW != 0 || IW != OW + FW - 1 || IH != OH + FH - 1) return false;
+    if (K % 8 != 0 || GC % 4 != 0 || GC > 256) return false;
+    if (chain_vector_run_axis(a.chain, a.arg_shape, 2) != 4) return false;
+    const int64_t BN = div_round_up(GC, 16) * 16;
+    int64_t tmem_cols = 32;
+    while (tmem_cols < G * BN) tmem_cols *= 2;
+    if (tmem_cols > 512) return false;
+    const int64_t TH = 128 / IW, halo_rows = TH + FH - 1, Q = G * K / 4;
+    const int64_t npix = div_round_up((FW - 1) + halo_rows * IW, 8) * 8 + 1;
+    const int64_t a_bytes = div_round_up(Q * npix * 16, 128) * 128, b_bytes = G * FH * FW * (K / 4) * BN * 16;
+    const int64_t smem = a_bytes + b_bytes + 64 + 128;
+    if (smem > 160 * 1024 || halo_rows * IW * Q > 256 * 16) return false;  // operands must fit; at most 16 staged loads per thread
+    const int64_t tiles = images * div_round_up(IH, TH);
+
+    int uniq = 0;
+    std::ostringstream ca, cb;
+    std::string ia = emit_chain(ca, a.chain, {{"batch", M * K, G}, {"gm", K, M}, {"gk", 1, K}}, uniq, "                ");
+    std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, G}, {"gk", N, K}, {"gn", 1, N}}, uniq, "        ");
+    const std::string name = "k" + num(ci);
+    out->source = subst(kConvBackwardInputTemplate,
+                        {{"LABEL", c.label}, {"NAME", name}, {"G", num(G)}, {"IMAGES", num(images)}, {"OH", num(OH)}, {"OW", num(OW)}, {"IH", num(IH)},
+                         {"IW", num(IW)}, {"FH", num(FH)}, {"FW", num(FW)}, {"K", num(K)}, {"GC", num(GC)}, {"BN", num(BN)}, {"TMEM_COLS", num(tmem_cols)},
+                         {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
+    KernelLaunch l;
+    l.entry = name;
+    const int64_t resident = std::max<int64_t>(1, std::min<int64_t>({8, (200 * 1024) / smem, 512 / tmem_cols}));
+    l.grid_x = (uint32_t)std::min<int64_t>(tiles, (int64_t)opt.sm_count * resident);  // persistent over tiles
+    l.block = 256;
+    l.smem = (uint32_t)smem;
+    l.label = "TensorCore" + c.label;
+    l.cluster = ci;
+    l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)(images * IH * IW * G * GC);
+    l.flops = 2.0 * (double)G * (double)(images * IH * IW) * (double)GC * (double)(FH * FW * K);
+    out->launches.push_back(l);
+    return true;
+}
+
 ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
     const OpNode& mm = g.ops().nodes[c.node_id];
     const ClusterInput& a = c.inputs[0];
     const ClusterInput& b = c.inputs[1];
     const int64_t BC = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
     const int64_t r_graph = mm.shape[0];
-    const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
+    const auto& cbi = c.conv_backward_input;
+    if (cbi.enabled && opt.use_tf32) {
+        ClusterCode code;
+        if (gen_conv_backward_input(g, c, ci, opt, &code)) return code;
+    }
+    const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows || cbi.enabled;  // fused output is [pixel, group, channel]
     const int64_t out_count = BC * M * N;
+    // fused conv backward-input: an A element exists only where (y - fy, x - fx) is a window position
+    std::string a_valid = "true";
+    if (cbi.enabled) {
+        std::ostringstream v;
+        v << "(unsigned)((gm / " << cbi.in_w << ") % " << cbi.in_h << " - gk / " << cbi.filter_w * cbi.matmul_k << ") < " << cbi.out_h
+          << "u && (unsigned)(gm % " << cbi.in_w << " - (gk / " << cbi.matmul_k << ") % " << cbi.filter_w << ") < " << cbi.out_w << "u";
+        a_valid = v.str();
+    }
 
     // Plain dense operands (row-major or transposed whole buffers) take the TMA + tcgen05 TF32 kernel when the
     // environment allows reduced operand precision; everything else stays on the strict-FP32 JIT path below.
@@ -715,7 +777,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     // Operands behind view chains (conv2d's im2col, grouped / transposed views) use the gathered tcgen05 kernel
     // when TF32 is allowed and the GEMM is big enough to matter; otherwise the strict-FP32 SIMT kernel.
     // shared-memory operand layout follows the direction that is contiguous in global memory
-    const bool a_mn = chain_vector_run_axis(a.chain, a.arg_shape, 2) < 4 && chain_vector_run_axis(a.chain, a.arg_shape, 1) == 4;
+    const bool a_mn = !cbi.enabled && chain_vector_run_axis(a.chain, a.arg_shape, 2) < 4 && chain_vector_run_axis(a.chain, a.arg_shape, 1) == 4;
     const bool b_mn = chain_vector_run_axis(b.chain, b.arg_shape, 1) < 4 && chain_vector_run_axis(b.chain, b.arg_shape, 2) == 4;
     const bool tc = opt.use_tf32 && 2.0 * (double)BC * (double)M * (double)N * (double)K >= 5e7 && N >= 8 && (M >= 128 || (a_mn && K >= 1024));
     GemmTile t = choose_gemm_tile(M, N);
@@ -796,7 +858,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     const int64_t k_tiles = div_round_up(std::min<int64_t>(KC, K), t.bk);
     // every unit is one aligned 16-byte run and the k loop is long enough to fill a pipeline: cp.async stages;
     // short-K GEMMs (convolution forward / backward-input) use the persistent register-staged kernel instead
-    const bool async_copy = tc && a_vec && b_vec && k_tiles >= 8;
+    const bool async_copy = tc && a_vec && b_vec && k_tiles >= 8 && !cbi.enabled;
     const int64_t stages = async_copy ? std::max<int64_t>(2, std::min<int64_t>({4, 196608 / std::max<int64_t>(one_stage, 1), k_tiles})) : 2;
     if (tc)
         code.source = subst(async_copy ? kMatMulTc3Template : kMatMulTc2Template,
@@ -804,14 +866,14 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
                              {"KC", num(KC)}, {"BC", num(BC)}, {"TMEM_COLS", num(tmem_cols)}, {"A_MN", a_mn ? "true" : "false"}, {"STAGES", num(stages)},
                              {"B_MN", b_mn ? "true" : "false"}, {"A_LAYOUT", a_mn ? "MN-major" : "K-major"}, {"B_LAYOUT", b_mn ? "MN-major" : "K-major"},
                              {"A_VEC", a_vec ? "true" : "false"}, {"B_VEC", b_vec ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
-                             {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
+                             {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}, {"A_VALID", a_valid}});
     else
     code.source = subst(kMatMulTemplate,
                         {{"LABEL", c.label}, {"NAME", name}, {"NT", num(t.nt)}, {"BM", num(t.bm)}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"TM", num(t.tm)},
                          {"TN", num(t.tn)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"KC", num(KC)}, {"BC", num(BC)},
                          {"A_DECODE", decode("lm", "BM", t.bm, "lk", "BK", t.bk, a_m_fast)},
                          {"B_DECODE", decode("ln", "BN", t.bn, "lk", "BK", t.bk, !b_k_fast)},
-                         {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
+                         {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}, {"A_VALID", a_valid}});
     KernelLaunch l;
     l.entry = name;
     l.grid_x = (uint32_t)(div_round_up(M, t.bm) * div_round_up(N, t.bn));

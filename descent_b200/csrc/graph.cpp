@@ -1,5 +1,6 @@
 // Graph passes and clustering (reference: src/graph.rs).  See graph.hpp for the design notes.
 #include "graph.hpp"
+#include "codegen.hpp"
 
 #include <climits>
 #include <cmath>
@@ -415,6 +416,69 @@ void Graph::build_per_element_program(Cluster& c) {
     c.label = label.str();
 }
 
+
+// conv2d's backward-input pass is MatMul (windows gradient = dY x W^T) -> view -> WindowsToImage (col2im).  When
+// the MatMul feeds nothing else, the pair is one implicit GEMM over the pixels of the (padded) image gradient:
+// the window matrix (filter_h*filter_w times the size of dY) never touches memory.  Returns true after
+// rewriting the MatMul's cluster in place; the caller skips the stand-alone WindowsToImage kernel.
+bool Graph::absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id) {
+    OpNode& node = ops_.nodes[id];
+    if (node.op.stride_w != 1 || node.op.stride_h != 1) return false;
+    const OpEdge& e = node.in[0];
+    const OpNode& mm = ops_.nodes[e.src];
+    if (mm.op.kind != OpKind::MatMul || mm.cluster_id < 0 || cons[e.src].size() != 1 || mm.shape[0] != 1) return false;
+    Cluster& mc = clusters[mm.cluster_id];
+    if (mc.kind != ClusterKind::MatMul || mc.matmul_absorbs_reduce || mc.conv_backward_input.enabled || mc.outputs[0] != e.src) return false;
+    const Shape& ws = e.arg_shape;  // [image, out_h, out_w, group, filter_h, filter_w, channel in group]
+    if (ws.len() != 7 || node.shape.len() != 4) return false;
+    const int64_t B = ws[0], OH = ws[1], OW = ws[2], G = ws[3], FH = ws[4], FW = ws[5], GC = ws[6];
+    const int64_t IH = node.shape[1], IW = node.shape[2];
+    const ClusterInput a = mc.inputs[0], b = mc.inputs[1];
+    const int64_t M = B * OH * OW, N = FH * FW * GC, K = a.arg_shape[2];
+    if (a.arg_shape.len() != 3 || b.arg_shape.len() != 3 || a.arg_shape[0] != G || a.arg_shape[1] != M || b.arg_shape[2] != N) return false;
+    if (node.shape[0] != B || node.shape[3] != G * GC) return false;
+    // the view between the two must be an affine map (at most one view, no clamping) that sends window element
+    // (image, oy, ox, group, fy, fx, c) to row (image, oy, ox) / column (fy, fx, c) of the group's product
+    if (e.chain.views.size() > 1 || (!e.chain.views.empty() && e.chain.views[0].any_clamp())) return false;
+    if (e.chain.input_count != G * M * N || e.chain.output_count != G * M * N) return false;
+    const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
+    const int64_t stride_group = rows_mode ? N : M * N, stride_row = rows_mode ? G * N : N;
+    const int64_t want[7] = {OH * OW * stride_row, OW * stride_row, stride_row, stride_group, FW * GC, GC, 1};
+    auto ws_strides = ws.strides();
+    if (eval_chain(e.chain, 0) != 0) return false;
+    for (int axis = 0; axis < 7; ++axis)
+        if (ws[axis] > 1 && eval_chain(e.chain, ws_strides[axis]) != want[axis]) return false;
+
+    // A'[group, (image, y, x), (fy, fx, k)] = A[group, (image, y - fy, x - fx), k]; positions outside the window
+    // grid are clamped here (so the address is always legal) and zeroed by the kernel's validity test
+    View va;
+    va.input_shape = Shape({G, B, OH, OW, K});
+    va.input_offsets.assign(5, 0);
+    va.output_shape = Shape({G, B, IH, IW, FH, FW, K});
+    va.output_mapping = {AxisMapping::identity(0, G), AxisMapping::identity(1, B), AxisMapping::source(2, 1), AxisMapping::source(3, 1),
+                         AxisMapping::source(2, -1), AxisMapping::source(3, -1), AxisMapping::identity(4, K)};
+    // B'[group, (fy, fx, k), c] = B[group, k, (fy, fx, c)]
+    View vb;
+    vb.input_shape = Shape({G, K, FH, FW, GC});
+    vb.input_offsets.assign(5, 0);
+    vb.output_shape = Shape({G, FH, FW, K, GC});
+    vb.output_mapping = {AxisMapping::identity(0, G), AxisMapping::identity(2, FH), AxisMapping::identity(3, FW), AxisMapping::identity(1, K),
+                         AxisMapping::identity(4, GC)};
+    mc.inputs[0].chain.views.push_back(va);  // a fresh boundary: never folded into the operand's own views
+    mc.inputs[0].chain.output_count = va.output_shape.element_count();
+    mc.inputs[0].arg_shape = Shape({G, B * IH * IW, FH * FW * K});
+    mc.inputs[1].chain.push(vb);
+    mc.inputs[1].arg_shape = Shape({G, FH * FW * K, GC});
+    mc.conv_backward_input = {true, IH, IW, OH, OW, FH, FW, K, {a, b}};
+    mc.members.push_back(id);
+    mc.outputs[0] = id;
+    std::ostringstream label;
+    label << "MatMul+WindowsToImage (k=" << FH * FW * K << ") " << node.shape.str();
+    mc.label = label.str();
+    node.cluster_id = mm.cluster_id;
+    return true;
+}
+
 void Graph::build_clusters() {
     auto order = ops_.topo_order();
     auto cons = ops_.consumers();
@@ -573,6 +637,10 @@ void Graph::build_clusters() {
                 label << "Unpad " << node.shape.str();
                 break;
             case OpKind::WindowsToImage:
+                if (absorb_windows_to_image(clusters, cons, id)) {
+                    clusters[node.cluster_id].level = level[id];
+                    continue;
+                }
                 c.kind = ClusterKind::WindowsToImage;
                 add_input(node.in[0]);
                 label << "WindowsToImage " << node.shape.str();

@@ -54,6 +54,15 @@ struct Cluster {
     // single-node kernels
     int node_id = -1;                  // the Reduce / MatMul / Unpad / WindowsToImage / ScatterAdd / AllReduce node
     bool matmul_absorbs_reduce = false;  // outputs[0] is the Reduce(axis 0) node that followed the MatMul
+    // MatMul whose only consumer was a stride-1 WindowsToImage (conv2d's backward-input pass): one implicit GEMM
+    // over output pixels, outputs[0] is the WindowsToImage node and the window matrix is never materialised.
+    // Row r = (image, y, x), k = (fy, fx, matmul k), column = channel within the group; an A element is zero
+    // unless (y - fy, x - fx) is a window position, i.e. lies in [0, out_h) x [0, out_w).
+    struct ConvBackwardInput {
+        bool enabled = false;
+        int64_t in_h = 0, in_w = 0, out_h = 0, out_w = 0, filter_h = 0, filter_w = 0, matmul_k = 0;
+        std::vector<ClusterInput> unfused;  // the MatMul's own operands [group, pixel, k] and [group, k, (fy, fx, channel)]
+    } conv_backward_input;
     int copy_from = -1;                // ScatterAdd: accumulator node taken in place (graph.rs:601-621)
     std::string label;                 // as the reference's Kernel::label_name (kernel.rs)
 };
@@ -82,6 +91,7 @@ private:
     void simplify_arithmetic();
     void eliminate_common_subgraphs();
     void hoist_all_reduce_views();
+    bool absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     void build_clusters();
     void build_per_element_program(Cluster& c);
 
