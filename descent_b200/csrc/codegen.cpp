@@ -639,7 +639,7 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
 
 #include "gemm_tc_template.inc"
 #include "gemm_tc_async_template.inc"
-#include "conv_bwd_input_template.inc"
+#include "halo_conv_template.inc"
 
 const char* kSplitSumTemplate = R"(
 // split-K partial sums of {{LABEL}}, added in ascending split order
@@ -674,38 +674,64 @@ GemmTile choose_gemm_tile(int64_t M, int64_t N) {
 }
 
 
-// conv2d backward-input as a halo-tiled implicit GEMM (conv_bwd_input_template.inc); returns false when the shape
-// falls outside what that kernel covers and the gathered GEMM should be used instead
-bool gen_conv_backward_input(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, ClusterCode* out) {
-    const auto& cbi = c.conv_backward_input;
-    const ClusterInput& a = cbi.unfused[0];
-    const ClusterInput& b = cbi.unfused[1];
-    const int64_t G = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
-    const int64_t IH = cbi.in_h, IW = cbi.in_w, OH = cbi.out_h, OW = cbi.out_w, FH = cbi.filter_h, FW = cbi.filter_w;
-    const int64_t GC = N / (FH * FW), images = M / (OH * OW);
-    if (IW > 128 || 128 % IW != 0 || IW != OW + FW - 1 || IH != OH + FH - 1) return false;
-    if (K % 8 != 0 || GC % 4 != 0 || GC > 256) return false;
+// ---- stride-1 convolutions as halo-tiled implicit GEMMs (halo_conv_template.inc) ---------------------
+struct HaloConv {
+    bool backward_input = false;
+    int64_t groups, images, out_h, out_w, filter_h, filter_w;
+    int64_t k_per_group;  // reduction channels per tap and group
+    int64_t n_per_group;  // output channels per group
+    bool rows_mode = true;  // forward: product stored [pixel, group, channel] (Rows) or [group, pixel, channel]
+};
+
+// `a` / `b` are the GEMM operands [group, pixel, k] and [group, k, n] behind their chains.  Returns false when the
+// shape falls outside what the kernel covers (the caller then uses the gathered GEMM).
+bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, const HaloConv& h, const ClusterInput& a, const ClusterInput& b,
+                   ClusterCode* out) {
+    const int64_t G = h.groups, OH = h.out_h, OW = h.out_w, FH = h.filter_h, FW = h.filter_w, KG = h.k_per_group, NG = h.n_per_group;
+    const int64_t W = OW + FW - 1, PH = OH + FH - 1;      // padded image
+    const int64_t rows = h.backward_input ? PH : OH;      // output rows per image
+    const int64_t M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
+    if (W > 128 || 128 % W != 0 || KG % 8 != 0 || NG % 4 != 0 || NG > 256) return false;
     if (chain_vector_run_axis(a.chain, a.arg_shape, 2) != 4) return false;
-    const int64_t BN = div_round_up(GC, 16) * 16;
+    const int64_t BN = div_round_up(NG, 16) * 16;
     int64_t tmem_cols = 32;
     while (tmem_cols < G * BN) tmem_cols *= 2;
     if (tmem_cols > 512) return false;
-    const int64_t TH = 128 / IW, halo_rows = TH + FH - 1, Q = G * K / 4;
-    const int64_t npix = div_round_up((FW - 1) + halo_rows * IW, 8) * 8 + 1;
-    const int64_t a_bytes = div_round_up(Q * npix * 16, 128) * 128, b_bytes = G * FH * FW * (K / 4) * BN * 16;
+    const int64_t TH = 128 / W, halo_rows = TH + FH - 1, Q = G * KG / 4, lead = h.backward_input ? FW - 1 : 0;
+    const int64_t npix = div_round_up(lead + halo_rows * W + FW - 1, 8) * 8 + 1;
+    const int64_t a_bytes = div_round_up(Q * npix * 16, 128) * 128, b_bytes = G * FH * FW * (KG / 4) * BN * 16;
     const int64_t smem = a_bytes + b_bytes + 64 + 128;
-    if (smem > 160 * 1024 || halo_rows * IW * Q > 256 * 16) return false;  // operands must fit; at most 16 staged loads per thread
-    const int64_t tiles = images * div_round_up(IH, TH);
+    if (smem > 160 * 1024 || halo_rows * W * Q > 256 * 16) return false;  // operands must fit; at most 16 staged loads per thread
+    const int64_t tiles = h.images * div_round_up(rows, TH);
 
     int uniq = 0;
-    std::ostringstream ca, cb;
+    std::ostringstream ca, cb, a_coords, b_coords, tap_pixel, out_ok, out_index;
     std::string ia = emit_chain(ca, a.chain, {{"batch", M * K, G}, {"gm", K, M}, {"gk", 1, K}}, uniq, "                ");
     std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, G}, {"gk", N, K}, {"gn", 1, N}}, uniq, "        ");
+    if (h.backward_input) {
+        // halo pixel (py, px) is window position (py - (FH-1), px); A is dY[group, (image, oy, ox), k]
+        a_coords << "const int oy = py - " << FH - 1 << "; const bool ok = px < " << OW << " && (unsigned)oy < " << OH << "u; const int gk = kin, gm = (image * "
+                 << OH << " + oy) * " << OW << " + px;";
+        b_coords << "const int gk = kin, gn = tap * NG + n;";
+        tap_pixel << "LEAD + (FH - 1 - fy) * W - fx";
+        out_ok << "true";
+        out_index << "((size_t)(image * ROWS + y) * W + x) * (G * NG) + g * NG";
+    } else {
+        // halo pixel (py, px) is padded-image position; any window element that reads it gives its address
+        a_coords << "const bool ok = py < " << PH << "; const int fy = max(py - " << OH - 1 << ", 0), fx = max(px - " << OW - 1
+                 << ", 0); const int gk = (fy * FW + fx) * KG + kin, gm = (image * " << OH << " + py - fy) * " << OW << " + px - fx;";
+        b_coords << "const int gk = tap * KG + kin, gn = n;";
+        tap_pixel << "fy * W + fx";
+        out_ok << "x < " << OW;
+        if (h.rows_mode) out_index << "((size_t)((image * ROWS + y) * " << OW << " + x) * G + g) * NG";
+        else out_index << "((size_t)g * " << M << " + (image * ROWS + y) * " << OW << " + x) * NG";
+    }
     const std::string name = "k" + num(ci);
-    out->source = subst(kConvBackwardInputTemplate,
-                        {{"LABEL", c.label}, {"NAME", name}, {"G", num(G)}, {"IMAGES", num(images)}, {"OH", num(OH)}, {"OW", num(OW)}, {"IH", num(IH)},
-                         {"IW", num(IW)}, {"FH", num(FH)}, {"FW", num(FW)}, {"K", num(K)}, {"GC", num(GC)}, {"BN", num(BN)}, {"TMEM_COLS", num(tmem_cols)},
-                         {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
+    out->source = subst(kHaloConvTemplate,
+                        {{"LABEL", c.label}, {"NAME", name}, {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)},
+                         {"FW", num(FW)}, {"KG", num(KG)}, {"NG", num(NG)}, {"BN", num(BN)}, {"LEAD", num(lead)}, {"TMEM_COLS", num(tmem_cols)},
+                         {"A_COORDS", a_coords.str()}, {"B_COORDS", b_coords.str()}, {"TAP_PIXEL", tap_pixel.str()}, {"OUT_OK", out_ok.str()},
+                         {"OUT_INDEX", out_index.str()}, {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
     KernelLaunch l;
     l.entry = name;
     const int64_t resident = std::max<int64_t>(1, std::min<int64_t>({8, (200 * 1024) / smem, 512 / tmem_cols}));
@@ -715,10 +741,65 @@ bool gen_conv_backward_input(const Graph& g, const Cluster& c, int ci, const Cod
     l.label = "TensorCore" + c.label;
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
-    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)(images * IH * IW * G * GC);
-    l.flops = 2.0 * (double)G * (double)(images * IH * IW) * (double)GC * (double)(FH * FW * K);
+    const int64_t out_pixels = h.images * rows * (h.backward_input ? W : OW);
+    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)(out_pixels * G * NG);
+    l.flops = 2.0 * (double)(out_pixels * G * NG) * (double)(FH * FW * KG);
     out->launches.push_back(l);
     return true;
+}
+
+bool gen_conv_backward_input(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, ClusterCode* out) {
+    const auto& cbi = c.conv_backward_input;
+    const ClusterInput& a = cbi.unfused[0];
+    const ClusterInput& b = cbi.unfused[1];
+    if (cbi.in_w != cbi.out_w + cbi.filter_w - 1 || cbi.in_h != cbi.out_h + cbi.filter_h - 1) return false;
+    HaloConv h;
+    h.backward_input = true;
+    h.groups = a.arg_shape[0];
+    h.out_h = cbi.out_h; h.out_w = cbi.out_w; h.filter_h = cbi.filter_h; h.filter_w = cbi.filter_w;
+    h.images = a.arg_shape[1] / (cbi.out_h * cbi.out_w);
+    h.k_per_group = a.arg_shape[2];
+    h.n_per_group = b.arg_shape[2] / (cbi.filter_h * cbi.filter_w);
+    return gen_halo_conv(g, c, ci, opt, h, a, b, out);
+}
+
+// Forward conv2d: the A operand is image_to_windows of the (padded) image, i.e. its chain ends in a view with
+// output [image, oy, ox, group, fy, fx, c] in which oy and fy walk one input axis with step 1, ox and fx
+// another, and group / c the channel axis (array.rs image_to_windows; stride 1), optionally followed by the
+// [pixel, group, k] -> [group, pixel, k] transposition.  Then A[g, (image, oy, ox), (fy, fx, c)] depends on
+// (oy + fy, ox + fx) only, which is what the halo kernel needs.
+bool gen_conv_forward(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, ClusterCode* out) {
+    const OpNode& mm = g.ops().nodes[c.node_id];
+    const ClusterInput& a = c.inputs[0];
+    const ClusterInput& b = c.inputs[1];
+    const int64_t G = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
+    if (mm.shape[0] != 1 || c.matmul_absorbs_reduce || a.chain.views.empty()) return false;
+    size_t wi = a.chain.views.size() - 1;
+    if (G > 1) {  // the transposition [M, G, K] -> [G, M, K]
+        const View& p = a.chain.views[wi];
+        if (wi == 0 || p.input_shape != Shape({M, G, K}) || p.output_shape != Shape({G, M, K}) || p.any_clamp()) return false;
+        const AxisMapping want[3] = {AxisMapping::identity(1, G), AxisMapping::identity(0, M), AxisMapping::identity(2, K)};
+        for (int i = 0; i < 3; ++i)
+            if (!(p.output_mapping[i] == want[i]) || p.input_offsets[i] != 0) return false;
+        --wi;
+    }
+    const View& w = a.chain.views[wi];
+    if (w.output_shape.len() != 7 || w.input_shape.len() != 4) return false;
+    const int64_t B = w.output_shape[0], OH = w.output_shape[1], OW = w.output_shape[2], FH = w.output_shape[4], FW = w.output_shape[5], C = w.output_shape[6];
+    if (w.output_shape[3] != G || B * OH * OW != M || FH * FW * C != K) return false;
+    auto maps = [&](int out_axis, int in_axis, int64_t step) {
+        const AxisMapping& m = w.output_mapping[out_axis];
+        if (w.output_shape[out_axis] == 1) return true;  // never needs a coordinate
+        return m.is_source && m.axis == in_axis && m.step == step;
+    };
+    if (!maps(0, 0, 1) || !maps(1, 1, 1) || !maps(2, 2, 1) || !maps(3, 3, C) || !maps(4, 1, 1) || !maps(5, 2, 1) || !maps(6, 3, 1)) return false;
+    HaloConv h;
+    h.backward_input = false;
+    h.groups = G; h.images = B; h.out_h = OH; h.out_w = OW; h.filter_h = FH; h.filter_w = FW;
+    h.k_per_group = C;
+    h.n_per_group = N;
+    h.rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
+    return gen_halo_conv(g, c, ci, opt, h, a, b, out);
 }
 
 ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
@@ -728,9 +809,9 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     const int64_t BC = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
     const int64_t r_graph = mm.shape[0];
     const auto& cbi = c.conv_backward_input;
-    if (cbi.enabled && opt.use_tf32) {
+    if (opt.use_tf32) {
         ClusterCode code;
-        if (gen_conv_backward_input(g, c, ci, opt, &code)) return code;
+        if (cbi.enabled ? gen_conv_backward_input(g, c, ci, opt, &code) : gen_conv_forward(g, c, ci, opt, &code)) return code;
     }
     const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows || cbi.enabled;  // fused output is [pixel, group, channel]
     const int64_t out_count = BC * M * N;
