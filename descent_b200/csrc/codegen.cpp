@@ -640,6 +640,7 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
 #include "gemm_tc_template.inc"
 #include "gemm_tc_async_template.inc"
 #include "halo_conv_template.inc"
+#include "thin_gemm_template.inc"
 
 const char* kSplitSumTemplate = R"(
 // split-K partial sums of {{LABEL}}, added in ascending split order
@@ -802,6 +803,73 @@ bool gen_conv_forward(const Graph& g, const Cluster& c, int ci, const CodegenOpt
     return gen_halo_conv(g, c, ci, opt, h, a, b, out);
 }
 
+// GEMMs with one tiny extent stream their big operand once (thin_gemm_template.inc); strict FP32 either way
+bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, ClusterCode* out) {
+    const OpNode& mm = g.ops().nodes[c.node_id];
+    const ClusterInput& a = c.inputs[0];
+    const ClusterInput& b = c.inputs[1];
+    const int64_t BC = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
+    if (c.conv_backward_input.enabled || !(c.matmul_absorbs_reduce || mm.shape[0] == 1)) return false;
+    const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
+    const std::string c_row = rows_mode ? "(((size_t)split * M + gm) * BC + batch) * N" : "(((size_t)split * BC + batch) * M + gm) * N";
+    const std::string name = "k" + num(ci);
+    int uniq = 0;
+    std::ostringstream ca, cb;
+    KernelLaunch l;
+    l.entry = name;
+    l.label = c.label;
+    l.cluster = ci;
+    l.grid_y = (uint32_t)BC;
+    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)(BC * M * N);
+    l.flops = 2.0 * (double)BC * (double)M * (double)N * (double)K;
+    l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
+    if (K <= 32 && N <= 32 && M >= 65536) {
+        std::string ia = emit_chain(ca, a.chain, {{"batch", M * K, BC}, {"gm", K, M}, {"gk", 1, K}}, uniq, "            ");
+        std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, BC}, {"gk", N, K}, {"gn", 1, N}}, uniq, "            ");
+        out->source = subst(kThinRowsTemplate, {{"LABEL", c.label}, {"NAME", name}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"BC", num(BC)},
+                                               {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
+        l.grid_x = (uint32_t)div_round_up(M, 256);
+        l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
+        out->launches.push_back(l);
+        return true;
+    }
+    if (M <= 16 && M * N <= 288 && K >= 65536) {
+        int64_t nsplit = 1;
+        while (M * (N / nsplit) > 80 && nsplit < 32 && (N / nsplit) % 2 == 0) nsplit *= 2;
+        if (N % nsplit != 0 || M * (N / nsplit) > 96) return false;
+        const int64_t nth = N / nsplit;
+        const bool b_vec = nth % 4 == 0 && chain_vector_run_axis(b.chain, b.arg_shape, 2) == 4;
+        std::string ia = emit_chain(ca, a.chain, {{"batch", M * K, BC}, {"gm", K, M}, {"gk", 1, K}}, uniq, "            ");
+        std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, BC}, {"gk", N, K}, {"gn", 1, N}}, uniq, "                ");
+        out->source = subst(kThinReduceTemplate, {{"LABEL", c.label}, {"NAME", name}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"BC", num(BC)},
+                                                 {"NSPLIT", num(nsplit)}, {"B_VEC", b_vec ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
+                                                 {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
+        const int64_t rows_per_cta = 256 / nsplit;
+        const int64_t S = std::max<int64_t>(1, std::min<int64_t>((int64_t)opt.sm_count * 2 / BC, K / (rows_per_cta * 8)));
+        l.grid_x = (uint32_t)S;
+        const int64_t out_count = BC * M * N;
+        if (S > 1) {
+            l.args.push_back({KernelArg::Scratch, -1, 0});
+            out->launches.push_back(l);
+            out->scratch_bytes = S * out_count * 4;
+            const std::string sname = name + "_splitsum";
+            out->source += subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
+            KernelLaunch s;
+            s.entry = sname;
+            s.grid_x = (uint32_t)div_round_up(out_count, 256);
+            s.label = "SplitSum " + c.label;
+            s.cluster = ci;
+            s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+            out->launches.push_back(s);
+        } else {
+            l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
+            out->launches.push_back(l);
+        }
+        return true;
+    }
+    return false;
+}
+
 ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
     const OpNode& mm = g.ops().nodes[c.node_id];
     const ClusterInput& a = c.inputs[0];
@@ -853,6 +921,11 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
             code.launches.push_back(l);
             return code;
         }
+    }
+
+    {
+        ClusterCode code;
+        if (gen_thin_matmul(g, c, ci, opt, &code)) return code;
     }
 
     // Operands behind view chains (conv2d's im2col, grouped / transposed views) use the gathered tcgen05 kernel
