@@ -682,6 +682,8 @@ struct HaloConv {
     int64_t k_per_group;  // reduction channels per tap and group
     int64_t n_per_group;  // output channels per group
     bool rows_mode = true;  // forward: product stored [pixel, group, channel] (Rows) or [group, pixel, channel]
+    int64_t unpad_h = 0, unpad_w = 0;  // backward-input: Unpad amounts fused into the epilogue
+    bool unpad_rows_first = true;
 };
 
 // `a` / `b` are the GEMM operands [group, pixel, k] and [group, k, n] behind their chains.  Returns false when the
@@ -701,7 +703,14 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
     const int64_t TH = 128 / W, halo_rows = TH + FH - 1, Q = G * KG / 4, lead = h.backward_input ? FW - 1 : 0;
     const int64_t npix = div_round_up(lead + halo_rows * W + FW - 1, 8) * 8 + 1;
     const int64_t a_bytes = div_round_up(Q * npix * 16, 128) * 128, b_bytes = G * FH * FW * (KG / 4) * BN * 16;
-    const int64_t smem = a_bytes + b_bytes + 64 + 128;
+    const bool unpad = h.unpad_h > 0 || h.unpad_w > 0;
+    if (unpad) {
+        // every padded row / column that folds into an output row / column must sit in the same tile as it
+        if (h.unpad_h >= TH || (rows - h.unpad_h - 1) / TH != (rows - 1) / TH || rows - 2 * h.unpad_h < 1 || W - 2 * h.unpad_w < 1) return false;
+        if (128 * (G * NG + 4) * 4 > 64 * 1024) return false;
+    }
+    const int64_t a_region = std::max<int64_t>(a_bytes, unpad ? div_round_up(128 * (G * NG + 4) * 4, 128) * 128 : 0);
+    const int64_t smem = a_region + b_bytes + 64 + 128;
     if (smem > 160 * 1024 || halo_rows * W * Q > 256 * 16) return false;  // operands must fit; at most 16 staged loads per thread
     const int64_t tiles = h.images * div_round_up(rows, TH);
 
@@ -731,6 +740,7 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
     out->source = subst(kHaloConvTemplate,
                         {{"LABEL", c.label}, {"NAME", name}, {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)},
                          {"FW", num(FW)}, {"KG", num(KG)}, {"NG", num(NG)}, {"BN", num(BN)}, {"LEAD", num(lead)}, {"TMEM_COLS", num(tmem_cols)},
+                         {"PY", num(h.unpad_h)}, {"PX", num(h.unpad_w)}, {"ROWS_FIRST", h.unpad_rows_first ? "true" : "false"},
                          {"A_COORDS", a_coords.str()}, {"B_COORDS", b_coords.str()}, {"TAP_PIXEL", tap_pixel.str()}, {"OUT_OK", out_ok.str()},
                          {"OUT_INDEX", out_index.str()}, {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
     KernelLaunch l;
@@ -742,7 +752,7 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
     l.label = "TensorCore" + c.label;
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
-    const int64_t out_pixels = h.images * rows * (h.backward_input ? W : OW);
+    const int64_t out_pixels = h.images * (rows - 2 * h.unpad_h) * ((h.backward_input ? W : OW) - 2 * h.unpad_w);
     l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)(out_pixels * G * NG);
     l.flops = 2.0 * (double)(out_pixels * G * NG) * (double)(FH * FW * KG);
     out->launches.push_back(l);
@@ -761,6 +771,9 @@ bool gen_conv_backward_input(const Graph& g, const Cluster& c, int ci, const Cod
     h.images = a.arg_shape[1] / (cbi.out_h * cbi.out_w);
     h.k_per_group = a.arg_shape[2];
     h.n_per_group = b.arg_shape[2] / (cbi.filter_h * cbi.filter_w);
+    h.unpad_h = cbi.unpad_h;
+    h.unpad_w = cbi.unpad_w;
+    h.unpad_rows_first = cbi.unpad_first_axis != 2;
     return gen_halo_conv(g, c, ci, opt, h, a, b, out);
 }
 
@@ -869,6 +882,8 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
     }
     return false;
 }
+
+extern const char* kUnpadTemplate;
 
 ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
     const OpNode& mm = g.ops().nodes[c.node_id];
@@ -1064,6 +1079,38 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
         s.cluster = ci;
         s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
         code.launches.push_back(s);
+    }
+    if (cbi.enabled && (cbi.unpad_h > 0 || cbi.unpad_w > 0)) {
+        // absorbed Unpads without the halo kernel's epilogue: the padded gradient goes to scratch and the plain
+        // Unpad kernels run from there, in the graph's order
+        const int64_t images = M / (cbi.in_h * cbi.in_w), channels = BC * N;
+        int64_t offset = div_round_up(code.scratch_bytes, 256) * 256;
+        KernelArg src{KernelArg::Scratch, -1, offset};
+        code.launches.back().args.back() = src;
+        int64_t h = cbi.in_h, w = cbi.in_w;
+        offset += div_round_up(images * h * w * channels * 4, 256) * 256;
+        const int order[2] = {cbi.unpad_first_axis == 2 ? 2 : 1, cbi.unpad_first_axis == 2 ? 1 : 2};
+        int remaining = (cbi.unpad_h > 0) + (cbi.unpad_w > 0);
+        for (int axis : order) {
+            const int64_t pad = axis == 1 ? cbi.unpad_h : cbi.unpad_w;
+            if (pad == 0) continue;
+            (axis == 1 ? h : w) -= 2 * pad;
+            const int64_t count = images * h * w * channels, inner = axis == 1 ? w * channels : channels;
+            const std::string uname = name + "_unpad" + num(axis);
+            code.source += subst(kUnpadTemplate, {{"LABEL", "Unpad of " + c.label}, {"NAME", uname}, {"COUNT", num(count)}, {"INNER", num(inner)},
+                                                 {"LEN", num(axis == 1 ? h : w)}, {"PAD", num(pad)}, {"CHAIN", ""}, {"IDX", "e"}});
+            KernelLaunch u;
+            u.entry = uname;
+            u.grid_x = (uint32_t)div_round_up(count, 256);
+            u.label = "Unpad of " + c.label;
+            u.cluster = ci;
+            KernelArg dst = --remaining > 0 ? KernelArg{KernelArg::Scratch, -1, offset} : KernelArg{KernelArg::NodeBuffer, c.outputs[0], 0};
+            u.args = {src, dst};
+            code.launches.push_back(u);
+            src = dst;
+            offset += div_round_up(count * 4, 256) * 256;
+        }
+        code.scratch_bytes = offset;
     }
     return code;
 }

@@ -417,6 +417,27 @@ void Graph::build_per_element_program(Cluster& c) {
 }
 
 
+// The Unpad(s) that undo conv2d's replicate padding run in the epilogue of the fused backward-input kernel: the
+// padded image gradient is never written either.
+bool Graph::absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id) {
+    OpNode& node = ops_.nodes[id];
+    const OpEdge& e = node.in[0];
+    const OpNode& src = ops_.nodes[e.src];
+    if (!e.chain.is_identity() || src.cluster_id < 0 || cons[e.src].size() != 1 || node.shape.len() != 4) return false;
+    Cluster& mc = clusters[src.cluster_id];
+    auto& cbi = mc.conv_backward_input;
+    if (mc.kind != ClusterKind::MatMul || !cbi.enabled || mc.outputs[0] != e.src || node.op.pad < 1) return false;
+    if (node.op.axis == 1 && cbi.unpad_h == 0) cbi.unpad_h = node.op.pad;
+    else if (node.op.axis == 2 && cbi.unpad_w == 0) cbi.unpad_w = node.op.pad;
+    else return false;
+    if (cbi.unpad_first_axis == 0) cbi.unpad_first_axis = node.op.axis;
+    mc.members.push_back(id);
+    mc.outputs[0] = id;
+    mc.label += "+Unpad";
+    node.cluster_id = src.cluster_id;
+    return true;
+}
+
 // conv2d's backward-input pass is MatMul (windows gradient = dY x W^T) -> view -> WindowsToImage (col2im).  When
 // the MatMul feeds nothing else, the pair is one implicit GEMM over the pixels of the (padded) image gradient:
 // the window matrix (filter_h*filter_w times the size of dY) never touches memory.  Returns true after
@@ -632,6 +653,10 @@ void Graph::build_clusters() {
                 break;
             }
             case OpKind::Unpad:
+                if (absorb_unpad(clusters, cons, id)) {
+                    clusters[node.cluster_id].level = level[id];
+                    continue;
+                }
                 c.kind = ClusterKind::Unpad;
                 add_input(node.in[0]);
                 label << "Unpad " << node.shape.str();

@@ -62,6 +62,10 @@ struct Cluster {
         bool enabled = false;
         int64_t in_h = 0, in_w = 0, out_h = 0, out_w = 0, filter_h = 0, filter_w = 0, matmul_k = 0;
         std::vector<ClusterInput> unfused;  // the MatMul's own operands [group, pixel, k] and [group, k, (fy, fx, channel)]
+        // Unpad nodes (the adjoint of conv2d's replicate padding) that followed the WindowsToImage, also absorbed:
+        // amounts along the image's h and w axes and which of the two the graph applies first (1 = h, 2 = w, 0 = none)
+        int64_t unpad_h = 0, unpad_w = 0;
+        int unpad_first_axis = 0;
     } conv_backward_input;
     int copy_from = -1;                // ScatterAdd: accumulator node taken in place (graph.rs:601-621)
     std::string label;                 // as the reference's Kernel::label_name (kernel.rs)
@@ -91,6 +95,7 @@ private:
     void simplify_arithmetic();
     void eliminate_common_subgraphs();
     void hoist_all_reduce_views();
+    bool absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     bool absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     void build_clusters();
     void build_per_element_program(Cluster& c);
