@@ -641,6 +641,7 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
 #include "gemm_tc_async_template.inc"
 #include "halo_conv_template.inc"
 #include "thin_gemm_template.inc"
+#include "halo_wgrad_template.inc"
 
 const char* kSplitSumTemplate = R"(
 // split-K partial sums of {{LABEL}}, added in ascending split order
@@ -794,7 +795,7 @@ bool gen_conv_forward(const Graph& g, const Cluster& c, int ci, const CodegenOpt
         if (wi == 0 || p.input_shape != Shape({M, G, K}) || p.output_shape != Shape({G, M, K}) || p.any_clamp()) return false;
         const AxisMapping want[3] = {AxisMapping::identity(1, G), AxisMapping::identity(0, M), AxisMapping::identity(2, K)};
         for (int i = 0; i < 3; ++i)
-            if (!(p.output_mapping[i] == want[i]) || p.input_offsets[i] != 0) return false;
+            if ((p.output_shape[i] > 1 && !(p.output_mapping[i] == want[i])) || p.input_offsets[i] != 0) return false;
         --wi;
     }
     const View& w = a.chain.views[wi];
@@ -814,6 +815,85 @@ bool gen_conv_forward(const Graph& g, const Cluster& c, int ci, const CodegenOpt
     h.n_per_group = N;
     h.rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
     return gen_halo_conv(g, c, ci, opt, h, a, b, out);
+}
+
+// conv2d weight gradient: A = transposed window matrix [group, (fy, fx, c), pixel], B = dY [group, pixel, co], the
+// Reduce over the k split absorbed (halo_wgrad_template.inc).  Same recognition of the window view as the forward.
+bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, ClusterCode* out) {
+    const OpNode& mm = g.ops().nodes[c.node_id];
+    const ClusterInput& a = c.inputs[0];
+    const ClusterInput& b = c.inputs[1];
+    const int64_t G = a.arg_shape[0], KW = a.arg_shape[1], MPIX = a.arg_shape[2], NCO = b.arg_shape[2];
+    if (!(c.matmul_absorbs_reduce || mm.shape[0] == 1) || mm.op.output_mode == MatMulOutputMode::Rows || a.chain.views.size() < 2) return false;
+    const View& p = a.chain.views.back();  // [pixel, group, (fy, fx, c)] -> [group, (fy, fx, c), pixel]
+    if (p.output_shape != Shape({G, KW, MPIX}) || p.any_clamp()) return false;
+    int src_axis[3];  // input axis that carries group / (fy, fx, c) / pixel
+    if (p.input_shape == Shape({MPIX, G, KW})) { src_axis[0] = 1; src_axis[1] = 2; src_axis[2] = 0; }
+    else if (G == 1 && p.input_shape == Shape({G, MPIX, KW})) { src_axis[0] = 0; src_axis[1] = 2; src_axis[2] = 1; }  // same order when there is one group
+    else return false;
+    for (int i = 0; i < 3; ++i) {
+        const AxisMapping want = AxisMapping::source(src_axis[i], 1);
+        if ((p.output_shape[i] > 1 && !(p.output_mapping[i] == want)) || p.input_offsets[i] != 0) return false;
+    }
+    const View& w = a.chain.views[a.chain.views.size() - 2];
+    if (w.output_shape.len() != 7 || w.input_shape.len() != 4) return false;
+    const int64_t B = w.output_shape[0], OH = w.output_shape[1], OW = w.output_shape[2], FH = w.output_shape[4], FW = w.output_shape[5], C = w.output_shape[6];
+    if (w.output_shape[3] != G || B * OH * OW != MPIX || FH * FW * C != KW) return false;
+    auto maps = [&](int out_axis, int in_axis, int64_t step) {
+        const AxisMapping& m = w.output_mapping[out_axis];
+        if (w.output_shape[out_axis] == 1) return true;
+        return m.is_source && m.axis == in_axis && m.step == step;
+    };
+    if (!maps(0, 0, 1) || !maps(1, 1, 1) || !maps(2, 2, 1) || !maps(3, 3, C) || !maps(4, 1, 1) || !maps(5, 2, 1) || !maps(6, 3, 1)) return false;
+    const int64_t W = OW + FW - 1;
+    if (W > 128 || 128 % W != 0 || C % 4 != 0 || NCO % 4 != 0 || FW * G * C > 128 || (G * NCO) % 16 != 0 || G * NCO > 256) return false;
+    if (chain_vector_run_axis(a.chain, a.arg_shape, 1) != 4 || chain_vector_run_axis(b.chain, b.arg_shape, 2) != 4) return false;
+    int64_t tmem_cols = 32;
+    while (tmem_cols < FH * G * NCO) tmem_cols *= 2;
+    if (tmem_cols > 512) return false;
+    const int64_t TH = 128 / W, halo_rows = TH + FH - 1;
+    if (FW - 1 > 4 || W % 4 != 0) return false;
+    const int64_t npix = div_round_up(4 + halo_rows * W, 4) * 4;  // mirrors NPIX / X_BLOCK / X_BYTES of the template
+    const int64_t x_block = npix * 128, m_blocks = div_round_up(FW * G * C, 32), n_blocks = div_round_up(G * NCO, 32);
+    const int64_t x_bytes = std::max<int64_t>(4 * x_block, m_blocks * x_block + n_blocks * 128 * 128);
+    if (x_block / 16 > 0x3fff || x_bytes + 64 + 1024 > 200 * 1024) return false;
+    if (halo_rows * W * (G * C / 4) > 256 * 12 || 128 * (G * NCO / 4) > 256 * 12) return false;  // staged loads per thread
+    const int64_t smem = x_bytes + 64 + 1024;
+    const int64_t tiles = B * div_round_up(OH, TH);
+    const int64_t resident = std::max<int64_t>(1, std::min<int64_t>({4, (200 * 1024) / smem, 512 / tmem_cols}));
+    const int64_t S = std::min<int64_t>(tiles, (int64_t)opt.sm_count * resident);
+
+    int uniq = 0;
+    std::ostringstream ca, cb;
+    std::string ia = emit_chain(ca, a.chain, {{"batch", KW * MPIX, G}, {"gm", MPIX, KW}, {"gk", 1, MPIX}}, uniq, "                ");
+    std::string ib = emit_chain(cb, b.chain, {{"batch", MPIX * NCO, G}, {"gk", NCO, MPIX}, {"gn", 1, NCO}}, uniq, "                ");
+    const std::string name = "k" + num(ci);
+    out->source = subst(kHaloWgradTemplate, {{"LABEL", c.label}, {"NAME", name}, {"G", num(G)}, {"IMAGES", num(B)}, {"OH", num(OH)}, {"OW", num(OW)},
+                                             {"FH", num(FH)}, {"FW", num(FW)}, {"CG", num(C)}, {"NCO", num(NCO)}, {"TMEM_COLS", num(tmem_cols)},
+                                             {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
+    const int64_t out_count = G * KW * NCO;
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)S;
+    l.block = 256;
+    l.smem = (uint32_t)smem;
+    l.label = "TensorCore" + c.label;
+    l.cluster = ci;
+    l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::Scratch, -1, 0}};
+    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)out_count;
+    l.flops = 2.0 * (double)G * (double)KW * (double)NCO * (double)MPIX;
+    out->launches.push_back(l);
+    out->scratch_bytes = S * out_count * 4;
+    const std::string sname = name + "_splitsum";
+    out->source += subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
+    KernelLaunch s;
+    s.entry = sname;
+    s.grid_x = (uint32_t)div_round_up(out_count, 256);
+    s.label = "SplitSum " + c.label;
+    s.cluster = ci;
+    s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+    out->launches.push_back(s);
+    return true;
 }
 
 // GEMMs with one tiny extent stream their big operand once (thin_gemm_template.inc); strict FP32 either way
@@ -895,6 +975,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     if (opt.use_tf32) {
         ClusterCode code;
         if (cbi.enabled ? gen_conv_backward_input(g, c, ci, opt, &code) : gen_conv_forward(g, c, ci, opt, &code)) return code;
+        if (!cbi.enabled && gen_conv_weight_gradient(g, c, ci, opt, &code)) return code;
     }
     const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows || cbi.enabled;  // fused output is [pixel, group, channel]
     const int64_t out_count = BC * M * N;
