@@ -22,6 +22,7 @@ SHAPES = [
     # images, height, width, in channels, out channels, groups
     (8, 14, 14, 16, 32, 2),   # conv-net's second convolution: padded width 16 -> halo kernels
     (4, 14, 14, 8, 16, 1),    # single group
+    (3, 14, 14, 32, 32, 2),   # 96 weight-gradient rows: the M=128 form of that kernel
     (2, 6, 6, 8, 8, 1),       # padded width 8: 16 image rows per tile, images smaller than a tile
     (3, 30, 30, 8, 16, 2),    # padded width 32, ragged last tile
     (5, 12, 12, 8, 16, 1),    # padded width 14 does not divide 128 -> gathered kernels
