@@ -303,7 +303,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(args), "mini_batch_per_gpu": m, "global_batch": global_batch, "optimizer": args.optimizer,
                    "parallelism": "dp%d" % world,
-                   "gemm_path": "tcgen05 tf32 operands, fp32 accumulate (TMA-fed dense GEMMs; gathered implicit-GEMM conv with M>=128); strict-fp32 simt for the rest" if args.precision == "tf32" else "strict-fp32 simt",
+                   "gemm_path": "tcgen05 tf32 operands, fp32 accumulate (TMA-fed dense GEMMs; halo-tiled implicit-GEMM conv forward / backward-input / weight-gradient); strict-fp32 streaming kernels for the 1-channel first conv and the tiny GEMMs" if args.precision == "tf32" else "strict-fp32 simt",
                    "cuda_graph": True,
                    "l2_policy": "working set per step (%.0f MB arena) exceeds the 126 MB L2" % (stats["arena_bytes"] / 1e6)
                    if stats["arena_bytes"] > 126e6 else "working set %.0f MB fits L2; no flush" % (stats["arena_bytes"] / 1e6)},
