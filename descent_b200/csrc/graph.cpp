@@ -182,6 +182,7 @@ Graph::Graph(SharedParameters parameters, const OpGraph& ops, DataParallel dp)
     eliminate_common_subgraphs();
     eliminate_dead_code();
     hoist_all_reduce_views();
+    sink_permutations_into_per_element();
     build_clusters();
 }
 
@@ -326,6 +327,77 @@ void Graph::hoist_all_reduce_views() {
             ViewChain chain = view;
             chain.append(e.chain);
             e.chain = chain;
+        }
+    }
+}
+
+// A per-element value that is only ever read through one axis permutation by other per-element ops (max-pool's
+// backward pass computes in window order [image, oy, ox, fy, fx, c] and its consumer reads it back in image order)
+// would be written to memory and gathered element by element.  Per-element ops commute with any bijective
+// re-indexing, so the permutation is pushed onto the op's own operands instead: the op is evaluated directly
+// in its consumers' order, the edge between them becomes an identity and the two kernels fuse.  Repeats until
+// the permutations have sunk to loads of values that exist in memory anyway.
+static bool chain_is_permutation(const ViewChain& chain) {
+    if (chain.is_identity() || chain.input_count != chain.output_count) return false;
+    for (const View& v : chain.views) {
+        std::vector<int> hits(v.input_shape.len(), 0);
+        for (int a = 0; a < v.input_shape.len(); ++a)
+            if (v.input_offsets[a] != 0) return false;
+        for (int i = 0; i < v.output_shape.len(); ++i) {
+            if (v.output_shape[i] == 1) continue;
+            const AxisMapping& m = v.output_mapping[i];
+            if (!m.is_source || m.step != 1 || v.input_shape[m.axis] != v.output_shape[i]) return false;
+            hits[m.axis] += 1;
+        }
+        for (int a = 0; a < v.input_shape.len(); ++a)
+            if (v.input_shape[a] > 1 && hits[a] != 1) return false;
+    }
+    return true;
+}
+
+void Graph::sink_permutations_into_per_element() {
+    auto movable = [&](const OpNode& n) {
+        return n.alive && n.op.is_per_element() && !n.op.is_inline_source() && n.op.kind != OpKind::Gather;
+    };
+    for (bool changed = true; changed;) {
+        changed = false;
+        auto cons = ops_.consumers();
+        // every consumer is a per-element op reading through the same permutation
+        auto common_permutation = [&](int id, ViewChain* chain, Shape* shape) {
+            if (cons[id].empty()) return false;
+            for (size_t i = 0; i < cons[id].size(); ++i) {
+                const OpNode& d = ops_.nodes[cons[id][i].first];
+                const OpEdge& e = d.in[cons[id][i].second];
+                if (!d.op.is_per_element() || d.op.is_gather_arg(e.arg) || d.shape.element_count() != e.chain.output_count) return false;
+                if (i == 0) { *chain = e.chain; *shape = e.arg_shape; }
+                else if (e.chain != *chain || e.arg_shape != *shape) return false;
+            }
+            return chain_is_permutation(*chain);
+        };
+        // the op and everything fused beneath it can follow: an operand that is computed in registers for this op
+        // alone sinks next; one that other ops share would have to be spilled to memory, so then nothing moves
+        std::function<bool(int)> can_sink = [&](int id) {
+            for (const OpEdge& e : ops_.nodes[id].in) {
+                const OpNode& src = ops_.nodes[e.src];
+                if (!movable(src) || !e.chain.is_identity() || src.shape.element_count() != ops_.nodes[id].shape.element_count()) continue;
+                if (cons[e.src].size() != 1 || !can_sink(e.src)) return false;
+            }
+            return true;
+        };
+        for (int id = (int)ops_.nodes.size() - 1; id >= 0; --id) {
+            OpNode& node = ops_.nodes[id];
+            if (!movable(node)) continue;
+            ViewChain perm;
+            Shape shape;
+            if (!common_permutation(id, &perm, &shape) || !can_sink(id)) continue;
+            for (OpEdge& e : node.in) {
+                e.chain.append(perm);
+                e.arg_shape = shape;
+            }
+            node.shape = shape;
+            for (auto [dst, k] : cons[id]) ops_.nodes[dst].in[k].chain = ViewChain::identity(shape.element_count());
+            changed = true;
+            break;  // consumer lists are stale
         }
     }
 }

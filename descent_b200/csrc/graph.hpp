@@ -95,6 +95,7 @@ private:
     void simplify_arithmetic();
     void eliminate_common_subgraphs();
     void hoist_all_reduce_views();
+    void sink_permutations_into_per_element();
     bool absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     bool absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     void build_clusters();
