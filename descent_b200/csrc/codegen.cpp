@@ -219,38 +219,11 @@ double chain_bytes(const Graph& g, const ClusterInput& in) {
 
 // ---- per-element (reference: PerElementKernel, kernel.rs:195-383) -------------------------------
 
-ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
-    const int64_t n = c.element_count;
-    const int vec = (n % 4 == 0) ? 4 : 1;
-    std::ostringstream os;
-    const std::string name = "k" + num(ci);
-    os << "// " << c.label << "\n";
-    os << "extern \"C\" __global__ void __launch_bounds__(256) " << name << "(";
-    for (size_t i = 0; i < c.inputs.size(); ++i) os << "const float* in" << i << ", ";
-    for (size_t i = 0; i < c.outputs.size(); ++i) os << "float* out" << i << ", ";
-    os << "const unsigned* dsc_step) {\n";
-    os << "    const unsigned dsc_seed = dsc_step[0]; (void)dsc_seed;\n";
-    os << "    const unsigned base = (blockIdx.x * 256u + threadIdx.x) * " << vec << "u;\n";
-    os << "    if (base >= " << unum(n) << ") return;\n";
-    std::vector<bool> vector_load(c.inputs.size(), false);
-    std::vector<bool> is_loaded(c.inputs.size(), false);
-    for (const auto& op : c.ops)
-        if (op.kind == PerElementOp::Load) is_loaded[op.input_index] = true;
-    if (vec == 4) {
-        for (size_t i = 0; i < c.inputs.size(); ++i) {
-            if (is_loaded[i] && c.inputs[i].chain.is_identity()) {
-                vector_load[i] = true;
-                os << "    const float4 q" << i << " = *reinterpret_cast<const float4*>(in" << i << " + base);\n";
-                os << "    const float vin" << i << "[4] = {q" << i << ".x, q" << i << ".y, q" << i << ".z, q" << i << ".w};\n";
-            }
-        }
-        for (size_t i = 0; i < c.outputs.size(); ++i) os << "    float vout" << i << "[4];\n";
-        os << "    #pragma unroll\n    for (int v = 0; v < 4; ++v) {\n";
-        os << "    const unsigned e = base + v;\n";
-    } else {
-        os << "    const unsigned e = base;\n    {\n";
-    }
-    int uniq = 0;
+// The straight-line program of a per-element cluster for element `e` (statements `const float t<i> = ...;`).
+// Inputs flagged in `vector_load` were fetched as `vin<i>[v]`; input `register_input` (if >= 0) is not in memory
+// at all: its value for this element is `acc[v]` (a GEMM epilogue evaluating the cluster on its accumulator).
+void emit_per_element_ops(std::ostringstream& os, const Cluster& c, const CodegenOptions& opt, int& uniq, const std::vector<bool>& vector_load,
+                          int register_input) {
     for (size_t oi = 0; oi < c.ops.size(); ++oi) {
         const PerElementOp& op = c.ops[oi];
         const std::string t = "t" + num(oi);
@@ -258,7 +231,9 @@ ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const Code
         switch (op.kind) {
             case PerElementOp::Load: {
                 const auto& in = c.inputs[op.input_index];
-                if (vector_load[op.input_index]) {
+                if (op.input_index == register_input) {
+                    os << "    const float " << t << " = acc[v];\n";
+                } else if (vector_load[op.input_index]) {
                     os << "    const float " << t << " = vin" << op.input_index << "[v];\n";
                 } else {
                     std::string idx = emit_chain(os, in.chain, "e", uniq);
@@ -334,6 +309,41 @@ ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const Code
             }
         }
     }
+}
+
+ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, const std::string& name_suffix = "") {
+    const int64_t n = c.element_count;
+    const int vec = (n % 4 == 0) ? 4 : 1;
+    std::ostringstream os;
+    const std::string name = "k" + num(ci) + name_suffix;
+    os << "// " << c.label << "\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(256) " << name << "(";
+    for (size_t i = 0; i < c.inputs.size(); ++i) os << "const float* in" << i << ", ";
+    for (size_t i = 0; i < c.outputs.size(); ++i) os << "float* out" << i << ", ";
+    os << "const unsigned* dsc_step) {\n";
+    os << "    const unsigned dsc_seed = dsc_step[0]; (void)dsc_seed;\n";
+    os << "    const unsigned base = (blockIdx.x * 256u + threadIdx.x) * " << vec << "u;\n";
+    os << "    if (base >= " << unum(n) << ") return;\n";
+    std::vector<bool> vector_load(c.inputs.size(), false);
+    std::vector<bool> is_loaded(c.inputs.size(), false);
+    for (const auto& op : c.ops)
+        if (op.kind == PerElementOp::Load) is_loaded[op.input_index] = true;
+    if (vec == 4) {
+        for (size_t i = 0; i < c.inputs.size(); ++i) {
+            if (is_loaded[i] && c.inputs[i].chain.is_identity()) {
+                vector_load[i] = true;
+                os << "    const float4 q" << i << " = *reinterpret_cast<const float4*>(in" << i << " + base);\n";
+                os << "    const float vin" << i << "[4] = {q" << i << ".x, q" << i << ".y, q" << i << ".z, q" << i << ".w};\n";
+            }
+        }
+        for (size_t i = 0; i < c.outputs.size(); ++i) os << "    float vout" << i << "[4];\n";
+        os << "    #pragma unroll\n    for (int v = 0; v < 4; ++v) {\n";
+        os << "    const unsigned e = base + v;\n";
+    } else {
+        os << "    const unsigned e = base;\n    {\n";
+    }
+    int uniq = 0;
+    emit_per_element_ops(os, c, opt, uniq, vector_load, -1);
     for (size_t i = 0; i < c.outputs.size(); ++i) {
         if (vec == 4) os << "    vout" << i << "[v] = t" << c.output_ops[i] << ";\n";
         else os << "    out" << i << "[e] = t" << c.output_ops[i] << ";\n";
@@ -676,6 +686,71 @@ GemmTile choose_gemm_tile(int64_t M, int64_t N) {
 }
 
 
+// ---- per-element epilogues of GEMM kernels ---------------------------------------------------------
+// `<kernel>_store4(index, r, C, ..., seed)` receives four consecutive elements of the product starting at linear
+// index `index`.  Without an absorbed cluster it stores them; with one it evaluates that cluster's program on them
+// (the cluster's other operands are loaded at the same element indices, 128-bit where they are plain arrays) and
+// stores the cluster's outputs instead.
+struct EpilogueCode {
+    std::string store4;   // the device function, emitted ahead of the kernel
+    std::string params;   // extra kernel parameters ("const float* in1, float* out0, ")
+    std::string args;     // the same names as call arguments ("in1, out0, ")
+    std::vector<KernelArg> launch_args;
+    double bytes = 0;     // algorithmic bytes of the extra operands and outputs
+};
+
+EpilogueCode gen_epilogue(const Graph& g, const Cluster& c, const std::string& kernel, const CodegenOptions& opt) {
+    EpilogueCode code;
+    std::ostringstream os;
+    if (c.epilogue.empty()) {
+        os << "__device__ __forceinline__ void " << kernel << "_store4(size_t index, float4 r, float* C, unsigned) { *reinterpret_cast<float4*>(C + index) = r; }\n";
+        code.store4 = os.str();
+        return code;
+    }
+    const Cluster& p = c.epilogue[0];
+    const int product = c.epilogue_product_input;
+    std::ostringstream params, args;
+    for (size_t i = 0; i < p.inputs.size(); ++i) {
+        if ((int)i == product) continue;
+        params << "const float* in" << i << ", ";
+        args << "in" << i << ", ";
+        code.launch_args.push_back({KernelArg::NodeBuffer, p.inputs[i].node_id, 0});
+        code.bytes += chain_bytes(g, p.inputs[i]);
+    }
+    for (size_t i = 0; i < p.outputs.size(); ++i) {
+        params << "float* out" << i << ", ";
+        args << "out" << i << ", ";
+        code.launch_args.push_back({KernelArg::NodeBuffer, p.outputs[i], 0});
+        code.bytes += 4.0 * (double)p.element_count;
+    }
+    code.params = params.str();
+    code.args = args.str();
+    os << "// epilogue: " << p.label << "\n";
+    os << "__device__ __forceinline__ void " << kernel << "_store4(size_t index, float4 r, float* C, " << code.params << "unsigned dsc_seed) {\n";
+    os << "    (void)C; (void)dsc_seed;\n    const unsigned base = (unsigned)index;\n    const float acc[4] = {r.x, r.y, r.z, r.w};\n";
+    std::vector<bool> vector_load(p.inputs.size(), false), is_loaded(p.inputs.size(), false);
+    for (const auto& op : p.ops)
+        if (op.kind == PerElementOp::Load) is_loaded[op.input_index] = true;
+    for (size_t i = 0; i < p.inputs.size(); ++i) {
+        if ((int)i == product || !is_loaded[i] || !p.inputs[i].chain.is_identity()) continue;
+        vector_load[i] = true;
+        os << "    const float4 q" << i << " = *reinterpret_cast<const float4*>(in" << i << " + base);\n";
+        os << "    const float vin" << i << "[4] = {q" << i << ".x, q" << i << ".y, q" << i << ".z, q" << i << ".w};\n";
+    }
+    for (size_t i = 0; i < p.outputs.size(); ++i) os << "    float vout" << i << "[4];\n";
+    os << "    #pragma unroll\n    for (int v = 0; v < 4; ++v) {\n    const unsigned e = base + v;\n";
+    int uniq = 0;
+    emit_per_element_ops(os, p, opt, uniq, vector_load, product);
+    for (size_t i = 0; i < p.outputs.size(); ++i) os << "    vout" << i << "[v] = t" << p.output_ops[i] << ";\n";
+    os << "    }\n";
+    for (size_t i = 0; i < p.outputs.size(); ++i)
+        os << "    *reinterpret_cast<float4*>(out" << i << " + base) = make_float4(vout" << i << "[0], vout" << i << "[1], vout" << i << "[2], vout" << i
+           << "[3]);\n";
+    os << "}\n";
+    code.store4 = os.str();
+    return code;
+}
+
 // ---- stride-1 convolutions as halo-tiled implicit GEMMs (halo_conv_template.inc) ---------------------
 struct HaloConv {
     bool backward_input = false;
@@ -713,7 +788,8 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
         if (h.unpad_h >= TH || (rows - h.unpad_h - 1) / TH != (rows - 1) / TH || rows - 2 * h.unpad_h < 1 || W - 2 * h.unpad_w < 1) return false;
         if (128 * (G * NG + 4) * 4 > 64 * 1024) return false;
     }
-    const int64_t a_region = std::max<int64_t>(a_bytes, unpad ? div_round_up(128 * (G * NG + 4) * 4, 128) * 128 : 0);
+    const bool stage_out = !h.backward_input && h.rows_mode && (G * NG) % 4 == 0 && 128 * (G * NG + 4) * 4 <= 64 * 1024;
+    const int64_t a_region = std::max<int64_t>(a_bytes, (unpad || stage_out) ? div_round_up(128 * (G * NG + 4) * 4, 128) * 128 : 0);
     const int64_t smem = a_region + b_bytes + 64 + 128;
     if (smem > 160 * 1024 || halo_rows * W * Q > 256 * 16) return false;  // operands must fit; at most 16 staged loads per thread
     const int64_t tiles = h.images * div_round_up(rows, TH);
@@ -741,10 +817,12 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
         else out_index << "((size_t)g * " << M << " + (image * ROWS + y) * " << OW << " + x) * NG";
     }
     const std::string name = "k" + num(ci);
+    if (!c.epilogue.empty() && (h.backward_input || !h.rows_mode || G * NG % 4 != 0)) return false;
+    const EpilogueCode epi = gen_epilogue(g, c, name, opt);
     out->source = subst(kHaloConvTemplate,
-                        {{"LABEL", c.label}, {"NAME", name}, {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)},
+                        {{"LABEL", c.label}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args}, {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)},
                          {"FW", num(FW)}, {"KG", num(KG)}, {"NG", num(NG)}, {"BN", num(BN)}, {"LEAD", num(lead)}, {"TMEM_COLS", num(tmem_cols)}, {"NPIX", num(npix)},
-                         {"PY", num(h.unpad_h)}, {"PX", num(h.unpad_w)}, {"ROWS_FIRST", h.unpad_rows_first ? "true" : "false"},
+                         {"PY", num(h.unpad_h)}, {"PX", num(h.unpad_w)}, {"STAGE_OUT", stage_out ? "true" : "false"}, {"OUT_W", num(OW)}, {"ROWS_FIRST", h.unpad_rows_first ? "true" : "false"},
                          {"A_COORDS", a_coords.str()}, {"B_COORDS", b_coords.str()}, {"TAP_PIXEL", tap_pixel.str()}, {"OUT_OK", out_ok.str()},
                          {"OUT_INDEX", out_index.str()}, {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
     KernelLaunch l;
@@ -756,8 +834,9 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
     l.label = "TensorCore" + c.label;
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+    l.args.insert(l.args.end(), epi.launch_args.begin(), epi.launch_args.end());
     const int64_t out_pixels = h.images * (rows - 2 * h.unpad_h) * ((h.backward_input ? W : OW) - 2 * h.unpad_w);
-    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)(out_pixels * G * NG);
+    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(out_pixels * G * NG) : epi.bytes);
     l.flops = 2.0 * (double)(out_pixels * G * NG) * (double)(FH * FW * KG);
     out->launches.push_back(l);
     return true;
@@ -925,14 +1004,19 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
     if (K <= 32 && N <= 32 && M >= 65536) {
         std::string ia = emit_chain(ca, a.chain, {{"batch", M * K, BC}, {"gm", K, M}, {"gk", 1, K}}, uniq, "            ");
         std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, BC}, {"gk", N, K}, {"gn", 1, N}}, uniq, "            ");
+        if (!c.epilogue.empty() && (N % 4 != 0 || !(rows_mode ? true : BC == 1))) return false;
+        const EpilogueCode epi = gen_epilogue(g, c, name, opt);
+        l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(BC * M * N) : epi.bytes);
         out->source = subst(kThinRowsTemplate, {{"LABEL", c.label}, {"NAME", name}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"BC", num(BC)},
+                                               {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args},
                                                {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
         l.grid_x = (uint32_t)div_round_up(M, 256);
         l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
+        l.args.insert(l.args.end(), epi.launch_args.begin(), epi.launch_args.end());
         out->launches.push_back(l);
         return true;
     }
-    if (M <= 16 && M * N <= 288 && K >= 65536) {
+    if (M <= 16 && M * N <= 288 && K >= 65536 && c.epilogue.empty()) {
         int64_t nsplit = 1;
         while (M * (N / nsplit) > 80 && nsplit < 32 && (N / nsplit) % 2 == 0) nsplit *= 2;
         if (N % nsplit != 0 || M * (N / nsplit) > 96) return false;
@@ -978,6 +1062,29 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     const int64_t BC = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
     const int64_t r_graph = mm.shape[0];
     const auto& cbi = c.conv_backward_input;
+    if (!c.epilogue.empty()) {
+        // an absorbed per-element cluster runs in the epilogue of the kernels that support it ...
+        ClusterCode code;
+        if (opt.use_tf32 && gen_conv_forward(g, c, ci, opt, &code)) return code;
+        code = ClusterCode();
+        if (gen_thin_matmul(g, c, ci, opt, &code)) return code;
+        // ... and as its own kernel behind any other GEMM: the product goes to scratch, never to a graph buffer
+        Cluster plain = c;
+        plain.epilogue.clear();
+        plain.epilogue_product_input = -1;
+        plain.inputs.resize(2);
+        plain.outputs = {c.node_id};
+        code = gen_matmul(g, plain, ci, opt);
+        const int64_t product_offset = div_round_up(code.scratch_bytes, 256) * 256;
+        code.scratch_bytes = product_offset + BC * M * N * 4;
+        ClusterCode tail = gen_per_element(g, c.epilogue[0], ci, opt, "_epilogue");
+        code.source += tail.source;
+        for (auto& l : tail.launches) code.launches.push_back(l);
+        for (auto& l : code.launches)
+            for (auto& arg : l.args)
+                if (arg.kind == KernelArg::NodeBuffer && arg.node_id == c.node_id) arg = KernelArg{KernelArg::Scratch, -1, product_offset};
+        return code;
+    }
     if (opt.use_tf32) {
         ClusterCode code;
         if (cbi.enabled ? gen_conv_backward_input(g, c, ci, opt, &code) : gen_conv_forward(g, c, ci, opt, &code)) return code;

@@ -417,7 +417,9 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
                 r.bytes = (size_t)(bucket_bytes / 4);
                 r.label = "AllReduce bucket [" + std::to_string(bucket_bytes / 4) + "]";
             } else if (l.kind == KernelLaunch::TensorGemm) {
-                for (const auto& a : l.args) r.buffers.push_back(device_address(a.node_id));
+                for (const auto& a : l.args)
+                    r.buffers.push_back(a.kind == KernelArg::NodeBuffer ? device_address(a.node_id)
+                                                                        : exec.arena + (uint64_t)(scratch_offset[ci] + a.scratch_offset));
                 r.gemm_m = l.gemm_m; r.gemm_n = l.gemm_n; r.gemm_k = l.gemm_k;
                 r.gemm_a_is_mk = l.gemm_a_is_mk; r.gemm_b_is_kn = l.gemm_b_is_kn;
                 exec.stats.kernel_launches += 1;

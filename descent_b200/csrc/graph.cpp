@@ -489,6 +489,59 @@ void Graph::build_per_element_program(Cluster& c) {
 }
 
 
+// conv2d / dense forward: MatMul -> (+ bias, activation, ...) as one kernel.  Runs after the per-element programs
+// exist; the merged cluster takes the per-element cluster's level (all of its other inputs are ready there, and the
+// MatMul's operands stay alive until then because the planner follows the final cluster order).
+void Graph::absorb_per_element_epilogues(std::vector<Cluster>& clusters) {
+    auto cons = ops_.consumers();
+    for (size_t mi = 0; mi < clusters.size(); ++mi) {
+        Cluster& mc = clusters[mi];
+        if (mc.kind != ClusterKind::MatMul || mc.matmul_absorbs_reduce || mc.conv_backward_input.enabled || !mc.epilogue.empty()) continue;
+        const int x = mc.outputs[0];
+        const OpNode& mm = ops_.nodes[x];
+        if (mm.op.kind != OpKind::MatMul || mm.shape[0] != 1 || mm.shape.at(-1) % 4 != 0 || cons[x].empty()) continue;
+        int pi = -1;
+        bool ok = true;
+        for (auto [dst, k] : cons[x]) {
+            const OpNode& d = ops_.nodes[dst];
+            const OpEdge& e = d.in[k];
+            if (d.cluster_id < 0 || clusters[d.cluster_id].kind != ClusterKind::PerElement || !e.chain.is_identity() || d.op.is_gather_arg(e.arg) ||
+                (pi >= 0 && d.cluster_id != pi)) { ok = false; break; }
+            pi = d.cluster_id;
+        }
+        if (!ok || pi < 0) continue;
+        Cluster& pc = clusters[pi];
+        if (pc.element_count != mm.shape.element_count() || pc.members.empty()) continue;
+        int product_input = -1;
+        for (size_t i = 0; i < pc.inputs.size() && ok; ++i) {
+            if (pc.inputs[i].node_id != x) continue;
+            if (!pc.inputs[i].chain.is_identity() || product_input >= 0) ok = false;
+            product_input = (int)i;
+        }
+        // results that are stored straight into a parameter stay in their own kernel: the in-place update rules of
+        // the planner are stated per per-element kernel
+        for (int out : pc.outputs)
+            for (auto [dst, k] : cons[out])
+                if (ops_.nodes[dst].op.kind == OpKind::Output) ok = false;
+        for (const auto& op : pc.ops)
+            if (op.kind == PerElementOp::Gather && op.input_index == product_input) ok = false;
+        if (!ok || product_input < 0) continue;
+        mc.epilogue.push_back(pc);
+        mc.epilogue_product_input = product_input;
+        for (size_t i = 0; i < pc.inputs.size(); ++i)
+            if ((int)i != product_input) mc.inputs.push_back(pc.inputs[i]);
+        mc.outputs = pc.outputs;
+        for (int id : pc.members) {
+            mc.members.push_back(id);
+            ops_.nodes[id].cluster_id = (int)mi;
+        }
+        mc.level = pc.level;
+        mc.label += " + " + pc.label;
+        pc.members.clear();  // dropped below
+        pc.outputs.clear();
+    }
+}
+
 // The Unpad(s) that undo conv2d's replicate padding run in the epilogue of the fused backward-input kernel: the
 // padded image gradient is never written either.
 bool Graph::absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id) {
@@ -790,6 +843,7 @@ void Graph::build_clusters() {
     }
     for (auto& c : clusters)
         if (c.kind == ClusterKind::PerElement) build_per_element_program(c);
+    absorb_per_element_epilogues(clusters);
 
     // levels are a topological order of clusters: fusable edges stay inside a cluster, all others climb
     std::vector<int> idx(clusters.size());
@@ -798,7 +852,11 @@ void Graph::build_clusters() {
     std::vector<int> new_index(clusters.size());
     for (size_t i = 0; i < idx.size(); ++i) new_index[idx[i]] = (int)i;
     clusters_.clear();
-    for (int i : idx) clusters_.push_back(clusters[i]);
+    for (size_t i = 0, kept = 0; i < idx.size(); ++i) {  // clusters absorbed into an epilogue have no members left
+        if (clusters[idx[i]].members.empty()) { new_index[idx[i]] = -1; continue; }
+        new_index[idx[i]] = (int)kept++;
+        clusters_.push_back(clusters[idx[i]]);
+    }
     for (auto& node : ops_.nodes)
         if (node.alive && node.cluster_id >= 0) node.cluster_id = new_index[node.cluster_id];
 }

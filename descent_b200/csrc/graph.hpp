@@ -68,6 +68,12 @@ struct Cluster {
         int unpad_first_axis = 0;
     } conv_backward_input;
     int copy_from = -1;                // ScatterAdd: accumulator node taken in place (graph.rs:601-621)
+    // MatMul whose product is consumed, element for element, by exactly one per-element cluster (conv2d's bias +
+    // activation): that cluster is evaluated on the accumulator in the GEMM's epilogue and the raw product never
+    // exists in memory.  `epilogue[0]` is the absorbed cluster; its input `epilogue_product_input` is the product;
+    // its other inputs are appended to `inputs` (from index 2 on, in order) and its outputs replace `outputs`.
+    std::vector<Cluster> epilogue;
+    int epilogue_product_input = -1;
     std::string label;                 // as the reference's Kernel::label_name (kernel.rs)
 };
 
@@ -96,6 +102,7 @@ private:
     void eliminate_common_subgraphs();
     void hoist_all_reduce_views();
     void sink_permutations_into_per_element();
+    void absorb_per_element_epilogues(std::vector<Cluster>& clusters);
     bool absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     bool absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     void build_clusters();
