@@ -180,6 +180,7 @@ Graph::Graph(SharedParameters parameters, const OpGraph& ops, DataParallel dp)
     eliminate_moves();
     simplify_arithmetic();
     eliminate_common_subgraphs();
+    reuse_activation_sign();
     eliminate_dead_code();
     hoist_all_reduce_views();
     sink_permutations_into_per_element();
@@ -279,6 +280,47 @@ void Graph::simplify_arithmetic() {
         mov_added = true;
     }
     if (mov_added) eliminate_moves();
+}
+
+// leaky_relu / relu keep the sign of their argument: with L = select(x > 0, x, c*x), c >= 0, the tests `x > 0` and
+// `L > 0` agree for every float (c*x <= 0 or NaN whenever x is not > 0).  The backward pass of the activation
+// (array.rs leaky_relu: select(x > 0, g, c*g)) therefore tests the activation it already needs for other reasons
+// (pooling masks, the next layer) instead of the pre-activation, which then no longer has to be kept in memory
+// between the forward and the backward pass.  Bit-exact.
+void Graph::reuse_activation_sign() {
+    auto is_zero = [&](const OpEdge* e) { return e && ops_.nodes[e->src].op.is_literal_f32(0.0f); };
+    auto plain = [&](const OpEdge* e, int src) { return e && e->src == src && e->chain.is_identity(); };
+    std::map<int, int> activation_of;  // x -> L
+    for (int id : ops_.topo_order()) {
+        const OpNode& n = ops_.nodes[id];
+        if (n.op.kind != OpKind::CompareAndSelect || n.op.compare != CompareMode::Gt || !is_zero(n.arg_edge(1))) continue;
+        const OpEdge* x = n.arg_edge(0);
+        if (!x || !x->chain.is_identity() || !plain(n.arg_edge(2), x->src) || ops_.nodes[x->src].shape != n.shape) continue;
+        const OpEdge* other = n.arg_edge(3);
+        bool keeps_sign = is_zero(other);
+        if (!keeps_sign && other) {
+            const OpNode& m = ops_.nodes[other->src];
+            if (other->chain.is_identity() && m.op.kind == OpKind::Binary && m.op.binary == BinaryOp::Mul) {
+                for (int a = 0; a < 2; ++a) {
+                    const Op& lit = ops_.nodes[m.arg_edge(1 - a)->src].op;
+                    if (plain(m.arg_edge(a), x->src) && lit.kind == OpKind::Literal && !lit.literal_is_u32 && lit.literal_f32_value() >= 0.0f &&
+                        lit.literal_f32_value() < 1e30f)
+                        keeps_sign = true;
+                }
+            }
+        }
+        if (keeps_sign) activation_of.emplace(x->src, id);
+    }
+    if (activation_of.empty()) return;
+    for (int id : ops_.topo_order()) {
+        OpNode& n = ops_.nodes[id];
+        if (n.op.kind != OpKind::CompareAndSelect || n.op.compare != CompareMode::Gt || !is_zero(n.arg_edge(1))) continue;
+        for (OpEdge& e : n.in) {
+            if (e.arg != 0 || !e.chain.is_identity()) continue;
+            auto it = activation_of.find(e.src);
+            if (it != activation_of.end() && it->second != id && it->second < id) e.src = it->second;
+        }
+    }
 }
 
 // merge structurally identical nodes (graph.rs:167-203)

@@ -100,6 +100,7 @@ private:
     void eliminate_moves();
     void simplify_arithmetic();
     void eliminate_common_subgraphs();
+    void reuse_activation_sign();
     void hoist_all_reduce_views();
     void sink_permutations_into_per_element();
     void absorb_per_element_epilogues(std::vector<Cluster>& clusters);
