@@ -420,6 +420,51 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, flo
 }
 )";
 
+// The same reduction for four adjacent outputs per thread when they are contiguous in memory for every k (the
+// reduced axis is not the innermost one and the operand's chain keeps aligned groups of four together): 128-bit
+// loads, four independent accumulators, identical order of additions per output.
+const char* kReduceVec4Template = R"(
+// {{LABEL}}  [4 outputs per thread]
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, float* out0, const unsigned* dsc_step) {
+    constexpr unsigned O = {{O}}u, OV = O / 4u, K = {{K}}u, INNER = {{INNER}}u, G = {{G}}u, TO = 256u / G;
+    constexpr unsigned S = {{S}}u, KS = (K + S - 1u) / S;  // S > 1: blockIdx.y owns a slice of k and writes a partial
+    const unsigned k_lo = blockIdx.y * KS, k_hi = min(K, k_lo + KS);
+    const unsigned tid = threadIdx.x;
+    const unsigned g = tid / TO;
+    const unsigned ol = tid % TO;
+    const unsigned ov = blockIdx.x * TO + ol, o = ov * 4u;
+    float4 acc = make_float4({{INIT}}, {{INIT}}, {{INIT}}, {{INIT}});
+    if (ov < OV) {
+        const unsigned oo = o / INNER, oi = o % INNER;
+        {{UNROLL}}
+        for (unsigned k = k_lo + g; k < k_hi; k += G) {
+            const unsigned e = (oo * K + k) * INNER + oi;
+{{CHAIN}}
+            const float4 v = *reinterpret_cast<const float4*>(in0 + {{IDX}});
+            acc.x = {{OPX}}; acc.y = {{OPY}}; acc.z = {{OPZ}}; acc.w = {{OPW}};
+        }
+    }
+    if (G > 1) {
+        __shared__ float4 red[256];
+        red[tid] = acc;
+        __syncthreads();
+        #pragma unroll
+        for (unsigned s = G / 2; s > 0; s >>= 1) {
+            if (g < s) {
+                float4 acc = red[tid];
+                const float4 v = red[tid + s * TO];
+                acc.x = {{OPX}}; acc.y = {{OPY}}; acc.z = {{OPZ}}; acc.w = {{OPW}};
+                red[tid] = acc;
+            }
+            __syncthreads();
+        }
+        if (g == 0 && ov < OV) *reinterpret_cast<float4*>(out0 + blockIdx.y * O + o) = red[tid];
+    } else if (ov < OV) {
+        *reinterpret_cast<float4*>(out0 + blockIdx.y * O + o) = acc;
+    }
+}
+)";
+
 const char* kReduceSplitTemplate = R"(
 // k-slice partials of {{LABEL}}, combined in ascending slice order
 extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws, float* out0, const unsigned* dsc_step) {
@@ -460,9 +505,14 @@ ClusterCode gen_reduce(const Graph& g, const Cluster& c, int ci, const CodegenOp
             kfast = dk != 0 && (d_o == 0 || dk < d_o);
         }
     }
+    const bool vec4 = !kfast && inner % 4 == 0 && O % 4 == 0 && chain_vector_run(in.chain, in.arg_shape.at(-1)) == 4;
+    if (vec4 && K > 16) {
+        const int64_t want = pow2_ceil(div_round_up((int64_t)opt.sm_count * 1024, O / 4));
+        G = std::max<int64_t>(1, std::min<int64_t>({want, (int64_t)256, pow2_floor(K / 4)}));
+    }
     // few outputs and a long axis: slice k across blockIdx.y as well, partials to scratch, combined in slice order
     int64_t S = 1;
-    const int64_t blocks = div_round_up(O, 256 / G);
+    const int64_t blocks = div_round_up(vec4 ? O / 4 : O, 256 / G);
     if (blocks < 2 * opt.sm_count && K / G >= 64) S = std::max<int64_t>(1, std::min<int64_t>(div_round_up(4 * opt.sm_count, blocks), K / (G * 16)));
     std::ostringstream chain;
     int uniq = 0;
@@ -470,6 +520,14 @@ ClusterCode gen_reduce(const Graph& g, const Cluster& c, int ci, const CodegenOp
     const bool is_max = node.op.reduce == ReduceOp::Max;
     const std::string name = "k" + num(ci);
     ClusterCode code;
+    if (vec4)
+        code.source = subst(kReduceVec4Template,
+                            {{"LABEL", c.label}, {"NAME", name}, {"O", num(O)}, {"K", num(K)}, {"INNER", num(inner)}, {"G", num(G)}, {"S", num(S)},
+                             {"INIT", is_max ? "__uint_as_float(0xff800000u)" : "0.f"}, {"UNROLL", K <= 16 ? "#pragma unroll" : "#pragma unroll 4"},
+                             {"CHAIN", chain.str()}, {"IDX", idx}, {"OPX", is_max ? "fmaxf(acc.x, v.x)" : "acc.x + v.x"},
+                             {"OPY", is_max ? "fmaxf(acc.y, v.y)" : "acc.y + v.y"}, {"OPZ", is_max ? "fmaxf(acc.z, v.z)" : "acc.z + v.z"},
+                             {"OPW", is_max ? "fmaxf(acc.w, v.w)" : "acc.w + v.w"}});
+    else
     code.source = subst(kReduceTemplate, {{"LABEL", c.label}, {"NAME", name}, {"O", num(O)}, {"K", num(K)}, {"INNER", num(inner)}, {"G", num(G)}, {"S", num(S)},
                                           {"G_OF_TID", kfast ? "tid % G" : "tid / TO"}, {"O_OF_TID", kfast ? "tid / G" : "tid % TO"},
                                           {"GSTRIDE", kfast ? "1u" : "TO"}, {"INIT", is_max ? "__uint_as_float(0xff800000u)" : "0.f"},
