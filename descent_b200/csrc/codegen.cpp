@@ -1185,6 +1185,30 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
             l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
             l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)out_count;
             l.flops = 2.0 * (double)M * (double)N * (double)K;
+            // few output tiles and a long reduction (dense-layer weight gradients): slice k across the idle SMs
+            const int64_t tiles = div_round_up(M, 128) * div_round_up(N, 128), k_blocks = div_round_up(K, 32);
+            int64_t S = 1;
+            if (tiles * 2 <= opt.sm_count && k_blocks >= 16) {
+                S = std::min<int64_t>(opt.sm_count / tiles, k_blocks / 8);
+                const int64_t per = div_round_up(k_blocks, S);
+                S = div_round_up(k_blocks, per);
+            }
+            if (S > 1) {
+                l.gemm_splits = (int)S;
+                l.args[2] = {KernelArg::Scratch, -1, 0};
+                code.launches.push_back(l);
+                code.scratch_bytes = S * out_count * 4;
+                const std::string sname = "k" + num(ci) + "_splitsum";
+                code.source = subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
+                KernelLaunch sum;
+                sum.entry = sname;
+                sum.grid_x = (uint32_t)div_round_up(out_count, 256);
+                sum.label = "SplitSum " + c.label;
+                sum.cluster = ci;
+                sum.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+                code.launches.push_back(sum);
+                return code;
+            }
             code.launches.push_back(l);
             return code;
         }

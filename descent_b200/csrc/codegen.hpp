@@ -22,6 +22,7 @@ struct KernelLaunch {
     int64_t zero_offset = 0, zero_bytes = 0;  // ZeroScratch
     int64_t gemm_m = 0, gemm_n = 0, gemm_k = 0;  // TensorGemm: args = {A, B, C}
     bool gemm_a_is_mk = true, gemm_b_is_kn = true;
+    int gemm_splits = 1;  // TensorGemm: k slices, each writing a partial product [M, N] into args[2] (then a scratch workspace)
     std::string label;
     int cluster = -1;
     double algorithmic_bytes = 0;  // 4*(sum of min(source, addressed) input elements + outputs)

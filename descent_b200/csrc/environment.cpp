@@ -93,6 +93,7 @@ struct ResolvedLaunch {
     double algorithmic_bytes = 0, flops = 0;
     int64_t gemm_m = 0, gemm_n = 0, gemm_k = 0;
     bool gemm_a_is_mk = true, gemm_b_is_kn = true;
+    int gemm_splits = 1;
 };
 
 struct Environment::GraphExec {
@@ -422,6 +423,7 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
                                                                         : exec.arena + (uint64_t)(scratch_offset[ci] + a.scratch_offset));
                 r.gemm_m = l.gemm_m; r.gemm_n = l.gemm_n; r.gemm_k = l.gemm_k;
                 r.gemm_a_is_mk = l.gemm_a_is_mk; r.gemm_b_is_kn = l.gemm_b_is_kn;
+                r.gemm_splits = l.gemm_splits;
                 exec.stats.kernel_launches += 1;
                 exec.stats.algorithmic_bytes += l.algorithmic_bytes;
                 exec.stats.flops += l.flops;
@@ -462,7 +464,7 @@ void Environment::launch_all(GraphExec& exec, std::vector<float>* per_launch_ms)
         else if (r.kind == KernelLaunch::ZeroScratch) check(dsc_fill_u32(ctx_, r.ptr, 0, 0, r.bytes / 4));
         else if (r.kind == KernelLaunch::AllReduce) check(dsc_dp_allreduce_sum_f32(ctx_, r.ptr, r.bytes));
         else if (r.kind == KernelLaunch::TensorGemm)
-            check(dsc_gemm_tf32(ctx_, r.buffers[0], r.buffers[1], r.buffers[2], r.gemm_m, r.gemm_n, r.gemm_k, r.gemm_a_is_mk, r.gemm_b_is_kn));
+            check(dsc_gemm_tf32_split_k(ctx_, r.buffers[0], r.buffers[1], r.buffers[2], r.gemm_m, r.gemm_n, r.gemm_k, r.gemm_a_is_mk, r.gemm_b_is_kn, r.gemm_splits));
         else check(dsc_launch(ctx_, r.kernel, r.gx, r.gy, r.gz, r.block, r.smem, r.buffers.data(), (int)r.buffers.size()));
         if (per_launch_ms) check(dsc_event_record(ctx_, events[i + 1]));
     }

@@ -110,13 +110,15 @@ struct SharedStorage {
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ c, int m, int n, int k) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, float* __restrict__ c, int m, int n, int k, int splits) {
     extern __shared__ uint8_t smem_raw[];
     using Storage = SharedStorage<BN, STAGES>;
     Storage& s = *reinterpret_cast<Storage*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN, num_tiles = tiles_m * tiles_n, k_blocks = (k + BK - 1) / BK;  // TMA zero-fills out-of-range boxes
+    // split K: work item = (split, tile); split s accumulates k-blocks [s * kbs, (s + 1) * kbs) into c + s * m * n
+    const int kbs = (k_blocks + splits - 1) / splits, num_items = num_tiles * splits;
     constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 4;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
 
@@ -147,9 +149,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         uint32_t stage = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int tile = item % num_tiles, kb_lo = (item / num_tiles) * kbs, kb_hi = min(k_blocks, kb_lo + kbs);
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-            for (int kb = 0; kb < k_blocks; ++kb) {
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
                 mbar_wait(&s.empty[stage], phase ^ 1);
                 mbar_expect_tx(&s.full[stage], STAGE_BYTES);
                 const int k0 = kb * BK;
@@ -177,11 +180,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         constexpr uint32_t A_TYPE = A_MN ? 1 : 2, B_TYPE = B_MN ? 1 : 2;
         constexpr uint32_t A_KSTEP = A_MN ? 1024 : 32, B_KSTEP = B_MN ? 1024 : 32;
         uint32_t stage = 0, phase = 0, acc_stage = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int kb_lo = (item / num_tiles) * kbs, kb_hi = min(k_blocks, kb_lo + kbs);
             mbar_wait(&s.tmem_empty[acc_stage], acc_phase ^ 1);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + acc_stage * BN;
-            for (int kb = 0; kb < k_blocks; ++kb) {
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
                 mbar_wait(&s.full[stage], phase);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(&s.a[stage][0]), b_addr = smem_u32(&s.b[stage][0]);
@@ -189,7 +193,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                     const uint64_t adesc = make_smem_desc(a_addr + kk * A_KSTEP, A_LBO, A_SBO, A_TYPE);
                     const uint64_t bdesc = make_smem_desc(b_addr + kk * B_KSTEP, B_LBO, B_SBO, B_TYPE);
-                    umma_tf32(tmem_d, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+                    umma_tf32(tmem_d, adesc, bdesc, idesc, (kb != kb_lo || kk != 0) ? 1u : 0u);
                 }
                 tcgen05_commit(&s.empty[stage]);  // frees the smem slot when these MMAs retire
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -201,12 +205,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ===== epilogue: TMEM -> registers -> global =====
         const int quad = warp % 4;  // TMEM lanes [32*quad, 32*quad+32)
         uint32_t acc_stage = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int tile = item % num_tiles, split = item / num_tiles;
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&s.tmem_full[acc_stage], acc_phase);
             tcgen05_fence_after();
             const int grow = m0 + quad * 32 + lane;
-            float* row = c + (size_t)grow * n + n0;
+            float* row = c + ((size_t)split * m + grow) * n + n0;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN && n0 + c0 < n; c0 += 32) {
                 uint32_t v[32];
@@ -250,14 +255,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch(dsc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, float* c, int m, int n, int k, int sm_count) {
+int launch(dsc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, float* c, int m, int n, int k, int sm_count, int splits) {
     auto kernel = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN>;
     const int smem = (int)sizeof(SharedStorage<BN, STAGES>) + 1024;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return dsc_internal_set_error(DSC_ERR_CUDA, cudaGetErrorString(e));
-    const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+    const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN) * splits;
     const int grid = tiles < sm_count ? tiles : sm_count;
-    kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)dsc_internal_stream(ctx)>>>(ma, mb, c, m, n, k);
+    kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)dsc_internal_stream(ctx)>>>(ma, mb, c, m, n, k, splits);
     e = cudaGetLastError();
     if (e != cudaSuccess) return dsc_internal_set_error(DSC_ERR_CUDA, cudaGetErrorString(e));
     return DSC_OK;
@@ -266,6 +271,15 @@ int launch(dsc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, float* c,
 }  // namespace
 
 extern "C" int dsc_gemm_tf32(dsc_ctx* ctx, uint64_t a, uint64_t b, uint64_t c, int64_t m, int64_t n, int64_t k, int a_is_mk, int b_is_kn) {
+    return dsc_gemm_tf32_split_k(ctx, a, b, c, m, n, k, a_is_mk, b_is_kn, 1);
+}
+
+extern "C" int dsc_gemm_tf32_split_k(dsc_ctx* ctx, uint64_t a, uint64_t b, uint64_t c, int64_t m, int64_t n, int64_t k, int a_is_mk, int b_is_kn, int splits) {
+    if (splits < 1 || (int64_t)(splits - 1) * 32 >= k) return dsc_internal_set_error(DSC_ERR_UNSUPPORTED, "dsc_gemm_tf32_split_k: every split needs at least one 32-wide k block");
+    {   // every split must own at least one k block: shrink to the number of non-empty slices
+        const int64_t k_blocks = (k + 31) / 32, kbs = (k_blocks + splits - 1) / splits;
+        if ((k_blocks + kbs - 1) / kbs != splits) return dsc_internal_set_error(DSC_ERR_UNSUPPORTED, "dsc_gemm_tf32_split_k: splits must divide the k blocks into non-empty slices");
+    }
     if (m <= 0 || n <= 0 || k <= 0 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX)
         return dsc_internal_set_error(DSC_ERR_UNSUPPORTED, "dsc_gemm_tf32: bad shape");
     // TMA needs 16-byte row pitches: the contiguous extent of each operand must be a multiple of 4 floats
@@ -293,13 +307,13 @@ extern "C" int dsc_gemm_tf32(dsc_ctx* ctx, uint64_t a, uint64_t b, uint64_t c, i
     float* cp = (float*)c;
     const int mi = (int)m, ni = (int)n, ki = (int)k;
     if (wide) {
-        if (!a_mn && !b_mn) return launch<256, 4, false, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
-        if (!a_mn && b_mn) return launch<256, 4, false, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
-        if (a_mn && !b_mn) return launch<256, 4, true, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
-        return launch<256, 4, true, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
+        if (!a_mn && !b_mn) return launch<256, 4, false, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count, splits);
+        if (!a_mn && b_mn) return launch<256, 4, false, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count, splits);
+        if (a_mn && !b_mn) return launch<256, 4, true, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count, splits);
+        return launch<256, 4, true, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count, splits);
     }
-    if (!a_mn && !b_mn) return launch<128, 6, false, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
-    if (!a_mn && b_mn) return launch<128, 6, false, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
-    if (a_mn && !b_mn) return launch<128, 6, true, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
-    return launch<128, 6, true, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count);
+    if (!a_mn && !b_mn) return launch<128, 6, false, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count, splits);
+    if (!a_mn && b_mn) return launch<128, 6, false, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count, splits);
+    if (a_mn && !b_mn) return launch<128, 6, true, false>(ctx, ma, mb, cp, mi, ni, ki, sm_count, splits);
+    return launch<128, 6, true, true>(ctx, ma, mb, cp, mi, ni, ki, sm_count, splits);
 }

@@ -111,6 +111,11 @@ int dsc_sync(dsc_ctx* ctx);
  * epilogue); the contiguous extent of A and of B must be a multiple of 4 floats and all three buffers
  * 16-byte aligned, otherwise DSC_ERR_UNSUPPORTED and the caller uses the JIT strict-FP32 path. */
 int dsc_gemm_tf32(dsc_ctx* ctx, uint64_t a, uint64_t b, uint64_t c, int64_t m, int64_t n, int64_t k, int a_is_mk, int b_is_kn);
+/* The same GEMM with the k range cut into `splits` slices of whole 32-wide k blocks (the reference splits long
+ * reductions the same way, r = ceil(K / 1024), op.rs:74, array.rs:515): slice s writes its partial product to
+ * c + s * M * N, i.e. `c` is a [splits, M, N] workspace that the caller sums in slice order.  `splits` must leave
+ * no slice empty: ceil(kb / ceil(kb / splits)) == splits for kb = ceil(K / 32), else DSC_ERR_UNSUPPORTED. */
+int dsc_gemm_tf32_split_k(dsc_ctx* ctx, uint64_t a, uint64_t b, uint64_t c, int64_t m, int64_t n, int64_t k, int a_is_mk, int b_is_kn, int splits);
 
 /* Data parallel (new): one NCCL communicator per context/rank. */
 int dsc_dp_unique_id(void* out128);                                  /* ncclGetUniqueId; 128 bytes */

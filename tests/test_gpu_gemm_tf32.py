@@ -9,17 +9,20 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def device_gemm(d, env, a_store, b_store, m, n, k, a_is_mk, b_is_kn):
+def device_gemm(d, env, a_store, b_store, m, n, k, a_is_mk, b_is_kn, splits=1):
     lib, ctx = d.lib, env.ctx()
     bufs = []
-    for arr in (a_store, b_store, np.zeros((m, n), np.float32)):
+    for arr in (a_store, b_store, np.zeros((splits, m, n), np.float32)):
         h = ctypes.c_uint64(0)
         assert lib.dsc_alloc(ctx, ctypes.c_size_t(arr.nbytes), ctypes.byref(h)) == 0
         assert lib.dsc_upload(ctx, h, ctypes.c_size_t(0), arr.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arr.nbytes), ctypes.c_size_t(0), 0) == 0
         bufs.append(h)
-    rc = lib.dsc_gemm_tf32(ctx, bufs[0], bufs[1], bufs[2], ctypes.c_int64(m), ctypes.c_int64(n), ctypes.c_int64(k), a_is_mk, b_is_kn)
+    if splits == 1:
+        rc = lib.dsc_gemm_tf32(ctx, bufs[0], bufs[1], bufs[2], ctypes.c_int64(m), ctypes.c_int64(n), ctypes.c_int64(k), a_is_mk, b_is_kn)
+    else:
+        rc = lib.dsc_gemm_tf32_split_k(ctx, bufs[0], bufs[1], bufs[2], ctypes.c_int64(m), ctypes.c_int64(n), ctypes.c_int64(k), a_is_mk, b_is_kn, splits)
     assert rc == 0, lib.dsc_last_error().decode()
-    out = np.empty((m, n), np.float32)
+    out = np.empty((splits, m, n) if splits > 1 else (m, n), np.float32)
     assert lib.dsc_download(ctx, bufs[2], ctypes.c_size_t(0), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(out.nbytes)) == 0, lib.dsc_last_error().decode()
     for h in bufs:
         lib.dsc_free(ctx, h)
@@ -40,6 +43,27 @@ def test_gemm_tf32_layouts(built_library, env, m, n, k, a_is_mk, b_is_kn):
     bound = 2.0 ** -10 * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)) + 1e-6
     err = np.abs(got - exact)
     assert (err <= bound).all(), "max err/bound %.3g at %s" % ((err / bound).max(), np.unravel_index((err / bound).argmax(), err.shape))
+
+
+@pytest.mark.parametrize("m,n,k,splits,a_is_mk,b_is_kn", [(1568, 128, 8192, 11, 0, 1), (128, 10 * 4, 8192, 32, 0, 1), (300, 200, 1000, 4, 1, 0)])
+def test_gemm_tf32_split_k(built_library, env, m, n, k, splits, a_is_mk, b_is_kn):
+    """Slice s of dsc_gemm_tf32_split_k is the product over its own k blocks: each partial is checked on its own, and
+    the partials in slice order add up to the full product (the dense-layer weight gradients take this path)."""
+    rng = np.random.default_rng(k + splits)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    b = rng.standard_normal((k, n)).astype(np.float32)
+    a_store = np.ascontiguousarray(a if a_is_mk else a.T)
+    b_store = np.ascontiguousarray(b if b_is_kn else b.T)
+    got = device_gemm(built_library, env, a_store, b_store, m, n, k, a_is_mk, b_is_kn, splits)
+    per = -(-(-(-k // 32)) // splits) * 32  # k elements per slice: ceil(ceil(k / 32) / splits) blocks of 32
+    for s in range(splits):
+        lo, hi = s * per, min(k, (s + 1) * per)
+        exact = a[:, lo:hi].astype(np.float64) @ b[lo:hi].astype(np.float64)
+        bound = 2.0 ** -10 * (np.abs(a[:, lo:hi]).astype(np.float64) @ np.abs(b[lo:hi]).astype(np.float64)) + 1e-6
+        assert (np.abs(got[s] - exact) <= bound).all(), s
+    lib, ctx = built_library.lib, env.ctx()
+    rc = lib.dsc_gemm_tf32_split_k(ctx, ctypes.c_uint64(256), ctypes.c_uint64(256), ctypes.c_uint64(256), ctypes.c_int64(128), ctypes.c_int64(128), ctypes.c_int64(96), 1, 1, 4)
+    assert rc == 5  # 3 k blocks cannot feed 4 slices
 
 
 def test_gemm_tf32_rejects_unaligned(built_library, env):
