@@ -880,7 +880,10 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
     out->source = subst(kHaloConvTemplate,
                         {{"LABEL", c.label}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args}, {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)},
                          {"FW", num(FW)}, {"KG", num(KG)}, {"NG", num(NG)}, {"BN", num(BN)}, {"LEAD", num(lead)}, {"TMEM_COLS", num(tmem_cols)}, {"NPIX", num(npix)},
-                         {"PY", num(h.unpad_h)}, {"PX", num(h.unpad_w)}, {"STAGE_OUT", stage_out ? "true" : "false"}, {"OUT_W", num(OW)}, {"ROWS_FIRST", h.unpad_rows_first ? "true" : "false"},
+                         {"PY", num(h.unpad_h)}, {"PX", num(h.unpad_w)}, {"STAGE_OUT", stage_out ? "true" : "false"}, {"OUT_W", num(OW)},
+                         // loading the next halo before the drain pays for the forward kernel (0.125 -> 0.117 ms) and costs the
+                         // backward one, whose epilogue is the longer Unpad pass (0.136 -> 0.175 ms): measured, conv-net m=8192
+                         {"PREFETCH", h.backward_input ? "false" : "true"}, {"ROWS_FIRST", h.unpad_rows_first ? "true" : "false"},
                          {"A_COORDS", a_coords.str()}, {"B_COORDS", b_coords.str()}, {"TAP_PIXEL", tap_pixel.str()}, {"OUT_OK", out_ok.str()},
                          {"OUT_INDEX", out_index.str()}, {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
     KernelLaunch l;
@@ -1076,6 +1079,7 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
     }
     if (M <= 16 && M * N <= 288 && K >= 65536 && c.epilogue.empty()) {
         int64_t nsplit = 1;
+        // at most 80 accumulators per thread; splitting further re-reads A and measured slower (0.133 -> 0.234 ms at 36)
         while (M * (N / nsplit) > 80 && nsplit < 32 && (N / nsplit) % 2 == 0) nsplit *= 2;
         if (N % nsplit != 0 || M * (N / nsplit) > 96) return false;
         const int64_t nth = N / nsplit;
