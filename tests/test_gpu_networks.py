@@ -119,3 +119,20 @@ def test_image_fit_test_graph(env):
     env.run(ex.test_graph, 0)
     want = run_graph(ex.test_graph_json, params, 0)
     assert max_rel_err(env.read(ex.image), want[ex.image.id]) <= 1e-5
+
+
+@pytest.mark.parametrize("precision", ["strict", "tf32"])
+@pytest.mark.parametrize("network,m", [("linear", 8), ("single-layer-dropout", 8), ("conv-net", 4), ("conv-blur-net", 2)])
+def test_cuda_matches_golden_steps(env, network, m, precision):
+    """The committed fixtures tests/golden/step_*.npz (one SGD step, every output) against the CUDA backend, without
+    running the oracle: 1e-5 relative for the strict-FP32 path (north_star), 2e-3 with TF32 tensor-core operands."""
+    from test_oracle_kat import load_golden_step
+    inputs, outputs, seed = load_golden_step(network, m)
+    env.set_tf32(precision == "tf32")
+    ex = env.example(network, m, optimizer="descent")
+    for pid, v in inputs.items():
+        env.write(env.parameter(pid), v)
+    env.run(ex.train_graph, seed)
+    tol = 1e-5 if precision == "strict" else 2e-3
+    worst = {pid: max_rel_err(env.read(env.parameter(pid)), want) for pid, want in outputs.items()}
+    assert max(worst.values()) <= tol, worst

@@ -1,6 +1,8 @@
 """Pins the CPU oracle (oracle/) against the reference's own known answers: the device tests of
 src/lib.rs:26-231, the array_api assert, and the bit-exact vectors derived in SURVEY.md Appendix D
 from kernel_common.glsl:205-216 and examples/image_fit/main.rs:163-175."""
+import os
+
 import numpy as np
 import pytest
 
@@ -95,3 +97,34 @@ def test_unpad_and_windows_adjoints():
     w = rng.standard_normal(win.shape).astype(np.float32)
     img = interp._windows_to_image(w.reshape(-1), list(w.shape), list(x.shape), 1, 1).reshape(x.shape)
     assert abs(float((win.astype(np.float64) * w).sum()) - float((x.astype(np.float64) * img).sum())) < 1e-3
+
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_STEPS = [("linear", 8), ("single-layer-dropout", 8), ("conv-net", 4), ("conv-blur-net", 2)]
+
+
+def load_golden_step(network, m):
+    z = np.load(os.path.join(GOLDEN_DIR, "step_%s_m%d.npz" % (network, m)))
+    inputs = {int(k[3:]): z[k] for k in z.files if k.startswith("in_")}
+    outputs = {int(k[4:]): z[k] for k in z.files if k.startswith("out_")}
+    return inputs, outputs, int(z["seed"][0])
+
+
+@pytest.mark.parametrize("network,m", GOLDEN_STEPS, ids=[g[0] for g in GOLDEN_STEPS])
+def test_oracle_reproduces_golden_steps(host_env, network, m):
+    """tests/golden/step_*.npz (made by tests/golden/make_golden.py) pin the oracle's arithmetic: one SGD step of each
+    fashion_mnist network, every output.  1e-6 relative leaves room for a different BLAS in the float64 products."""
+    inputs, outputs, seed = load_golden_step(network, m)
+    ex = host_env.example(network, m, optimizer="descent")
+    got = run_graph(ex.train_graph_json, inputs, seed)
+    assert set(got) == set(outputs)
+    for pid, want in outputs.items():
+        scale = max(float(np.abs(want).max()), 1e-30)
+        assert float(np.abs(got[pid].astype(np.float64) - want).max()) <= 1e-6 * scale, (network, pid)
+
+
+def test_integer_vectors_are_bit_exact():
+    """pcg hash and Rand (kernel_common.glsl:205-216) against the committed vectors."""
+    z = np.load(os.path.join(GOLDEN_DIR, "integer_vectors.npz"))
+    np.testing.assert_array_equal(interp.pcg(z["index"]), z["pcg"])
+    np.testing.assert_array_equal(interp.rand_from_index(3, z["index"], 7).view(np.uint32), z["rand_uid3_seed7"])
