@@ -125,7 +125,10 @@ def test_image_fit_test_graph(env):
 @pytest.mark.parametrize("network,m", [("linear", 8), ("single-layer-dropout", 8), ("conv-net", 4), ("conv-blur-net", 2)])
 def test_cuda_matches_golden_steps(env, network, m, precision):
     """The committed fixtures tests/golden/step_*.npz (one SGD step, every output) against the CUDA backend, without
-    running the oracle: 1e-5 relative for the strict-FP32 path (north_star), 2e-3 with TF32 tensor-core operands."""
+    running the oracle: 1e-5 relative for the strict-FP32 path (north_star).  With TF32 operands the hardware truncates
+    (test_gpu_gemm_tf32.py), a one-sided 2^-10 error per operand: 2e-3 of each tensor's maximum, except conv-blur-net at
+    m = 2, whose weight gradients are cancellation residues of two samples (5e-2; the same step matches the
+    TF32-emulating oracle to 1e-4 in test_gpu_tf32_and_dp.py)."""
     from test_oracle_kat import load_golden_step
     inputs, outputs, seed = load_golden_step(network, m)
     env.set_tf32(precision == "tf32")
@@ -133,6 +136,6 @@ def test_cuda_matches_golden_steps(env, network, m, precision):
     for pid, v in inputs.items():
         env.write(env.parameter(pid), v)
     env.run(ex.train_graph, seed)
-    tol = 1e-5 if precision == "strict" else 2e-3
+    tol = 1e-5 if precision == "strict" else (5e-2 if network == "conv-blur-net" else 2e-3)
     worst = {pid: max_rel_err(env.read(env.parameter(pid)), want) for pid, want in outputs.items()}
     assert max(worst.values()) <= tol, worst
