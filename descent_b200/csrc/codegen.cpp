@@ -997,16 +997,24 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     const int64_t TH = 128 / W, halo_rows = TH + FH - 1;
     if (FW - 1 > 4 || W % 4 != 0) return false;
     const int64_t npix = div_round_up(4 + halo_rows * W, 4) * 4;  // mirrors NPIX / X_BLOCK / X_BYTES of the template
-    const int64_t x_block = npix * 128, m_blocks = div_round_up(FW * G * C, 32), n_blocks = div_round_up(G * NCO, 32);
+    const int64_t x_block = npix * 128, m_blocks = div_round_up(FW * G * C, 32);
     // M = 64 would fit 48 real rows, but measured slower on B200 (0.227 vs 0.200 ms, conv-net m=8192): the MMA is paced
     // as if M were 128 either way and the third resident CTA does not pay for itself
     const int64_t m_rows = 128;
-    const int64_t x_bytes = std::max<int64_t>((m_rows / 32) * x_block, m_blocks * x_block + n_blocks * 128 * 128);
+    // one wide MMA per k-step when all filter rows fit in N <= 256 and the FH dY copies fit in shared memory
+    // (measured on conv-net m=8192: 0.201 -> 0.152 ms)
+    bool wide = FH * G * NCO <= 256;
+    auto smem_bytes = [&](bool w) {
+        const int64_t y_block = (w ? halo_rows * W : 128) * 128, nb = div_round_up(w ? FH * G * NCO : G * NCO, 32);
+        return std::max<int64_t>((m_rows / 32) * x_block, m_blocks * x_block + nb * y_block);
+    };
+    if (wide && (smem_bytes(true) + 64 + 1024 > 110 * 1024 || (halo_rows * W * 128) / 16 > 0x3fff)) wide = false;  // keep two CTAs per SM
+    const int64_t x_bytes = smem_bytes(wide);
     if (x_block / 16 > 0x3fff || x_bytes + 64 + 1024 > 200 * 1024) return false;
     if (halo_rows * W * (G * C / 4) > 256 * 12 || 128 * (G * NCO / 4) > 256 * 12) return false;  // staged loads per thread
     const int64_t smem = x_bytes + 64 + 1024;
     const int64_t tiles = B * div_round_up(OH, TH);
-    const int64_t resident = std::max<int64_t>(1, std::min<int64_t>({4, (200 * 1024) / smem, 512 / tmem_cols}));
+    const int64_t resident = std::max<int64_t>(1, std::min<int64_t>({4, (224 * 1024) / (smem + 1024), 512 / tmem_cols}));  // 227 KB per SM, 1 KB reserved per CTA
     const int64_t S = std::min<int64_t>(tiles, (int64_t)opt.sm_count * resident);
 
     int uniq = 0;
@@ -1015,7 +1023,7 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     std::string ib = emit_chain(cb, b.chain, {{"batch", MPIX * NCO, G}, {"gk", NCO, MPIX}, {"gn", 1, NCO}}, uniq, "                ");
     const std::string name = "k" + num(ci);
     out->source = subst(kHaloWgradTemplate, {{"LABEL", c.label}, {"NAME", name}, {"G", num(G)}, {"IMAGES", num(B)}, {"OH", num(OH)}, {"OW", num(OW)},
-                                             {"FH", num(FH)}, {"FW", num(FW)}, {"CG", num(C)}, {"NCO", num(NCO)}, {"TMEM_COLS", num(tmem_cols)}, {"MROWS", num(m_rows)},
+                                             {"FH", num(FH)}, {"FW", num(FW)}, {"CG", num(C)}, {"NCO", num(NCO)}, {"TMEM_COLS", num(tmem_cols)}, {"MROWS", num(m_rows)}, {"WIDE", wide ? "true" : "false"},
                                              {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
     const int64_t out_count = G * KW * NCO;
     KernelLaunch l;
