@@ -1519,65 +1519,122 @@ const char* kScatterTemplate = R"(
 // {{LABEL}}: per-chunk sorted partial sums ({{NSRC}} chained source(s))
 extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part({{SRC_PARAMS}}float* partial, const unsigned* dsc_step) {
     constexpr unsigned CH = {{CH}}u, ROWS = {{ROWS}}u, INNER = {{INNER}}u, OUTER = {{OUTER}}u, PER = CH / 256u;
-    __shared__ unsigned keys[CH];
-    __shared__ float vals[CH];
-    const unsigned tid = threadIdx.x, gchunk = blockIdx.x, outer = blockIdx.y;
-    for (unsigned lp = tid; lp < CH; lp += 256u) {
-        unsigned key = 0xffffffffu;
+    constexpr unsigned NONE = 0xffffffffu;
+    __shared__ unsigned keys[CH + 1];
+    struct Run { unsigned row; float sum; unsigned open; };
+    __shared__ Run warp_tail[8];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, gchunk = blockIdx.x, outer = blockIdx.y;
+    // element i = tid + q * 256 lives in register q of thread tid while sorting
+    unsigned sk[PER];
+    #pragma unroll
+    for (unsigned q = 0; q < PER; ++q) {
+        const unsigned lp = tid + q * 256u;
+        unsigned key = NONE;
 {{LOAD_KEYS}}
-        keys[lp] = key;
+        sk[q] = key;
     }
-    __syncthreads();
-    // bitonic sort: keys are unique, so the order (row, then position) is fully determined
+    // bitonic sort; keys are unique, so the order (row, then position) is fully determined.  Partners 256 or 512
+    // apart sit in the same thread, partners closer than 32 in the same warp (shuffles); only the three distances
+    // in between go through shared memory.
+    #pragma unroll
     for (unsigned k = 2; k <= CH; k <<= 1) {
+        #pragma unroll
         for (unsigned j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned i = tid; i < CH; i += 256u) {
-                const unsigned ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned a = keys[i], b = keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+            if (j >= 256u) {
+                #pragma unroll
+                for (unsigned q = 0; q < PER; ++q) {
+                    const unsigned qq = q ^ (j >> 8);
+                    if (qq > q) {
+                        const bool up = ((tid + q * 256u) & k) == 0;
+                        const unsigned a = sk[q], b = sk[qq];
+                        if ((a > b) == up) { sk[q] = b; sk[qq] = a; }
+                    }
                 }
+            } else if (j < 32u) {
+                #pragma unroll
+                for (unsigned q = 0; q < PER; ++q) {
+                    const unsigned i = tid + q * 256u;
+                    const unsigned other = __shfl_xor_sync(0xffffffffu, sk[q], j);
+                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                    sk[q] = keep_min ? min(sk[q], other) : max(sk[q], other);
+                }
+            } else {
+                #pragma unroll
+                for (unsigned q = 0; q < PER; ++q) keys[tid + q * 256u] = sk[q];
+                __syncthreads();
+                #pragma unroll
+                for (unsigned q = 0; q < PER; ++q) {
+                    const unsigned i = tid + q * 256u;
+                    const unsigned other = keys[i ^ j];
+                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                    sk[q] = keep_min ? min(sk[q], other) : max(sk[q], other);
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
+    }
+    #pragma unroll
+    for (unsigned q = 0; q < PER; ++q) keys[tid + q * 256u] = sk[q];
+    if (tid == 0) keys[CH] = NONE;
+    __syncthreads();
+    // sums of equal rows: thread t now owns the sorted elements t * PER .. t * PER + PER - 1
+    unsigned row[PER + 1], pos[PER];
+    #pragma unroll
+    for (unsigned q = 0; q <= PER; ++q) {
+        const unsigned key = keys[tid * PER + q];
+        row[q] = key == NONE ? NONE : key / CH;
+        if (q < PER) pos[q] = key % CH;
     }
     for (unsigned w = 0; w < INNER; ++w) {
-        for (unsigned i = tid; i < CH; i += 256u) {
-            const unsigned key = keys[i];
+        float val[PER];
+        #pragma unroll
+        for (unsigned q = 0; q < PER; ++q) {
             float v = 0.f;
-            if (key != 0xffffffffu) {
-                const unsigned lp = key % CH;
+            if (row[q] != NONE) {
+                const unsigned lp = pos[q];
 {{LOAD_VALUES}}
             }
-            vals[i] = v;
+            val[q] = v;
         }
+        // inclusive segmented sums inside the thread, then across threads: a fixed order of additions
+        #pragma unroll
+        for (unsigned q = 1; q < PER; ++q)
+            if (row[q] == row[q - 1]) val[q] += val[q - 1];
+        Run run{row[PER - 1], val[PER - 1], row[0] == row[PER - 1] ? 1u : 0u};  // the run that ends at this thread's last element
+        #pragma unroll
+        for (unsigned d = 1; d < 32u; d <<= 1) {
+            const unsigned r = __shfl_up_sync(0xffffffffu, run.row, d);
+            const float s = __shfl_up_sync(0xffffffffu, run.sum, d);
+            const unsigned o = __shfl_up_sync(0xffffffffu, run.open, d);
+            if (lane >= d && run.open && r == run.row) { run.sum = s + run.sum; run.open = o; }
+        }
+        if (lane == 31u) warp_tail[warp] = run;
         __syncthreads();
-        // segmented inclusive scan (Hillis-Steele); equal rows at distance d imply one segment between them
-        for (unsigned d = 1; d < CH; d <<= 1) {
-            float add[PER];
-            #pragma unroll
-            for (unsigned q = 0; q < PER; ++q) {
-                const unsigned i = tid + q * 256u;
-                add[q] = 0.f;
-                if (i >= d && keys[i] != 0xffffffffu && keys[i - d] / CH == keys[i] / CH) add[q] = vals[i - d];
-            }
-            __syncthreads();
-            #pragma unroll
-            for (unsigned q = 0; q < PER; ++q) {
-                const unsigned i = tid + q * 256u;
-                if (i >= d && keys[i] != 0xffffffffu && keys[i - d] / CH == keys[i] / CH) vals[i] = add[q] + vals[i];
-            }
-            __syncthreads();
+        // carry into this thread = the run that ends at the previous thread's last element, over the whole block
+        Run before{NONE, 0.f, 0u};
+        for (unsigned pw = 0; pw < warp; ++pw) {  // earlier warps, in order
+            const Run t = warp_tail[pw];
+            if (t.open && before.row == t.row) before.sum = before.sum + t.sum;
+            else before = t;
         }
-        for (unsigned i = tid; i < CH; i += 256u) {
-            const unsigned key = keys[i];
-            if (key == 0xffffffffu) continue;
-            const unsigned row = key / CH;
-            const bool tail = (i == CH - 1) || (keys[i + 1] / CH != row);
-            if (tail) partial[((gchunk * OUTER + outer) * ROWS + row) * INNER + w] = vals[i];
+        {
+            Run prev;  // previous lane's inclusive run (within the warp)
+            prev.row = __shfl_up_sync(0xffffffffu, run.row, 1);
+            prev.sum = __shfl_up_sync(0xffffffffu, run.sum, 1);
+            prev.open = __shfl_up_sync(0xffffffffu, run.open, 1);
+            if (lane > 0) {
+                if (prev.open && before.row == prev.row) before.sum = before.sum + prev.sum;
+                else before = prev;
+            }
         }
-        __syncthreads();
+        #pragma unroll
+        for (unsigned q = 0; q < PER; ++q) {
+            if (row[q] == NONE) continue;
+            const bool head_run = row[q] == row[0];
+            const float total = (head_run && before.row == row[q]) ? before.sum + val[q] : val[q];
+            if (row[q + 1] != row[q]) partial[((gchunk * OUTER + outer) * ROWS + row[q]) * INNER + w] = total;
+        }
+        __syncthreads();  // warp_tail is reused by the next w
     }
 }
 
