@@ -712,14 +712,24 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
 #include "halo_wgrad_template.inc"
 
 const char* kSplitSumTemplate = R"(
-// split-K partial sums of {{LABEL}}, added in ascending split order
+// split-K partial sums of {{LABEL}}: 32 outputs x 8 split lanes per CTA.  Lane g adds splits g, g + 8, ... in ascending
+// order, then the eight lane sums are added in lane order: a fixed order, independent of timing.
 extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws, float* out0, const unsigned* dsc_step) {
     constexpr unsigned COUNT = {{COUNT}}u, S = {{S}}u;
-    const unsigned i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= COUNT) return;
-    float acc = ws[i];
-    #pragma unroll 8
-    for (unsigned s = 1; s < S; ++s) acc += ws[s * COUNT + i];
+    __shared__ float red[8][32];
+    const unsigned tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+    const unsigned i = blockIdx.x * 32u + tx;
+    float part = 0.f;
+    if (i < COUNT) {
+        #pragma unroll 4
+        for (unsigned s = ty; s < S; s += 8u) part += ws[s * COUNT + i];
+    }
+    red[ty][tx] = part;
+    __syncthreads();
+    if (ty != 0 || i >= COUNT) return;
+    float acc = red[0][tx];
+    #pragma unroll
+    for (unsigned g = 1; g < 8u; ++g) acc += red[g][tx];
     out0[i] = acc;
 }
 )";
@@ -1042,7 +1052,7 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     out->source += subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
     KernelLaunch s;
     s.entry = sname;
-    s.grid_x = (uint32_t)div_round_up(out_count, 256);
+    s.grid_x = (uint32_t)div_round_up(out_count, 32);
     s.label = "SplitSum " + c.label;
     s.cluster = ci;
     s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
@@ -1109,7 +1119,7 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
             out->source += subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
             KernelLaunch s;
             s.entry = sname;
-            s.grid_x = (uint32_t)div_round_up(out_count, 256);
+            s.grid_x = (uint32_t)div_round_up(out_count, 32);
             s.label = "SplitSum " + c.label;
             s.cluster = ci;
             s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
@@ -1214,7 +1224,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
                 code.source = subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
                 KernelLaunch sum;
                 sum.entry = sname;
-                sum.grid_x = (uint32_t)div_round_up(out_count, 256);
+                sum.grid_x = (uint32_t)div_round_up(out_count, 32);
                 sum.label = "SplitSum " + c.label;
                 sum.cluster = ci;
                 sum.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
@@ -1362,7 +1372,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
         code.source += subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
         KernelLaunch s;
         s.entry = sname;
-        s.grid_x = (uint32_t)div_round_up(out_count, 256);
+        s.grid_x = (uint32_t)div_round_up(out_count, 32);
         s.label = "SplitSum " + c.label;
         s.cluster = ci;
         s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
@@ -1519,11 +1529,20 @@ const char* kScatterTemplate = R"(
 // {{LABEL}}: per-chunk sorted partial sums ({{NSRC}} chained source(s))
 extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part({{SRC_PARAMS}}float* partial, const unsigned* dsc_step) {
     constexpr unsigned CH = {{CH}}u, ROWS = {{ROWS}}u, INNER = {{INNER}}u, OUTER = {{OUTER}}u, PER = CH / 256u;
+    constexpr unsigned NCHUNK = {{NCHUNK}}u, CPB = {{CPB}}u;  // chunks in total, chunks per CTA
+    constexpr bool TABLE = {{TABLE}};  // the whole table fits in shared memory: a CTA adds its chunks there, in chunk order,
+                                       // and writes one dense partial (no zero fill of the scratch buffer, CPB x fewer partials)
     constexpr unsigned NONE = 0xffffffffu;
     __shared__ unsigned keys[CH + 1];
     struct Run { unsigned row; float sum; unsigned open; };
     __shared__ Run warp_tail[8];
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, gchunk = blockIdx.x, outer = blockIdx.y;
+    __shared__ float table[TABLE ? ROWS * INNER : 1];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, outer = blockIdx.y;
+    if (TABLE) {
+        for (unsigned i = tid; i < ROWS * INNER; i += 256u) table[i] = 0.f;
+        __syncthreads();
+    }
+    for (unsigned gchunk = blockIdx.x * CPB; gchunk < min(NCHUNK, (blockIdx.x + 1u) * CPB); ++gchunk) {
     // element i = tid + q * 256 lives in register q of thread tid while sorting
     unsigned sk[PER];
     #pragma unroll
@@ -1632,17 +1651,23 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part({{SRC_PARAMS}}fl
             if (row[q] == NONE) continue;
             const bool head_run = row[q] == row[0];
             const float total = (head_run && before.row == row[q]) ? before.sum + val[q] : val[q];
-            if (row[q + 1] != row[q]) partial[((gchunk * OUTER + outer) * ROWS + row[q]) * INNER + w] = total;
+            if (row[q + 1] != row[q]) {
+                if (TABLE) table[row[q] * INNER + w] += total;  // one thread per (row, w) and chunk; chunks are separated by barriers
+                else partial[((gchunk * OUTER + outer) * ROWS + row[q]) * INNER + w] = total;
+            }
         }
         __syncthreads();  // warp_tail is reused by the next w
     }
+    }
+    if (TABLE)
+        for (unsigned i = tid; i < ROWS * INNER; i += 256u) partial[(blockIdx.x * OUTER + outer) * ROWS * INNER + i] = table[i];
 }
 
 // {{LABEL}}: accumulator + chunk partials in ascending chunk order
 extern "C" __global__ void __launch_bounds__(256) {{NAME}}_sum({{ACC_PARAM}}const float* partial, float* out0, const unsigned* dsc_step) {
     // 32 table elements x 8 chunk lanes per CTA: lane g adds chunks g, g+8, ... in ascending order, then the eight
     // lane sums are added to the accumulator in lane order -- a fixed order, independent of timing
-    constexpr unsigned TOTAL = {{TOTAL}}u, NCHUNK = {{NCHUNK}}u;
+    constexpr unsigned TOTAL = {{TOTAL}}u, NCHUNK = {{NBLOCKS}}u;
     __shared__ float red[8][32];
     const unsigned tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
     const unsigned e = blockIdx.x * 32u + tx;
@@ -1662,7 +1687,7 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}_sum({{ACC_PARAM}}cons
 }
 )";
 
-ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci) {
+ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
     const OpNode& node = g.ops().nodes[c.node_id];  // the first scatter of the chain: same table shape and axis as the rest
     const int nsrc = (int)c.members.size();
     const int axis = node.op.axis;
@@ -1707,23 +1732,30 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci) {
     if (acc_literal) acc_value = "__uint_as_float(" + num(acc_node.op.literal_bits) + "u)";
     else acc_value = "acc_in[" + emit_chain(ac, c.inputs[2 * nsrc].chain, "e", uniq, "    ") + "]";
     const std::string name = "k" + num(ci);
+    // small tables are accumulated in shared memory, several chunks per CTA (two waves of CTAs at least)
+    const bool table = rows * inner <= 8192;
+    const int64_t cpb = table ? std::max<int64_t>(1, std::min<int64_t>(8, nchunk_total / (2 * opt.sm_count))) : 1;
+    const int64_t nblocks = div_round_up(nchunk_total, cpb);
     ClusterCode code;
     code.source = subst(kScatterTemplate,
                         {{"LABEL", c.label}, {"NAME", name}, {"NSRC", num(nsrc)}, {"SRC_PARAMS", params.str()}, {"CH", num(ch)}, {"ROWS", num(rows)},
                          {"INNER", num(inner)}, {"OUTER", num(outer)}, {"LOAD_KEYS", load_keys.str()}, {"LOAD_VALUES", load_values.str()},
-                         {"ACC_PARAM", acc_literal ? "" : "const float* acc_in, "}, {"TOTAL", num(total)}, {"NCHUNK", num(nchunk_total)},
+                         {"ACC_PARAM", acc_literal ? "" : "const float* acc_in, "}, {"TOTAL", num(total)}, {"NCHUNK", num(nchunk_total)}, {"NBLOCKS", num(nblocks)},
+                         {"CPB", num(cpb)}, {"TABLE", table ? "true" : "false"},
                          {"ACC_CHAIN", ac.str()}, {"ACC_VALUE", acc_value}});
-    code.scratch_bytes = nchunk_total * total * 4;
-    KernelLaunch z;
-    z.kind = KernelLaunch::ZeroScratch;
-    z.zero_offset = 0;
-    z.zero_bytes = code.scratch_bytes;
-    z.label = "Fill(0) " + num(nchunk_total * total);
-    z.cluster = ci;
-    code.launches.push_back(z);
+    code.scratch_bytes = nblocks * total * 4;
+    if (!table) {
+        KernelLaunch z;
+        z.kind = KernelLaunch::ZeroScratch;
+        z.zero_offset = 0;
+        z.zero_bytes = code.scratch_bytes;
+        z.label = "Fill(0) " + num(nblocks * total);
+        z.cluster = ci;
+        code.launches.push_back(z);
+    }
     KernelLaunch p;
     p.entry = name + "_part";
-    p.grid_x = (uint32_t)nchunk_total;
+    p.grid_x = (uint32_t)nblocks;
     p.grid_y = (uint32_t)outer;
     p.label = c.label;
     p.cluster = ci;
@@ -1792,7 +1824,7 @@ ClusterCode generate_cluster_code(const Graph& graph, int ci, const CodegenOptio
         case ClusterKind::MatMul: return gen_matmul(graph, c, ci, opt);
         case ClusterKind::Unpad: return gen_unpad(graph, c, ci);
         case ClusterKind::WindowsToImage: return gen_w2i(graph, c, ci);
-        case ClusterKind::ScatterAdd: return gen_scatter_add(graph, c, ci);
+        case ClusterKind::ScatterAdd: return gen_scatter_add(graph, c, ci, opt);
         case ClusterKind::AllReduce: {
             ClusterCode code;
             KernelLaunch l;
