@@ -6,6 +6,7 @@
 #include "codegen.hpp"
 
 #include <cmath>
+#include <map>
 #include <cstdlib>
 #include <cstdio>
 
@@ -481,7 +482,7 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws, floa
 }
 )";
 
-ClusterCode gen_reduce(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
+ClusterCode gen_reduce(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, const std::string& name_suffix = "") {
     const OpNode& node = g.ops().nodes[c.node_id];
     const ClusterInput& in = c.inputs[0];
     const int axis = node.op.axis;
@@ -518,7 +519,7 @@ ClusterCode gen_reduce(const Graph& g, const Cluster& c, int ci, const CodegenOp
     int uniq = 0;
     std::string idx = emit_chain(chain, in.chain, "e", uniq, "            ");
     const bool is_max = node.op.reduce == ReduceOp::Max;
-    const std::string name = "k" + num(ci);
+    const std::string name = "k" + num(ci) + name_suffix;
     ClusterCode code;
     if (vec4)
         code.source = subst(kReduceVec4Template,
@@ -1011,6 +1012,7 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     // M = 64 would fit 48 real rows, but measured slower on B200 (0.227 vs 0.200 ms, conv-net m=8192): the MMA is paced
     // as if M were 128 either way and the third resident CTA does not pay for itself
     const int64_t m_rows = 128;
+    const bool colsum = !c.column_sum.empty() && 256 % (G * NCO / 4) == 0;  // dY is summed on the side (bias gradient), exact FP32
     // one wide MMA per k-step when all filter rows fit in N <= 256 and the FH dY copies fit in shared memory
     // (measured on conv-net m=8192: 0.201 -> 0.152 ms)
     bool wide = FH * G * NCO <= 256;
@@ -1034,8 +1036,10 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     const std::string name = "k" + num(ci);
     out->source = subst(kHaloWgradTemplate, {{"LABEL", c.label}, {"NAME", name}, {"G", num(G)}, {"IMAGES", num(B)}, {"OH", num(OH)}, {"OW", num(OW)},
                                              {"FH", num(FH)}, {"FW", num(FW)}, {"CG", num(C)}, {"NCO", num(NCO)}, {"TMEM_COLS", num(tmem_cols)}, {"MROWS", num(m_rows)}, {"WIDE", wide ? "true" : "false"},
+                                             {"COLSUM", colsum ? "true" : "false"},
                                              {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
     const int64_t out_count = G * KW * NCO;
+    const int64_t colsum_offset = div_round_up(S * out_count * 4, 256) * 256;
     KernelLaunch l;
     l.entry = name;
     l.grid_x = (uint32_t)S;
@@ -1043,7 +1047,8 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     l.smem = (uint32_t)smem;
     l.label = "TensorCore" + c.label;
     l.cluster = ci;
-    l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::Scratch, -1, 0}};
+    l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::Scratch, -1, 0},
+              {KernelArg::Scratch, -1, colsum ? colsum_offset : 0}};
     l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)out_count;
     l.flops = 2.0 * (double)G * (double)KW * (double)NCO * (double)MPIX;
     out->launches.push_back(l);
@@ -1057,6 +1062,19 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     s.cluster = ci;
     s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
     out->launches.push_back(s);
+    if (colsum) {
+        out->column_sum_done = true;
+        out->scratch_bytes = colsum_offset + S * G * NCO * 4;
+        const std::string cname = name + "_colsum";
+        out->source += subst(kSplitSumTemplate, {{"LABEL", "column sums of " + c.label}, {"NAME", cname}, {"COUNT", num(G * NCO)}, {"S", num(S)}});
+        KernelLaunch cs;
+        cs.entry = cname;
+        cs.grid_x = (uint32_t)div_round_up(G * NCO, 32);
+        cs.label = "SplitSum column sums " + c.label;
+        cs.cluster = ci;
+        cs.args = {{KernelArg::Scratch, -1, colsum_offset}, {KernelArg::NodeBuffer, c.outputs[1], 0}};
+        out->launches.push_back(cs);
+    }
     return true;
 }
 
@@ -1104,17 +1122,38 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
         const bool b_vec = nth % 4 == 0 && chain_vector_run_axis(b.chain, b.arg_shape, 2) == 4;
         std::string ia = emit_chain(ca, a.chain, {{"batch", M * K, BC}, {"gm", K, M}, {"gk", 1, K}}, uniq, "            ");
         std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, BC}, {"gk", N, K}, {"gn", 1, N}}, uniq, "                ");
+        const bool colsum = !c.column_sum.empty();
         out->source = subst(kThinReduceTemplate, {{"LABEL", c.label}, {"NAME", name}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"BC", num(BC)},
+                                                 {"COLSUM", colsum ? "true" : "false"},
                                                  {"NSPLIT", num(nsplit)}, {"B_VEC", b_vec ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
                                                  {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
         const int64_t rows_per_cta = 256 / nsplit;
         const int64_t S = std::max<int64_t>(1, std::min<int64_t>((int64_t)opt.sm_count * 2 / BC, K / (rows_per_cta * 8)));
         l.grid_x = (uint32_t)S;
         const int64_t out_count = BC * M * N;
+        // column sums: [S, BC, N] partials behind the product's partials, or straight into outputs[1]
+        const int64_t colsum_offset = div_round_up(S * out_count * 4, 256) * 256;
+        const KernelArg colsum_arg = !colsum ? KernelArg{KernelArg::NodeBuffer, c.outputs[0], 0}  // unused by the kernel
+                                     : S > 1 ? KernelArg{KernelArg::Scratch, -1, colsum_offset} : KernelArg{KernelArg::NodeBuffer, c.outputs[1], 0};
+        out->column_sum_done = colsum;
+        if (colsum) l.algorithmic_bytes += 4.0 * (double)(BC * N);
         if (S > 1) {
             l.args.push_back({KernelArg::Scratch, -1, 0});
+            l.args.push_back(colsum_arg);
             out->launches.push_back(l);
             out->scratch_bytes = S * out_count * 4;
+            if (colsum) {
+                out->scratch_bytes = colsum_offset + S * BC * N * 4;
+                const std::string cname = name + "_colsum";
+                out->source += subst(kSplitSumTemplate, {{"LABEL", "column sums of " + c.label}, {"NAME", cname}, {"COUNT", num(BC * N)}, {"S", num(S)}});
+                KernelLaunch cs;
+                cs.entry = cname;
+                cs.grid_x = (uint32_t)div_round_up(BC * N, 32);
+                cs.label = "SplitSum column sums " + c.label;
+                cs.cluster = ci;
+                cs.args = {{KernelArg::Scratch, -1, colsum_offset}, {KernelArg::NodeBuffer, c.outputs[1], 0}};
+                out->launches.push_back(cs);
+            }
             const std::string sname = name + "_splitsum";
             out->source += subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
             KernelLaunch s;
@@ -1126,6 +1165,7 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
             out->launches.push_back(s);
         } else {
             l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
+            l.args.push_back(colsum_arg);
             out->launches.push_back(l);
         }
         return true;
@@ -1210,7 +1250,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
             // few output tiles and a long reduction (dense-layer weight gradients): slice k across the idle SMs
             const int64_t tiles = div_round_up(M, 128) * div_round_up(N, 128), k_blocks = div_round_up(K, 32);
             int64_t S = 1;
-            if (tiles * 2 <= opt.sm_count && k_blocks >= 16) {
+            if (tiles * 4 <= opt.sm_count && k_blocks >= 16) {  // below 4 slices the extra pass over [S, M, N] costs more than it saves
                 S = std::min<int64_t>(opt.sm_count / tiles, k_blocks / 8);
                 const int64_t per = div_round_up(k_blocks, S);
                 S = div_round_up(k_blocks, per);
@@ -1821,7 +1861,34 @@ ClusterCode generate_cluster_code(const Graph& graph, int ci, const CodegenOptio
     switch (c.kind) {
         case ClusterKind::PerElement: return gen_per_element(graph, c, ci, opt);
         case ClusterKind::Reduce: return gen_reduce(graph, c, ci, opt);
-        case ClusterKind::MatMul: return gen_matmul(graph, c, ci, opt);
+        case ClusterKind::MatMul: {
+            ClusterCode code = gen_matmul(graph, c, ci, opt);
+            if (!c.column_sum.empty() && !code.column_sum_done) {
+                // the GEMM kernel chosen for this shape does not produce the column sums: run the absorbed Reduce chain
+                // after it, intermediate results in scratch
+                std::map<int, int64_t> scratch_of;  // intermediate reduce node -> scratch offset
+                for (size_t i = 0; i < c.column_sum.size(); ++i) {
+                    const Cluster& rc = c.column_sum[i];
+                    ClusterCode r = gen_reduce(graph, rc, ci, opt, "_colsum" + num((int64_t)i));
+                    const int64_t base = div_round_up(code.scratch_bytes, 256) * 256;
+                    code.scratch_bytes = base + div_round_up(r.scratch_bytes, 256) * 256;
+                    if (i + 1 < c.column_sum.size()) {
+                        scratch_of[rc.outputs[0]] = code.scratch_bytes;
+                        code.scratch_bytes += div_round_up(graph.ops().nodes[rc.outputs[0]].shape.element_count() * 4, 256) * 256;
+                    }
+                    code.source += r.source;
+                    for (auto& l : r.launches) {
+                        for (auto& arg : l.args) {
+                            if (arg.kind == KernelArg::Scratch) arg.scratch_offset += base;
+                            else if (scratch_of.count(arg.node_id)) arg = KernelArg{KernelArg::Scratch, -1, scratch_of[arg.node_id]};
+                        }
+                        if (l.kind == KernelLaunch::ZeroScratch) l.zero_offset += base;
+                        code.launches.push_back(l);
+                    }
+                }
+            }
+            return code;
+        }
         case ClusterKind::Unpad: return gen_unpad(graph, c, ci);
         case ClusterKind::WindowsToImage: return gen_w2i(graph, c, ci);
         case ClusterKind::ScatterAdd: return gen_scatter_add(graph, c, ci, opt);

@@ -33,6 +33,7 @@ struct ClusterCode {
     std::string source;
     std::vector<KernelLaunch> launches;
     int64_t scratch_bytes = 0;
+    bool column_sum_done = false;  // the GEMM kernel also produced Cluster::column_sum's result (outputs[1])
 };
 
 struct CodegenOptions {

@@ -584,6 +584,65 @@ void Graph::absorb_per_element_epilogues(std::vector<Cluster>& clusters) {
     }
 }
 
+// dW = A^T x dY and db = column sums of dY read the same array: when the graph reduces the GEMM's B operand [K, C]
+// over all of K (reduce_sum axis by axis, array.rs) and nothing needs the result before the GEMM's turn, the Reduce
+// chain joins the MatMul's cluster (see Cluster::column_sum).
+void Graph::absorb_column_sums(std::vector<Cluster>& clusters) {
+    auto cons = ops_.consumers();
+    for (size_t mi = 0; mi < clusters.size(); ++mi) {
+        Cluster& mc = clusters[mi];
+        if (mc.kind != ClusterKind::MatMul || mc.members.empty() || !mc.epilogue.empty() || mc.conv_backward_input.enabled || !mc.column_sum.empty()) continue;
+        const ClusterInput& b = mc.inputs[1];
+        const int64_t G = b.arg_shape[0], K = b.arg_shape[1], N = b.arg_shape[2], C = G * N;
+        const OpNode& y = ops_.nodes[b.node_id];
+        if (K < 4096 || y.shape.element_count() != K * C || y.shape.at(-1) != C) continue;
+        // B[g, k, n] must be Y[k * C + g * N + n]
+        if (b.chain.views.size() > 1 || (!b.chain.views.empty() && b.chain.views[0].any_clamp())) continue;
+        if (eval_chain(b.chain, 0) != 0 || (G > 1 && eval_chain(b.chain, K * N) != N) || (K > 1 && eval_chain(b.chain, N) != C) ||
+            (N > 1 && eval_chain(b.chain, 1) != 1))
+            continue;
+        // follow Reduce(sum) nodes from Y while each has a single consumer; stop when K has been summed away
+        std::vector<int> chain;
+        int cur = b.node_id;
+        int64_t reduced = 1;
+        while (reduced < K) {
+            int next = -1;
+            for (auto [dst, k] : cons[cur]) {
+                const OpNode& d = ops_.nodes[dst];
+                const OpEdge& e = d.in[k];
+                if (d.op.kind == OpKind::Reduce && d.op.reduce == ReduceOp::Sum && e.chain.is_identity() && d.cluster_id >= 0 &&
+                    clusters[d.cluster_id].kind == ClusterKind::Reduce && clusters[d.cluster_id].members.size() == 1 &&
+                    d.op.axis < e.arg_shape.len() - 1 && e.arg_shape.at(-1) == C && (cur == b.node_id || cons[cur].size() == 1)) {
+                    next = dst;
+                    reduced *= e.arg_shape[d.op.axis];
+                    break;
+                }
+            }
+            if (next < 0) break;
+            chain.push_back(next);
+            cur = next;
+        }
+        if (chain.empty() || reduced != K || ops_.nodes[cur].shape.element_count() != C) continue;
+        // nobody may need the sums before this cluster runs, and they must not be stored straight into a parameter
+        bool ok = true;
+        for (auto [dst, k] : cons[cur]) {
+            const OpNode& d = ops_.nodes[dst];
+            if (d.op.kind == OpKind::Output || (d.cluster_id >= 0 && clusters[d.cluster_id].level <= mc.level)) ok = false;
+        }
+        if (!ok) continue;
+        for (int id : chain) {
+            Cluster& rc = clusters[ops_.nodes[id].cluster_id];
+            mc.column_sum.push_back(rc);
+            rc.members.clear();
+            rc.outputs.clear();
+            mc.members.push_back(id);
+            ops_.nodes[id].cluster_id = (int)mi;
+        }
+        mc.outputs.push_back(cur);
+        mc.label += " +ColumnSum";
+    }
+}
+
 // The Unpad(s) that undo conv2d's replicate padding run in the epilogue of the fused backward-input kernel: the
 // padded image gradient is never written either.
 bool Graph::absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id) {
@@ -886,6 +945,7 @@ void Graph::build_clusters() {
     for (auto& c : clusters)
         if (c.kind == ClusterKind::PerElement) build_per_element_program(c);
     absorb_per_element_epilogues(clusters);
+    absorb_column_sums(clusters);
 
     // levels are a topological order of clusters: fusable edges stay inside a cluster, all others climb
     std::vector<int> idx(clusters.size());

@@ -74,6 +74,11 @@ struct Cluster {
     // its other inputs are appended to `inputs` (from index 2 on, in order) and its outputs replace `outputs`.
     std::vector<Cluster> epilogue;
     int epilogue_product_input = -1;
+    // MatMul whose B operand is a [K, C] array that the graph also sums over K with a chain of Reduce(sum) nodes (the
+    // bias gradient next to a convolution's / dense layer's weight gradient: both read dY once per step).  The GEMM
+    // kernels that stream B produce those column sums on the side; `column_sum[i]` are the absorbed Reduce clusters in
+    // order (other GEMM kernels simply run them after the product) and outputs[1] is the last Reduce's node.
+    std::vector<Cluster> column_sum;
     std::string label;                 // as the reference's Kernel::label_name (kernel.rs)
 };
 
@@ -104,6 +109,7 @@ private:
     void hoist_all_reduce_views();
     void sink_permutations_into_per_element();
     void absorb_per_element_epilogues(std::vector<Cluster>& clusters);
+    void absorb_column_sums(std::vector<Cluster>& clusters);
     bool absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     bool absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     void build_clusters();

@@ -129,4 +129,6 @@ def test_split_k_reduce_is_absorbed(host_env):
     for n in g["nodes"]:
         by_cluster.setdefault(n["cluster"], []).append(n["op"])
     for n in mm:
-        assert sorted(by_cluster[n["cluster"]]) == ["MatMul", "Reduce"]
+        ops = sorted(by_cluster[n["cluster"]])
+        # the split-K Reduce always; further Reduce nodes are the bias-gradient chain that shares the GEMM's B operand
+        assert ops[:2] == ["MatMul", "Reduce"] and set(ops[2:]) <= {"Reduce"}, ops
