@@ -9,8 +9,8 @@ One JSON line on rank 0.  `value` = global samples / max-over-ranks device time 
 batch resident in HBM; `e2e` = the same through the public API with host buffers: every step uploads one batch
 from pinned host memory (Environment.prefetch_pinned, overlapped with the previous step on a copy stream), runs,
 and reads the loss back.  `roofline` describes the kernel with the largest share of the step (CUDA events per
-launch on the context's stream), against MEASURED_PEAKS.json.  `cpu_baseline` times the numpy port of the
-reference semantics (oracle/) on a bounded sample of the same workload on the host cores.
+launch on the context's stream), against MEASURED_PEAKS.json.  `cpu_baseline` times the multi-threaded C++ port of the
+reference's op semantics (oracle/cpu_ref.cpp) on a bounded sample of the same workload on all host cores.
 """
 import argparse
 import json
@@ -91,55 +91,79 @@ def make_inputs(ex, rng, network):
     return params, x, y
 
 
-def cpu_baseline(network, sample_batch, optimizer, steps=2):
-    """The numpy port of the reference semantics (oracle/) on a bounded sample: host-only graph build, then the
-    interpreter runs whole training steps.  numpy's BLAS threads are whatever the box gives it."""
-    import descent_b200 as d
-    from oracle import run_graph
-    env = d.Environment(-1)
-    ex = env.example(network, sample_batch, optimizer=optimizer)
-    rng = np.random.default_rng(0x5EED5EED)
-    params, x, y = make_inputs(ex, rng, network)
-    for node in ex.train_graph_json["nodes"]:
-        if node["op"] == "Input" and node["parameter"] not in params:
-            shape = env.parameter(node["parameter"]).shape()
-            params[node["parameter"]] = np.full(shape, 1.0 / 16.0, np.float32)
-    params[ex.x.id], params[ex.y.id] = x, y
-    run_graph(ex.train_graph_json, params, 1)  # warm-up (numpy allocations, BLAS threads)
-    t0 = time.perf_counter()
-    for s in range(steps):
-        params.update(run_graph(ex.train_graph_json, params, s))
-    dt = (time.perf_counter() - t0) / steps
-    env.close()
-    try:
-        import threadpoolctl
-        cores = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
-    except Exception:
-        cores = 1
-    return {"value": sample_batch / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": "%d training steps of %s at mini-batch %d through oracle/interp.py (numpy, f64-accumulated sums)" % (steps, network, sample_batch),
-            "ms_per_step": dt * 1e3}
+class CpuReference:
+    """The multi-threaded C++ port of the reference's op semantics (oracle/cpu_ref.cpp) on a bounded sample of the
+    workload: host-only graph build, then whole training steps of the exported graph (after the reference's graph
+    passes, so views are folded) on every host thread the box has."""
+
+    def __init__(self, network, sample_batch, optimizer):
+        import descent_b200 as d
+        from oracle import cpu_ref
+        self.network, self.sample_batch = network, sample_batch
+        self.env = d.Environment(-1)
+        ex = self.env.example(network, sample_batch, optimizer=optimizer)
+        rng = np.random.default_rng(0x5EED5EED)
+        self.params, x, y = make_inputs(ex, rng, network)
+        graph = ex.train_graph.export_json()
+        for node in graph["nodes"]:
+            if node["op"] == "Input" and node["parameter"] not in self.params:
+                shape = self.env.parameter(node["parameter"]).shape()
+                self.params[node["parameter"]] = np.full(shape, 1.0 / 16.0, np.float32)
+        self.params[ex.x.id], self.params[ex.y.id] = x, y
+        self.threads = cpu_ref.hardware_threads()
+        self.program = cpu_ref.Program(graph)
+        self.seed = 0
+
+    def step(self):
+        """One training step; returns its wall time in seconds (measured inside the library, around the graph run)."""
+        out, seconds = self.program.run(self.params, self.seed, self.threads)
+        self.params.update({pid: v.reshape(-1) for pid, v in out.items()})
+        self.seed += 1
+        return seconds
+
+    def describe(self, steps, ms_per_step):
+        return {"value": self.sample_batch / (ms_per_step * 1e-3), "unit": "samples/s", "cores": self.threads, "kind": "port",
+                "sample": "%d training steps of %s at mini-batch %d through oracle/cpu_ref.cpp (C++ port of the reference's op semantics, "
+                          "one 64-invocation work item per pool task, %d host threads)" % (steps, self.network, self.sample_batch, self.threads),
+                "ms_per_step": ms_per_step}
+
+    def close(self):
+        self.program.close()
+        self.env.close()
+
+
+CPU_SAMPLE_BATCH = {"conv-net": 1000, "conv-blur-net": 1000, "multi-hash": 16384, "siren": 16384, "relu": 16384, "relu-pe": 16384}
+
+
+def cpu_baseline(network, optimizer, budget_s=15.0):
+    """Bounded sample for the `cpu_baseline` object of the main arm: one warm-up step, then steps until ~budget_s."""
+    ref = CpuReference(network, CPU_SAMPLE_BATCH.get(network, 1000), optimizer)
+    ref.step()
+    times = []
+    while sum(times) < budget_s and len(times) < 20:
+        times.append(ref.step())
+    base = ref.describe(len(times), float(np.mean(times)) * 1e3)
+    ref.close()
+    return base
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    sample = {"conv-net": 256, "conv-blur-net": 256, "multi-hash": 4096}.get(args.workload, 1024)
-    times = []
-    base = None
-    for _ in range(max(1, args.warmup // 3) + args.steps):
-        base = cpu_baseline(args.workload, sample, args.optimizer, steps=1)
-        times.append(base["ms_per_step"])
-    times = times[-args.steps:]
-    ms = float(np.mean(times))
-    value = sample / (ms * 1e-3)
-    base["value"] = value
+    ref = CpuReference(args.workload, CPU_SAMPLE_BATCH.get(args.workload, 1000), args.optimizer)
+    for _ in range(args.warmup):
+        ref.step()
+    times = [ref.step() for _ in range(args.steps)]
+    ms = float(np.mean(times)) * 1e3
+    base = ref.describe(args.steps, ms)
+    ref.close()
     print(json.dumps({
-        "impl": "reference", "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": "train samples/s", "value": base["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": workload_name(args), "sample_mini_batch": sample,
-                                        "note": "CPU port of the reference semantics (oracle/); the reference's Vulkan path cannot be built here (SURVEY.md section 0)"},
-        "cpu_baseline": base, "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "data": "synthetic", "config": {"workload": workload_name(args), "sample_mini_batch": ref.sample_batch,
+                                        "note": "multi-threaded C++ port of the reference's op semantics (oracle/cpu_ref.cpp) on the host cores; the "
+                                                "reference's own Vulkan path cannot be built or run here (SURVEY.md section 0)"},
+        "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def workload_name(args):
@@ -293,8 +317,7 @@ def main():
 
     base = None
     if not args.no_cpu_baseline and world == 1:
-        sample = {"conv-net": 256, "conv-blur-net": 256, "multi-hash": 4096}.get(args.workload, 1024)
-        base = cpu_baseline(args.workload, sample, args.optimizer, steps=3)
+        base = cpu_baseline(args.workload, args.optimizer)
 
     out = {
         "metric": "train samples/s", "value": global_batch / (ms_per_step * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,

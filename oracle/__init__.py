@@ -4,7 +4,11 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 this package, and only as the checker or the reported CPU baseline -- never on the product path
 (descent_b200 does not import it and fails loudly without its CUDA library).
 
-What it is: a numpy restatement of the *semantics* of the reference (sjb3d/descent) for every op of
+Two parts.  `oracle.cpu_ref` (oracle/cpu_ref.cpp, built by `make -C oracle`) is a multi-threaded C++ port of the
+same op semantics, laid out the way the reference's kernels compute (one invocation per element, sequential-K
+reduce, float-atomic scatter); it is what bench.py times as `cpu_baseline` / `--impl reference`, and it is checked
+against the numpy interpreter and the reference's known answers in tests/test_oracle_kat.py.  The parity oracle
+proper: a numpy restatement of the *semantics* of the reference (sjb3d/descent) for every op of
 its graph IR -- `oracle.interp` interprets the raw op graph the frontend exports as JSON, one function
 per `Op` variant, each citing the reference file:line it follows.
 

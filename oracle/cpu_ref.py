@@ -1,0 +1,89 @@
+"""ctypes front end of oracle/cpu_ref.cpp: the multi-threaded CPU restatement used as the reported CPU baseline
+(TEST INFRASTRUCTURE -- see oracle/__init__.py; loaded only by tests/ and bench.py's cpu_baseline / --impl reference).
+
+    build()                      g++ -O2 -> oracle/_build/libcpu_ref.so (called from __graft_entry__.build())
+    run_graph(graph, params, seed, threads) -> ({parameter id: new value}, seconds)
+"""
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libcpu_ref.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(HERE, "cpu_ref.cpp")
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= os.path.getmtime(src):
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", src, "-o", LIB_PATH], check=True)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.cpu_ref_create.restype = ctypes.c_void_p
+        _lib.cpu_ref_create.argtypes = [ctypes.c_char_p]
+        _lib.cpu_ref_destroy.argtypes = [ctypes.c_void_p]
+        _lib.cpu_ref_set_input.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]
+        _lib.cpu_ref_set_output.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]
+        _lib.cpu_ref_run.restype = ctypes.c_double
+        _lib.cpu_ref_run.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int]
+        _lib.cpu_ref_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def hardware_threads():
+    return int(lib().cpu_ref_hardware_threads())
+
+
+class Program:
+    """One exported graph, parsed once; run() evaluates a step on `threads` host threads."""
+
+    def __init__(self, graph):
+        self._lib = lib()
+        self._h = self._lib.cpu_ref_create(json.dumps(graph).encode())
+        if not self._h:
+            raise RuntimeError(self._lib.cpu_ref_error().decode())
+        self.output_shapes = {n["parameter"]: n["shape"] for n in graph["nodes"] if n["op"] == "Output"}
+        self._keep = {}
+
+    def run(self, params, seed=0, threads=0):
+        threads = threads or hardware_threads()
+        for pid, v in params.items():
+            a = np.ascontiguousarray(v, dtype=np.float32).reshape(-1)
+            self._keep[("in", pid)] = a
+            self._lib.cpu_ref_set_input(self._h, int(pid), a.ctypes.data, a.size)
+        outputs = {}
+        for pid, shape in self.output_shapes.items():
+            a = np.empty(int(np.prod(shape)), np.float32)
+            outputs[pid] = a
+            self._lib.cpu_ref_set_output(self._h, int(pid), a.ctypes.data, a.size)
+        seconds = self._lib.cpu_ref_run(self._h, ctypes.c_uint32(int(seed) & 0xFFFFFFFF), int(threads))
+        if seconds < 0:
+            raise RuntimeError(self._lib.cpu_ref_error().decode())
+        return {pid: a.reshape(self.output_shapes[pid]) for pid, a in outputs.items()}, seconds
+
+    def close(self):
+        if self._h:
+            self._lib.cpu_ref_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def run_graph(graph, params, seed=0, threads=0):
+    prog = Program(graph)
+    try:
+        return prog.run(params, seed, threads)
+    finally:
+        prog.close()

@@ -128,3 +128,42 @@ def test_integer_vectors_are_bit_exact():
     z = np.load(os.path.join(GOLDEN_DIR, "integer_vectors.npz"))
     np.testing.assert_array_equal(interp.pcg(z["index"]), z["pcg"])
     np.testing.assert_array_equal(interp.rand_from_index(3, z["index"], 7).view(np.uint32), z["rand_uid3_seed7"])
+
+
+# ---- oracle/cpu_ref.cpp (the C++ port timed as the CPU baseline) against the numpy oracle ---------------------------
+
+@pytest.mark.parametrize("network,m,optimizer", [("conv-net", 4, "descent"), ("conv-blur-net", 2, "descent"), ("single-layer-dropout", 8, "descent"),
+                                                 ("multi-hash", 64, "adam")])
+@pytest.mark.parametrize("optimised", [False, True], ids=["raw-graph", "after-passes"])
+def test_cpu_ref_matches_numpy_oracle(host_env, network, m, optimizer, optimised):
+    """Every output of one training step, raw graph and the graph after the frontend's passes (what bench.py times).
+    1e-4 of each tensor's maximum: cpu_ref sums sequentially in f32 like the reference's kernels, the oracle in f64.
+    (SGD for the fashion_mnist nets: Adam's first step is ill-conditioned in near-zero gradient entries, see
+    test_gpu_networks.py.)"""
+    from helpers import init_example_params, synthetic_batch
+    from oracle import cpu_ref
+    ex = host_env.example(network, m, optimizer=optimizer)
+    rng = np.random.default_rng(11)
+    params = init_example_params(ex, rng)
+    params[ex.x.id], params[ex.y.id] = synthetic_batch(ex, rng)
+    for node in ex.train_graph_json["nodes"]:
+        if node["op"] == "Input" and node["parameter"] not in params:
+            shape = host_env.parameter(node["parameter"]).shape()
+            params[node["parameter"]] = np.full(shape, 1.0 / 16.0, np.float32)
+    want = run_graph(ex.train_graph_json, params, 3)
+    got, seconds = cpu_ref.run_graph(ex.train_graph.export_json() if optimised else ex.train_graph_json, params, 3, threads=4)
+    assert set(got) == set(want) and seconds >= 0
+    for pid, w in want.items():
+        scale = max(float(np.abs(w).max()), 1e-30)
+        assert float(np.abs(got[pid].astype(np.float64) - w).max()) <= 1e-4 * scale, (network, pid)
+
+
+@pytest.mark.parametrize("make_case", ALL_CASES, ids=lambda f: f.__name__)
+def test_cpu_ref_reference_known_answers(host_env, make_case):
+    """The reference's own device tests (src/lib.rs:26-231) through the C++ port, exact."""
+    from oracle import cpu_ref
+    case = make_case()
+    scope, ins, outs = instantiate(host_env, case)
+    got, _ = cpu_ref.run_graph(scope.export_json(), {p.id: data for p, (_, _, data) in zip(ins, case.inputs)}, TEST_RAND_SEED, threads=2)
+    for p, (_, _, expected) in zip(outs, case.outputs):
+        np.testing.assert_array_equal(got[p.id].reshape(-1), np.asarray(expected, np.float32).reshape(-1))
