@@ -4,6 +4,7 @@
 #include "environment.hpp"
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <climits>
 #include <cmath>
@@ -17,11 +18,50 @@ void check(int rc) {
     if (rc != DSC_OK) fail(std::string("device layer: ") + dsc_last_error());
 }
 
+namespace {
+// every occurrence of identifier prefix `from` (followed by a non-digit) -> `to`: kernel names are k<cluster>[_suffix]
+std::string rename_kernels(const std::string& text, const std::string& from, const std::string& to) {
+    std::string out;
+    size_t pos = 0;
+    for (;;) {
+        const size_t hit = text.find(from, pos);
+        if (hit == std::string::npos) break;
+        const size_t end = hit + from.size();
+        const bool boundary_before = hit == 0 || !(isalnum((unsigned char)text[hit - 1]) || text[hit - 1] == '_');
+        const bool boundary_after = end >= text.size() || !isdigit((unsigned char)text[end]);
+        out.append(text, pos, hit - pos);
+        out += (boundary_before && boundary_after) ? to : from;
+        pos = end;
+    }
+    out.append(text, pos, std::string::npos);
+    return out;
+}
+}  // namespace
+
+// One translation unit per graph.  Clusters whose generated code is identical up to the kernel name (the same GEMM
+// or per-element program at every timestep of an unrolled LSTM, the per-level kernels of a hash grid) are compiled
+// once: later clusters launch the first one's kernels with their own buffers.
 std::string generate_graph_source(const Graph& graph, const CodegenOptions& options, std::vector<ClusterCode>* per_cluster) {
     std::string src = kernel_prelude();
+    std::map<std::string, int> first_with_body;
     for (int ci = 0; ci < (int)graph.clusters().size(); ++ci) {
         ClusterCode code = generate_cluster_code(graph, ci, options);
-        src += code.source;
+        const std::string name = "k" + std::to_string(ci);
+        if (!code.source.empty()) {
+            std::string body = rename_kernels(code.source, name, "k@");
+            const std::string label = "// " + graph.clusters()[ci].label;  // labels carry shapes but also node-specific text: keep them out of the key
+            auto it = first_with_body.find(body);
+            if (it == first_with_body.end()) {
+                first_with_body.emplace(std::move(body), ci);
+                src += code.source;
+            } else {
+                const std::string original = "k" + std::to_string(it->second);
+                for (auto& l : code.launches)
+                    if (!l.entry.empty()) l.entry = rename_kernels(l.entry, name, original);
+                code.source.clear();
+            }
+            (void)label;
+        }
         if (per_cluster) per_cluster->push_back(std::move(code));
     }
     return src;

@@ -276,9 +276,60 @@ std::unique_ptr<Example> build_image_fit(Environment& env, const ExampleConfig& 
     return ex;
 }
 
+// examples/sentiment/main.rs:119-170: word indices -> one-hot -> embedding matmul -> LSTM over the sentence -> dense 3
+// -> softmax cross-entropy, Adam(0.002).  The data pipeline (DynaSent jsonl, vocabulary) is out of scope; the
+// vocabulary size and sentence length are configuration.
+namespace {
+class Sentiment : public Module {
+public:
+    Sentiment(Environment& env, int64_t vocab, int64_t words, int64_t embedding_size, int64_t lstm_size)
+        : vocab_(vocab), words_(words), embedding_size_(embedding_size), lstm_(env, embedding_size, lstm_size),
+          fc_(Dense::builder(lstm_size, 3).build(env)),
+          embedding_(env.trainable_parameter(Shape{vocab, embedding_size}, "em", Initializer::rand_uniform(1.0f))) {}
+    DualArray eval(DualArray input, const EvalContext& ctx) const override {
+        const int64_t m = input.shape()[0];
+        DualArray x = DualArray(input.value().one_hot(vocab_).with_empty_grad());
+        x = x.reshape(Shape{m * words_, vocab_}).matmul(embedding_).reshape(Shape{m, words_, embedding_size_});
+        return fc_.eval(lstm_.eval(x, ctx), ctx);
+    }
+
+private:
+    int64_t vocab_, words_, embedding_size_;
+    LSTMCell lstm_;
+    Dense fc_;
+    Parameter embedding_;
+};
+}  // namespace
+
+std::unique_ptr<Example> build_sentiment(Environment& env, const ExampleConfig& cfg) {
+    auto ex = std::make_unique<Example>();
+    ex->family = "sentiment";
+    const int64_t m = cfg.mini_batch_size, vocab = cfg.image_width > 0 ? cfg.image_width : 4096, words = cfg.image_height > 0 ? cfg.image_height : 32;
+    ex->module = std::make_unique<Sentiment>(env, vocab, words, 128, 64);
+    ex->x = env.static_parameter(Shape{m, words, 1}, "x");
+    ex->y = env.static_parameter(Shape{m, 1}, "y");
+    ex->learning_rate_scale = env.static_parameter(Shape{1}, "lr_scale");
+    ex->loss_sum = env.static_parameter(Shape{1}, "loss");
+    ex->accuracy_sum = env.static_parameter(Shape{1}, "accuracy");
+    auto scope = env.scope();
+    DualArray x = ex->module->train(scope->parameter(ex->x));
+    Array loss = softmax_cross_entropy_loss(x, ex->y).set_loss();
+    Array accuracy = softmax_cross_entropy_accuracy(x, ex->y);
+    scope->update_parameter_value(ex->loss_sum, [&](Array s) { return s + loss.reduce_sum(0, false); });
+    scope->update_parameter_value(ex->accuracy_sum, [&](Array s) { return s + accuracy.reduce_sum(0, false); });
+    Array lr_scale = scope->parameter_value(ex->learning_rate_scale);
+    ex->parameters = scope->trainable_parameters();
+    scope->all_reduce_gradients(ex->parameters);
+    ex->optimizer = make_optimizer(env, *scope, ex->parameters, cfg.optimizer, lr_scale, 0.002f, 0.999f);
+    ex->train_graph_json = scope->export_json();
+    ex->train_graph.reset(scope->build_graph());
+    return ex;
+}
+
 std::unique_ptr<Example> build_example(Environment& env, const ExampleConfig& config) {
     for (const char* n : {"relu", "relu-pe", "siren", "multi-hash"})
         if (config.network == n) return build_image_fit(env, config);
+    if (config.network == "sentiment") return build_sentiment(env, config);
     return build_fashion_mnist(env, config);
 }
 

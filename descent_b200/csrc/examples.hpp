@@ -10,6 +10,7 @@ namespace descent {
 struct ExampleConfig {
     std::string network;            // fashion_mnist: linear | single-layer | single-layer-dropout | conv-net | conv-blur-net
                                     // image_fit: relu | relu-pe | siren | multi-hash
+                                    // sentiment: sentiment (image_width = vocabulary size, image_height = words per sentence)
     int64_t mini_batch_size = 1000; // per rank
     std::string optimizer = "adam"; // adam | descent
     float weight_decay = 1.0e-8f;   // fashion_mnist default (main.rs:103-104); image_fit uses none
@@ -17,7 +18,7 @@ struct ExampleConfig {
 };
 
 struct Example {
-    std::string family;  // "fashion_mnist" | "image_fit"
+    std::string family;  // "fashion_mnist" | "image_fit" | "sentiment"
     std::unique_ptr<Module> module;
     std::vector<std::unique_ptr<Module>> owned;  // sub-modules kept alive
     Parameter x, y, learning_rate_scale, loss_sum, accuracy_sum, image;
@@ -30,6 +31,7 @@ struct Example {
 
 std::unique_ptr<Example> build_fashion_mnist(Environment& env, const ExampleConfig& config);
 std::unique_ptr<Example> build_image_fit(Environment& env, const ExampleConfig& config);
+std::unique_ptr<Example> build_sentiment(Environment& env, const ExampleConfig& config);
 std::unique_ptr<Example> build_example(Environment& env, const ExampleConfig& config);
 
 }  // namespace descent

@@ -20,6 +20,8 @@ def init_example_params(ex, rng, siren=False):
                 v = rng.uniform(-scale, scale, shape)
             else:
                 v = rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)  # Initializer::for_relu (parameter.rs:17-20)
+        elif name == "em":  # Initializer::RandUniform(1.0) (examples/sentiment/main.rs:131-135)
+            v = rng.uniform(-1.0, 1.0, shape)
         elif name == "f":
             v = rng.standard_normal(shape) * np.sqrt(2.0 / (shape[2] * shape[3] * shape[4]))
         else:  # biases
@@ -36,6 +38,9 @@ def init_example_params(ex, rng, siren=False):
 
 def synthetic_batch(ex, rng):
     xs, ys = ex.x.shape(), ex.y.shape()
+    if len(xs) == 3:  # sentiment: word indices as f32, 0 = padding; labels 0..2 (examples/sentiment/main.rs:176-190)
+        vocab = [p for p in ex.parameters if p.name() == "em"][0].shape()[0]
+        return rng.integers(0, vocab, xs).astype(np.float32), rng.integers(0, 3, ys).astype(np.float32)
     if len(xs) == 4:  # fashion_mnist: x in [0,1), integer labels as f32 (main.rs:56,69)
         return rng.random(xs, dtype=np.float32), rng.integers(0, 10, ys).astype(np.float32)
     w = 512

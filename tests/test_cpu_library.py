@@ -61,6 +61,28 @@ def test_generated_kernels_compile_for_sm100a(built_library, host_env, network, 
     assert built_library.nvrtc_compile(source) > 0
 
 
+@pytest.mark.parametrize("network,m,kwargs", [("conv-net", 8192, {}), ("conv-blur-net", 256, {}), ("multi-hash", 262144, {}), ("single-layer", 1024, {}),
+                                              ("sentiment", 64, {"image_width": 512, "image_height": 8})])
+def test_tensor_core_kernels_compile_for_sm100a(built_library, host_env, network, m, kwargs):
+    """The TF32 variant of the step: halo-tiled conv kernels, gathered tcgen05 GEMMs, epilogues, column sums (all JIT
+    templates with inline tcgen05 / TMEM PTX) must at least compile without a GPU."""
+    ex = host_env.example(network, m, **kwargs)
+    source = ex.train_graph.kernel_source(tf32=True)
+    assert built_library.nvrtc_compile(source) > 0
+
+
+def test_sentiment_example_structure(built_library, host_env):
+    """examples/sentiment/main.rs:119-170: embedding [vocab, 128], LSTM 128 -> 64 (4 gates x (wi, wh, b)), dense 64 -> 3."""
+    vocab, words = 500, 32
+    ex = host_env.example("sentiment", 16, image_width=vocab, image_height=words)
+    shapes = {p.name(): p.shape() for p in ex.parameters}
+    assert shapes["em"] == (vocab, 128) and shapes["w"] == (64, 3) and shapes["forget_wh"] == (64, 64) and shapes["cell_wi"] == (128, 64)
+    assert sum(p.element_count() for p in ex.parameters) == vocab * 128 + 4 * (128 * 64 + 64 * 64 + 64) + 64 * 3 + 3
+    assert ex.x.shape() == (16, words, 1)
+    small = host_env.example("sentiment", 16, image_width=64, image_height=4)  # strict-FP32 kernels of a 4-word unroll
+    assert built_library.nvrtc_compile(small.train_graph.kernel_source()) > 0
+
+
 def test_parameter_counts_match_reference_readme(host_env):
     """examples/image_fit/README.md:31-34 and the conv-net size quoted in SURVEY.md section 5."""
     expected = {"relu": 44099, "relu-pe": 51779, "siren": 44099, "multi-hash": 43977, "conv-net": 204618, "linear": 7850}

@@ -30,6 +30,7 @@ CASES = [
     ("relu-pe", 256, 1e-5),
     ("siren", 256, 1e-5),
     ("multi-hash", 512, 1e-5),
+    ("sentiment", 16, 1e-5),  # vocabulary 200, 8 words: examples/sentiment/main.rs at a size the oracle finishes quickly
 ]
 
 
@@ -38,7 +39,7 @@ CASES = [
 def test_one_training_step_matches_oracle(env, network, m, tol, optimizer):
     if optimizer == "descent" and network in ("relu", "relu-pe", "siren", "multi-hash"):
         pytest.skip("image_fit always trains with Adam (examples/image_fit/main.rs:319)")
-    ex = env.example(network, m, optimizer=optimizer)
+    ex = env.example(network, m, optimizer=optimizer, **({"image_width": 200, "image_height": 8} if network == "sentiment" else {}))
     rng = np.random.default_rng(SEED_BASE + len(network))
     params = init_example_params(ex, rng, siren=(network == "siren"))
     params[ex.x.id], params[ex.y.id] = synthetic_batch(ex, rng)
