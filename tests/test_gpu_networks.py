@@ -62,7 +62,9 @@ def check_adam_update(env, ex, params, want):
     """optimizer.rs:83-97 on the backend's own state; state order is [t, m0, v0, m1, v1, ...] (optimizer.rs:79-95)."""
     f32 = np.float32
     beta1, beta2, eps = f32(0.9), f32(0.99 if ex.accuracy_sum is None else 0.999), f32(1e-8)
-    lr = f32(0.02 if ex.accuracy_sum is None else 0.005) * f32(params[ex.learning_rate_scale.id][0])
+    # image_fit 0.02 (main.rs:319), sentiment 0.002 (sentiment/main.rs:166), fashion_mnist 0.005 (main.rs:275)
+    base_lr = 0.02 if ex.accuracy_sum is None else 0.002 if any(p.name() == "em" for p in ex.parameters) else 0.005
+    lr = f32(base_lr) * f32(params[ex.learning_rate_scale.id][0])
     t = f32(env.read_parameter_scalar(ex.optimizer_state[0]))
     alpha = lr * np.sqrt(f32(1) - np.exp(np.log(beta2) * t, dtype=f32), dtype=f32) / (f32(1) - np.exp(np.log(beta1) * t, dtype=f32))
     for i, p in enumerate(ex.parameters):
