@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 DEFAULT_BATCH = {"conv-net": 8192, "conv-blur-net": 8192, "linear": 8192, "single-layer": 8192, "single-layer-dropout": 8192,
-                 "multi-hash": 262144, "siren": 65536, "relu": 65536, "relu-pe": 65536}
+                 "multi-hash": 262144, "siren": 65536, "relu": 65536, "relu-pe": 65536, "sentiment": 256}
 
 
 def peaks():
@@ -132,7 +132,7 @@ class CpuReference:
         self.env.close()
 
 
-CPU_SAMPLE_BATCH = {"conv-net": 1000, "conv-blur-net": 1000, "multi-hash": 16384, "siren": 16384, "relu": 16384, "relu-pe": 16384}
+CPU_SAMPLE_BATCH = {"sentiment": 256, "conv-net": 1000, "conv-blur-net": 1000, "multi-hash": 16384, "siren": 16384, "relu": 16384, "relu-pe": 16384}
 
 
 def cpu_baseline(network, optimizer, budget_s=15.0):
@@ -167,6 +167,8 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_name(args):
+    if args.workload == "sentiment":
+        return "sentiment (vocabulary 4096, 32 words, embedding 128, LSTM 64)"
     return "fashion_mnist %s" % args.workload if args.workload in ("linear", "single-layer", "single-layer-dropout", "conv-net", "conv-blur-net") \
         else "image_fit %s" % args.workload
 
