@@ -154,3 +154,20 @@ def test_split_k_reduce_is_absorbed(host_env):
         ops = sorted(by_cluster[n["cluster"]])
         # the split-K Reduce always; further Reduce nodes are the bias-gradient chain that shares the GEMM's B operand
         assert ops[:2] == ["MatMul", "Reduce"] and set(ops[2:]) <= {"Reduce"}, ops
+
+
+def test_conv_net_fusions_are_in_place(host_env):
+    """The cluster-level rewrites DESIGN.md section 1 lists, on conv-net's training step: conv backward-input absorbs
+    col2im and both Unpads, bias + activation run in the conv GEMMs' epilogues, the bias-gradient Reduce chains ride on
+    the weight-gradient GEMMs, pool backward and activation backward are one per-element kernel, and the
+    pre-activations are never stored (no cluster writes a tensor that only a `x > 0` test reads)."""
+    m = 4096  # the column sums join a GEMM only when its reduction is long enough to be worth streaming once (K >= 4096)
+    ex = host_env.example("conv-net", m)
+    labels = [c["label"] for c in ex.train_graph.export_json()["clusters"]]
+    assert sum("MatMul+WindowsToImage" in l and l.endswith("+Unpad+Unpad") for l in labels) == 1, labels
+    assert sum(l.startswith("MatMul") and " + PerElement" in l for l in labels) >= 3, labels          # conv1, conv2, dense layers
+    assert sum("+ColumnSum" in l for l in labels) == 4, labels                                          # two convs, two dense layers
+    assert not any(l.startswith("WindowsToImage") or l.startswith("Unpad") for l in labels), labels
+    big = [l for l in labels if l.startswith("PerElement") and "[%d]" % (m * 28 * 28 * 16) in l]
+    assert len(big) == 1, big  # forward bias+leaky lives in the conv epilogue; backward pool+leaky is the one kernel left
+    assert len(labels) <= 45, len(labels)
