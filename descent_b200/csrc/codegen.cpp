@@ -312,18 +312,12 @@ void emit_per_element_ops(std::ostringstream& os, const Cluster& c, const Codege
     }
 }
 
-ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, const std::string& name_suffix = "") {
+// Body of a per-element kernel for the block `block` (an expression): loads, the straight-line program, stores.
+// Uses the names in<i> / out<i> of the cluster's own inputs and outputs.
+void emit_per_element_body(std::ostringstream& os, const Cluster& c, const CodegenOptions& opt, const std::string& block) {
     const int64_t n = c.element_count;
     const int vec = (n % 4 == 0) ? 4 : 1;
-    std::ostringstream os;
-    const std::string name = "k" + num(ci) + name_suffix;
-    os << "// " << c.label << "\n";
-    os << "extern \"C\" __global__ void __launch_bounds__(256) " << name << "(";
-    for (size_t i = 0; i < c.inputs.size(); ++i) os << "const float* in" << i << ", ";
-    for (size_t i = 0; i < c.outputs.size(); ++i) os << "float* out" << i << ", ";
-    os << "const unsigned* dsc_step) {\n";
-    os << "    const unsigned dsc_seed = dsc_step[0]; (void)dsc_seed;\n";
-    os << "    const unsigned base = (blockIdx.x * 256u + threadIdx.x) * " << vec << "u;\n";
+    os << "    const unsigned base = (" << block << " * 256u + threadIdx.x) * " << vec << "u;\n";
     os << "    if (base >= " << unum(n) << ") return;\n";
     std::vector<bool> vector_load(c.inputs.size(), false);
     std::vector<bool> is_loaded(c.inputs.size(), false);
@@ -354,23 +348,56 @@ ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const Code
         for (size_t i = 0; i < c.outputs.size(); ++i)
             os << "    *reinterpret_cast<float4*>(out" << i << " + base) = make_float4(vout" << i << "[0], vout" << i << "[1], vout" << i
                << "[2], vout" << i << "[3]);\n";
+}
+
+int64_t per_element_blocks(const Cluster& c) { return div_round_up(div_round_up(c.element_count, c.element_count % 4 == 0 ? 4 : 1), 256); }
+
+ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, const std::string& name_suffix = "") {
+    std::ostringstream os;
+    const std::string name = "k" + num(ci) + name_suffix;
+    os << "// " << c.label << "\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(256) " << name << "(";
+    const bool grouped = !c.group.empty();
+    for (size_t i = 0; i < c.inputs.size(); ++i) os << "const float* " << (grouped ? "gin" : "in") << i << ", ";
+    for (size_t i = 0; i < c.outputs.size(); ++i) os << "float* " << (grouped ? "gout" : "out") << i << ", ";
+    os << "const unsigned* dsc_step) {\n";
+    os << "    const unsigned dsc_seed = dsc_step[0]; (void)dsc_seed;\n";
+    int64_t blocks = 0;
+    if (!grouped) {
+        emit_per_element_body(os, c, opt, "blockIdx.x");
+        blocks = per_element_blocks(c);
+    } else {
+        // block ranges select the program; each program sees its own buffers under the usual names
+        size_t in_base = 0, out_base = 0;
+        for (const Cluster& sub : c.group) {
+            const int64_t b = per_element_blocks(sub);
+            os << "    if (blockIdx.x < " << unum(blocks + b) << ") {  // " << sub.label << "\n";
+            for (size_t i = 0; i < sub.inputs.size(); ++i) os << "    const float* in" << i << " = gin" << in_base + i << ";\n";
+            for (size_t i = 0; i < sub.outputs.size(); ++i) os << "    float* out" << i << " = gout" << out_base + i << ";\n";
+            emit_per_element_body(os, sub, opt, "(blockIdx.x - " + unum(blocks) + ")");
+            os << "    return;\n    }\n";
+            blocks += b;
+            in_base += sub.inputs.size();
+            out_base += sub.outputs.size();
+        }
+    }
     os << "}\n\n";
 
     ClusterCode code;
     code.source = os.str();
     KernelLaunch l;
     l.entry = name;
-    l.grid_x = (uint32_t)div_round_up(div_round_up(n, vec), 256);
+    l.grid_x = (uint32_t)blocks;
     l.label = c.label;
     l.cluster = ci;
-    for (const auto& in : c.inputs) {
-        l.args.push_back({KernelArg::NodeBuffer, in.node_id, 0});
-        l.algorithmic_bytes += chain_bytes(g, in);
-    }
-    for (int out : c.outputs) {
-        l.args.push_back({KernelArg::NodeBuffer, out, 0});
-        l.algorithmic_bytes += 4.0 * (double)n;
-    }
+    auto account = [&](const Cluster& sub) {
+        for (const auto& in : sub.inputs) l.algorithmic_bytes += chain_bytes(g, in);
+        l.algorithmic_bytes += 4.0 * (double)sub.element_count * (double)sub.outputs.size();
+    };
+    if (grouped) for (const Cluster& sub : c.group) account(sub);
+    else account(c);
+    for (const auto& in : c.inputs) l.args.push_back({KernelArg::NodeBuffer, in.node_id, 0});
+    for (int out : c.outputs) l.args.push_back({KernelArg::NodeBuffer, out, 0});
     code.launches.push_back(l);
     return code;
 }

@@ -643,6 +643,80 @@ void Graph::absorb_column_sums(std::vector<Cluster>& clusters) {
     }
 }
 
+// Launch-bound tails (a few thousand elements per kernel, microseconds each) are merged per dependency level: the
+// programs are independent by construction of the levels.  A program that reads a parameter is never grouped with
+// one that writes the same parameter: the planner lets a kernel update a parameter in place when it reads the old
+// value at the same element, which only holds inside one program.
+void Graph::group_small_per_element(std::vector<Cluster>& clusters) {
+    constexpr int64_t kSmall = 1 << 18;  // elements
+    constexpr size_t kMaxBuffers = 40;
+    auto cons = ops_.consumers();
+    auto params_read = [&](const Cluster& c) {
+        std::set<int> ids;
+        for (const auto& in : c.inputs)
+            if (ops_.nodes[in.node_id].op.kind == OpKind::Input) ids.insert(ops_.nodes[in.node_id].op.parameter_id);
+        return ids;
+    };
+    auto params_written = [&](const Cluster& c) {
+        std::set<int> ids;
+        for (int out : c.outputs)
+            for (auto [dst, k] : cons[out])
+                if (ops_.nodes[dst].op.kind == OpKind::Output) ids.insert(ops_.nodes[dst].op.parameter_id);
+        return ids;
+    };
+    std::map<int, std::vector<size_t>> by_level;
+    for (size_t i = 0; i < clusters.size(); ++i) {
+        const Cluster& c = clusters[i];
+        if (c.kind == ClusterKind::PerElement && !c.members.empty() && c.group.empty() && c.element_count <= kSmall) by_level[c.level].push_back(i);
+    }
+    for (auto& [level, ids] : by_level) {
+        std::vector<size_t> open;  // indices of group heads at this level
+        for (size_t i : ids) {
+            const auto reads = params_read(clusters[i]), writes = params_written(clusters[i]);
+            bool placed = false;
+            for (size_t head : open) {
+                Cluster& h = clusters[head];
+                if (h.inputs.size() + h.outputs.size() + clusters[i].inputs.size() + clusters[i].outputs.size() > kMaxBuffers) continue;
+                bool conflict = false;
+                for (const Cluster& sub : h.group) {
+                    const auto r2 = params_read(sub), w2 = params_written(sub);
+                    for (int p : reads) conflict |= w2.count(p) > 0;
+                    for (int p : writes) conflict |= r2.count(p) > 0 || w2.count(p) > 0;
+                }
+                if (conflict) continue;
+                Cluster sub = clusters[i];
+                h.group.push_back(sub);
+                h.inputs.insert(h.inputs.end(), sub.inputs.begin(), sub.inputs.end());
+                h.outputs.insert(h.outputs.end(), sub.outputs.begin(), sub.outputs.end());
+                for (int id : sub.members) {
+                    h.members.push_back(id);
+                    ops_.nodes[id].cluster_id = (int)head;
+                }
+                h.element_count += sub.element_count;
+                clusters[i].members.clear();
+                clusters[i].outputs.clear();
+                placed = true;
+                break;
+            }
+            if (!placed) {
+                Cluster& h = clusters[i];
+                Cluster self = h;
+                h.group.push_back(self);  // a group of one until someone joins
+                open.push_back(i);
+            }
+        }
+        for (size_t head : open) {
+            Cluster& h = clusters[head];
+            if (h.group.size() == 1) { h.group.clear(); continue; }  // stays an ordinary per-element cluster
+            std::ostringstream label;
+            label << "PerElementGroup (" << h.group.size() << " programs) [" << h.element_count << "]";
+            h.label = label.str();
+            h.ops.clear();
+            h.output_ops.clear();
+        }
+    }
+}
+
 // The Unpad(s) that undo conv2d's replicate padding run in the epilogue of the fused backward-input kernel: the
 // padded image gradient is never written either.
 bool Graph::absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id) {
@@ -946,6 +1020,7 @@ void Graph::build_clusters() {
         if (c.kind == ClusterKind::PerElement) build_per_element_program(c);
     absorb_per_element_epilogues(clusters);
     absorb_column_sums(clusters);
+    group_small_per_element(clusters);
 
     // levels are a topological order of clusters: fusable edges stay inside a cluster, all others climb
     std::vector<int> idx(clusters.size());

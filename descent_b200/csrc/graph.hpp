@@ -79,6 +79,10 @@ struct Cluster {
     // kernels that stream B produce those column sums on the side; `column_sum[i]` are the absorbed Reduce clusters in
     // order (other GEMM kernels simply run them after the product) and outputs[1] is the last Reduce's node.
     std::vector<Cluster> column_sum;
+    // PerElement: several small per-element programs of one dependency level (different element counts: the Adam
+    // updates of all parameter tensors, the per-level bookkeeping of a hash grid) launched as ONE kernel; block ranges
+    // select the program.  inputs / outputs are the concatenation of the sub-clusters' in order.
+    std::vector<Cluster> group;
     std::string label;                 // as the reference's Kernel::label_name (kernel.rs)
 };
 
@@ -110,6 +114,7 @@ private:
     void sink_permutations_into_per_element();
     void absorb_per_element_epilogues(std::vector<Cluster>& clusters);
     void absorb_column_sums(std::vector<Cluster>& clusters);
+    void group_small_per_element(std::vector<Cluster>& clusters);
     bool absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     bool absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     void build_clusters();
