@@ -134,3 +134,24 @@ def test_siren_positional_encoding_mse(host_env):
     for i, p in enumerate(ex.parameters):
         m_state = out[ex.optimizer_state[1 + 2 * i].id].astype(np.float64) / np.float64(np.float32(1.0) - np.float32(0.9))
         np.testing.assert_allclose(m_state, ws[i].grad.numpy(), rtol=2e-3, atol=1e-6 * max(1.0, float(ws[i].grad.abs().max())))
+
+
+@pytest.mark.parametrize("network,m,kwargs", [("linear", 16, {}), ("single-layer-dropout", 16, {}), ("conv-net", 6, {}), ("conv-blur-net", 3, {}), ("relu-pe", 32, {}),
+                                              ("siren", 32, {}), ("multi-hash", 48, {}), ("sentiment", 4, {"image_width": 40, "image_height": 5})])
+def test_graph_passes_preserve_every_output_bit_for_bit(host_env, network, m, kwargs):
+    """The graph the backend compiles (after dead-code / move elimination, x*1 and x+0 simplification, CSE, all-reduce
+    view hoisting, permutation sinking and activation-sign reuse, descent_b200/csrc/graph.cpp) must compute exactly
+    what the raw graph computes: the oracle interprets both and every output has to be identical, bit for bit."""
+    from helpers import init_example_params, synthetic_batch
+    ex = host_env.example(network, m, **kwargs)
+    rng = np.random.default_rng(len(network) + m)
+    params = init_example_params(ex, rng, siren=(network == "siren"))
+    params[ex.x.id], params[ex.y.id] = synthetic_batch(ex, rng)
+    for node in ex.train_graph_json["nodes"]:
+        if node["op"] == "Input" and node["parameter"] not in params:
+            params[node["parameter"]] = np.full(host_env.parameter(node["parameter"]).shape(), 1.0 / 16.0, np.float32)
+    raw = run_graph(ex.train_graph_json, params, 9)
+    optimised = run_graph(ex.train_graph.export_json(), params, 9)
+    assert set(raw) == set(optimised)
+    for pid, want in raw.items():
+        np.testing.assert_array_equal(optimised[pid].view(np.uint32), want.view(np.uint32), err_msg="%s parameter %d" % (network, pid))
