@@ -171,3 +171,21 @@ def test_conv_net_fusions_are_in_place(host_env):
     big = [l for l in labels if l.startswith("PerElement") and "[%d]" % (m * 28 * 28 * 16) in l]
     assert len(big) == 1, big  # forward bias+leaky lives in the conv epilogue; backward pool+leaky is the one kernel left
     assert len(labels) <= 45, len(labels)
+
+
+def test_invalid_shapes_are_errors_not_crashes(host_env):
+    """The reference asserts / panics on these (shape.rs:44-48: every extent > 0 and at most 7 axes; reshape and broadcast
+    mismatches, shape.rs:421-455,578-602); across the C ABI they surface as error codes (DescentError here)."""
+    d = __import__("descent_b200")
+    for shape in ([0, 3], [4, -1], [2] * 8):
+        with pytest.raises(d.DescentError):
+            host_env.static_parameter(shape, "bad")
+    a = host_env.static_parameter([4, 3], "a")
+    b = host_env.static_parameter([5, 2], "b")
+    scope = host_env.scope()
+    with pytest.raises(d.DescentError):
+        scope.parameter_value(a).reshape([5, 3])
+    with pytest.raises(d.DescentError):
+        scope.parameter_value(a) + scope.parameter_value(b)
+    with pytest.raises(d.DescentError):
+        host_env.run(scope.build_graph(), 0)  # a host-only environment has no execution path at all
