@@ -225,6 +225,10 @@ class Environment:
         """Tensor-core (tcgen05, TF32 operands, FP32 accumulate) path for plain dense MatMuls; default off = strict FP32."""
         _check(lib.dsc_env_set_tf32(self._h, int(on)))
 
+    def set_sm_count(self, sm_count):
+        """Plan as if the device had `sm_count` SMs (0 = real): persistent kernels walk many tiles per CTA (tests)."""
+        _check(lib.dsc_env_set_sm_count(self._h, int(sm_count)))
+
     def print_timings(self, label):
         _check(lib.dsc_env_print_timings(self._h, label.encode()))
 

@@ -33,7 +33,7 @@ def _headers_mtime():
     m = 0.0
     for d in (CSRC, os.path.join(ROOT, "..", "include")):
         for name in os.listdir(d):
-            if name.endswith((".hpp", ".h", ".cuh")):
+            if name.endswith((".hpp", ".h", ".cuh", ".inc")):  # kernel templates are #included by codegen.cpp
                 m = max(m, os.path.getmtime(os.path.join(d, name)))
     return m
 

@@ -156,6 +156,12 @@ int dsc_env_set_tf32(dsc_env* env, int on) {
     env->env->set_tf32(on != 0);
     return DSC_OK;
 }
+int dsc_env_set_sm_count(dsc_env* env, int sm_count) {
+    return guarded([&] {
+        DSC_CHECK(sm_count >= 0 && sm_count <= 4096, "sm_count override out of range: " << sm_count);
+        env->env->set_sm_count_override(sm_count);
+    });
+}
 int dsc_env_print_timings(dsc_env* env, const char* label) { return guarded([&] { env->env->print_timings(label); }); }
 int dsc_env_init_data_parallel(dsc_env* env, int world, int rank, const void* id) {
     return guarded([&] { env->env->init_data_parallel(world, rank, id); });

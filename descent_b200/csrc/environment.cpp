@@ -45,6 +45,25 @@ std::string generate_graph_source(const Graph& graph, const CodegenOptions& opti
     std::string src = kernel_prelude();
     std::map<std::string, int> first_with_body;
     for (int ci = 0; ci < (int)graph.clusters().size(); ++ci) {
+        {
+            // generated kernels index with 32-bit integers: refuse anything they could not address instead of wrapping
+            const Cluster& c = graph.clusters()[ci];
+            constexpr int64_t kLimit = (int64_t)1 << 31;
+            auto check_cluster = [&](const Cluster& k) {
+                for (const auto& in : k.inputs)
+                    DSC_CHECK(in.chain.input_count < kLimit && in.chain.output_count < kLimit && in.arg_shape.element_count() < kLimit,
+                              "cluster '" << k.label << "' addresses " << std::max(in.chain.input_count, in.chain.output_count)
+                                          << " elements through one operand; kernels index with 32 bits (limit 2^31): use a smaller per-GPU mini-batch");
+                for (int out : k.outputs)
+                    DSC_CHECK(graph.ops().nodes[out].shape.element_count() < kLimit,
+                              "cluster '" << k.label << "' writes " << graph.ops().nodes[out].shape.element_count()
+                                          << " elements; kernels index with 32 bits (limit 2^31): use a smaller per-GPU mini-batch");
+            };
+            check_cluster(c);
+            for (const Cluster& sub : c.group) check_cluster(sub);
+            for (const Cluster& sub : c.epilogue) check_cluster(sub);
+            for (const Cluster& sub : c.column_sum) check_cluster(sub);
+        }
         ClusterCode code = generate_cluster_code(graph, ci, options);
         const std::string name = "k" + std::to_string(ci);
         if (!code.source.empty()) {
@@ -145,6 +164,7 @@ struct Environment::GraphExec {
     GraphStats stats;
     std::string source;
     std::vector<uint64_t> parameter_buffers_at_plan;  // the plan bakes device addresses in
+    CodegenOptions options;  // what the plan was generated for: a change (set_tf32, set_sm_count_override) re-plans
     void release() {  // the environment is going away (or the graph is): give everything back while the context lives
         if (cuda_graph) dsc_graph_destroy(cuda_graph);
         if (module) dsc_module_destroy(module);
@@ -284,7 +304,14 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
     require_device("running a graph");
     if (graph.executor_state) {
         auto* exec = static_cast<GraphExec*>(graph.executor_state.get());
-        if (exec->ctx == ctx_) return *exec;
+        const CodegenOptions now = codegen_options();
+        if (exec->ctx == ctx_ && exec->options.use_tf32 == now.use_tf32 && exec->options.sm_count == now.sm_count) return *exec;
+        if (exec->ctx == ctx_) {  // options changed since this graph was planned: drop the old plan
+            check(dsc_sync(ctx_));
+            live_execs_.erase(std::remove_if(live_execs_.begin(), live_execs_.end(), [&](const std::shared_ptr<void>& e) { return e.get() == exec; }),
+                              live_execs_.end());
+            graph.executor_state.reset();
+        }
     }
     DSC_CHECK(graph.parameters() == parameters_, "graph was built for another environment");
     DSC_CHECK(graph.dp().world == dp_.world && graph.dp().rank == dp_.rank, "graph was built before data parallel was initialised");
@@ -297,10 +324,8 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
     const int nc = (int)clusters.size();
     auto cons = ops.consumers();
 
-    CodegenOptions opt;
-    opt.sm_count = sm_count_;
-    opt.dp_rank = dp_.rank;
-    opt.use_tf32 = use_tf32_;
+    const CodegenOptions opt = codegen_options();
+    exec.options = opt;
     std::vector<ClusterCode> codes;
     exec.source = generate_graph_source(graph, opt, &codes);
 
@@ -572,12 +597,13 @@ std::vector<KernelTiming> Environment::profile(const Graph& graph, uint32_t rand
 }
 
 GraphStats Environment::stats(const Graph& graph) { return prepare(graph).stats; }
-std::string Environment::kernel_source(const Graph& graph) {
+std::string Environment::kernel_source(const Graph& graph) { return generate_graph_source(graph, codegen_options(), nullptr); }
+CodegenOptions Environment::codegen_options() const {
     CodegenOptions opt;
-    opt.sm_count = sm_count_;
+    opt.sm_count = sm_count_override_ > 0 ? sm_count_override_ : sm_count_;
     opt.dp_rank = dp_.rank;
     opt.use_tf32 = use_tf32_;
-    return generate_graph_source(graph, opt, nullptr);
+    return opt;
 }
 
 // average total + the five most expensive kernels by label (timestamp.rs:155-179)

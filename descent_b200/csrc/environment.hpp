@@ -91,6 +91,10 @@ public:
     // false (default): every GEMM is strict FP32 (SIMT).  true: plain dense MatMuls of graphs prepared afterwards run
     // on the tensor cores with TF32 operands and FP32 accumulation (BASELINE.json north_star (b)).
     void set_tf32(bool on) { use_tf32_ = on; }
+    // Plan graphs as if the device had `n` SMs (0 = the real count).  Persistent kernels size their grids from it, so a
+    // small value makes every CTA walk many tiles on a small problem: the regime of the large-batch benchmark, at sizes
+    // the oracle finishes in seconds (tests).  A graph planned under other options is planned again at its next run.
+    void set_sm_count_override(int n) { sm_count_override_ = n; }
     void init_data_parallel(int world, int rank, const void* nccl_unique_id128);
     void set_data_parallel_for_tracing(int world, int rank) {  // host-only environments: rank-specific graphs without NCCL
         DSC_CHECK(ctx_ == nullptr, "use init_data_parallel on a device environment");
@@ -123,6 +127,8 @@ private:
     bool use_cuda_graph_ = true;
     bool profile_runs_ = false;
     bool use_tf32_ = false;
+    int sm_count_override_ = 0;
+    CodegenOptions codegen_options() const;
     std::vector<std::pair<std::string, double>> timing_totals_;  // label -> accumulated ms
     int timing_runs_ = 0;
     std::vector<std::shared_ptr<void>> live_execs_;

@@ -55,8 +55,12 @@ int dsc_graphdef_destroy(dsc_graphdef* graph);
 int dsc_env_run(dsc_env* env, dsc_graphdef* graph, uint32_t rand_seed);                                      /* run :326 */
 int dsc_env_sync(dsc_env* env);
 int dsc_env_set_options(dsc_env* env, int use_cuda_graph, int profile_runs);
-/* 0 (default): all GEMMs strict FP32.  1: plain dense MatMuls of graphs first run afterwards use the tcgen05 TF32 kernel. */
+/* 0 (default): all GEMMs strict FP32.  1: MatMuls / convolutions run on tcgen05 with TF32 operands.  A graph that was
+ * planned under the other setting is planned again at its next run. */
 int dsc_env_set_tf32(dsc_env* env, int on);
+/* Plan graphs as if the device had `sm_count` SMs (0 = the real count): persistent kernels then walk many tiles per CTA
+ * on small problems, which is how the parity tests reach the regime of the large-batch benchmark. */
+int dsc_env_set_sm_count(dsc_env* env, int sm_count);
 int dsc_env_print_timings(dsc_env* env, const char* label);                                                  /* print_timings :518 */
 int dsc_env_init_data_parallel(dsc_env* env, int world, int rank, const void* nccl_unique_id128);            /* new: SURVEY.md 8e */
 /* JSON: [{"label","entry","cluster","ms","bytes","flops"}...] per launch of one run, averaged over `iterations` eager runs */

@@ -274,6 +274,12 @@ struct Program {
     std::map<int, const float*> inputs;
     std::map<int, float*> outputs;
     std::map<int, int64_t> input_counts, output_counts;
+    // checker mode (tests only; the timed baseline leaves both off): sums of Reduce / MatMul are accumulated in float64
+    // and rounded once, exactly like oracle/interp.py (_reduce, _matmul), so large-batch steps can be checked at the
+    // same tolerances as the numpy interpreter; MatMul nodes listed in tf32_nodes see their operands truncated to TF32
+    // (10 explicit mantissa bits, interp.tf32_operand "trunc": what tcgen05 kind::tf32 does to FP32 operands).
+    bool f64_accumulate = false;
+    std::vector<int> tf32_nodes;
 };
 
 thread_local std::string g_error;
@@ -515,6 +521,12 @@ struct Runner {
                 for (int64_t i = b; i < e; ++i) {
                     const int64_t oo = i / inner, oi = i % inner;
                     const float* p = a.data() + oo * K * inner + oi;
+                    if (prog.f64_accumulate && !is_max) {
+                        double acc = 0.0;
+                        for (int64_t k = 0; k < K; ++k) acc += (double)p[k * inner];
+                        o[i] = (float)acc;
+                        continue;
+                    }
                     float acc = is_max ? -INFINITY : 0.f;
                     for (int64_t k = 0; k < K; ++k) acc = is_max ? std::max(acc, p[k * inner]) : acc + p[k * inner];
                     o[i] = acc;
@@ -529,6 +541,29 @@ struct Runner {
             const bool rows = n.mode == "Rows";
             out.assign((size_t)n.count, 0.f);
             float* o = out.data();
+            const bool tf32 = std::find(prog.tf32_nodes.begin(), prog.tf32_nodes.end(), n.id) != prog.tf32_nodes.end();
+            if (prog.f64_accumulate || tf32) {
+                auto operand_value = [tf32](float v) { return tf32 ? u2f(f2u(v) & 0xFFFFE000u) : v; };
+                pool.run(R * BC * M, 16, [&](int64_t s, int64_t e) {
+                    std::vector<double> acc((size_t)N);
+                    std::vector<float> row((size_t)N);
+                    for (int64_t i = s; i < e; ++i) {
+                        const int64_t m = i % M, b = (i / M) % BC, c = i / (M * BC);
+                        const int64_t lo = c * chunk, hi = std::min(K, lo + chunk);
+                        std::fill(acc.begin(), acc.end(), 0.0);
+                        const float* arow = a.data() + (b * M + m) * K;
+                        for (int64_t k = lo; k < hi; ++k) {
+                            const double av = (double)operand_value(arow[k]);
+                            const float* brow = bm.data() + (b * K + k) * N;
+                            for (int64_t j = 0; j < N; ++j) acc[j] += av * (double)operand_value(brow[j]);
+                        }
+                        for (int64_t j = 0; j < N; ++j) row[j] = (float)acc[j];
+                        float* dst = rows ? o + ((c * M + m) * BC + b) * N : o + ((c * BC + b) * M + m) * N;
+                        memcpy(dst, row.data(), (size_t)N * 4);
+                    }
+                });
+                return;
+            }
             pool.run(R * BC * M, 16, [&](int64_t s, int64_t e) {
                 std::vector<float> acc((size_t)N);
                 for (int64_t i = s; i < e; ++i) {
@@ -661,6 +696,12 @@ int cpu_ref_set_output(void* h, int parameter, float* data, int64_t count) {
     auto* p = static_cast<Program*>(h);
     p->outputs[parameter] = data;
     p->output_counts[parameter] = count;
+    return 0;
+}
+int cpu_ref_set_checker_mode(void* h, int f64_accumulate, const int* tf32_nodes, int tf32_node_count) {
+    auto* p = static_cast<Program*>(h);
+    p->f64_accumulate = f64_accumulate != 0;
+    p->tf32_nodes.assign(tf32_nodes, tf32_nodes + tf32_node_count);
     return 0;
 }
 // One Environment::run of the graph on `threads` host threads; returns the wall time in seconds, or -1.

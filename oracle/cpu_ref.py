@@ -3,6 +3,9 @@
 
     build()                      g++ -O2 -> oracle/_build/libcpu_ref.so (called from __graft_entry__.build())
     run_graph(graph, params, seed, threads) -> ({parameter id: new value}, seconds)
+    check_graph(graph, params, seed, tf32_nodes) -> {parameter id: new value}: "checker mode" -- float64-accumulated sums
+        like oracle.interp (and optional TF32 operand truncation on the listed MatMul nodes), for parity tests at
+        mini-batch sizes the numpy interpreter takes minutes for (m = 1000 ... 8192)
 """
 import ctypes
 import json
@@ -38,6 +41,7 @@ def lib():
         _lib.cpu_ref_run.restype = ctypes.c_double
         _lib.cpu_ref_run.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int]
         _lib.cpu_ref_error.restype = ctypes.c_char_p
+        _lib.cpu_ref_set_checker_mode.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
     return _lib
 
 
@@ -55,6 +59,10 @@ class Program:
             raise RuntimeError(self._lib.cpu_ref_error().decode())
         self.output_shapes = {n["parameter"]: n["shape"] for n in graph["nodes"] if n["op"] == "Output"}
         self._keep = {}
+
+    def set_checker_mode(self, f64_accumulate=True, tf32_nodes=()):
+        ids = np.asarray(sorted(int(i) for i in tf32_nodes), dtype=np.int32)
+        self._lib.cpu_ref_set_checker_mode(self._h, int(f64_accumulate), ids.ctypes.data if ids.size else None, int(ids.size))
 
     def run(self, params, seed=0, threads=0):
         threads = threads or hardware_threads()
@@ -85,5 +93,16 @@ def run_graph(graph, params, seed=0, threads=0):
     prog = Program(graph)
     try:
         return prog.run(params, seed, threads)
+    finally:
+        prog.close()
+
+
+def check_graph(graph, params, seed=0, tf32_nodes=(), threads=0):
+    """The step as oracle.interp.run_graph computes it (float64-accumulated Reduce / MatMul sums rounded once, TF32
+    truncation on `tf32_nodes`), on all host threads: the checker for large mini-batches."""
+    prog = Program(graph)
+    try:
+        prog.set_checker_mode(True, tf32_nodes)
+        return prog.run(params, seed, threads)[0]
     finally:
         prog.close()

@@ -167,3 +167,26 @@ def test_cpu_ref_reference_known_answers(host_env, make_case):
     got, _ = cpu_ref.run_graph(scope.export_json(), {p.id: data for p, (_, _, data) in zip(ins, case.inputs)}, TEST_RAND_SEED, threads=2)
     for p, (_, _, expected) in zip(outs, case.outputs):
         np.testing.assert_array_equal(got[p.id].reshape(-1), np.asarray(expected, np.float32).reshape(-1))
+
+
+@pytest.mark.parametrize("network,m,tf32", [("conv-net", 16, False), ("conv-net", 16, True), ("single-layer-dropout", 32, True)])
+def test_cpu_ref_checker_mode_matches_numpy_oracle(host_env, network, m, tf32):
+    """cpu_ref's checker mode (float64-accumulated sums, TF32 truncation on chosen MatMuls) is the numpy interpreter's
+    arithmetic on all host cores: the large-batch GPU parity tests (m = 1000 / 8192, tests/test_gpu_bench_regime.py) rely
+    on it where the interpreter would take minutes.  Every output of one SGD step within 2e-6 of each tensor's maximum
+    (both round a float64 sum once; only the order of the float64 additions differs).  With TF32 truncation 2e-5: a last-bit
+    difference in one layer's output can cross a truncation boundary of the next layer's operand (2^-10 of that element)."""
+    from helpers import init_example_params, synthetic_batch
+    from oracle import cpu_ref
+    ex = host_env.example(network, m, optimizer="descent")
+    rng = np.random.default_rng(12)
+    params = init_example_params(ex, rng)
+    params[ex.x.id], params[ex.y.id] = synthetic_batch(ex, rng)
+    matmuls = {n["id"] for n in ex.train_graph_json["nodes"] if n["op"] == "MatMul"}
+    nodes = set(sorted(matmuls)[::2]) if tf32 else set()  # every other MatMul: the per-node selection is exercised too
+    want = run_graph(ex.train_graph_json, params, 3, tf32=("trunc", nodes) if nodes else None)
+    got = cpu_ref.check_graph(ex.train_graph_json, params, 3, tf32_nodes=nodes, threads=4)
+    assert set(got) == set(want)
+    for pid, w in want.items():
+        scale = max(float(np.abs(w).max()), 1e-30)
+        assert float(np.abs(got[pid].astype(np.float64) - w).max()) <= (2e-5 if tf32 else 2e-6) * scale, (network, pid)
