@@ -647,9 +647,36 @@ void Graph::absorb_column_sums(std::vector<Cluster>& clusters) {
 // programs are independent by construction of the levels.  A program that reads a parameter is never grouped with
 // one that writes the same parameter: the planner lets a kernel update a parameter in place when it reads the old
 // value at the same element, which only holds inside one program.
+// Multi-tensor optimiser step (north_star (c): SGD / Adam as one hand-scheduled kernel, optimizer.rs:62-112).  The
+// reference's optimisers emit one per-element update per parameter tensor, which the level schedule places right
+// behind that tensor's gradient: eight (conv-net) or sixteen (multi-hash) launches of a few microseconds each spread
+// over the backward pass.  A per-element cluster whose every result goes straight into a parameter (theta, m, v, the
+// running loss / accuracy sums) has no consumer inside the step, so it can run at the very end: all of them move to
+// one final level, where group_small_per_element makes them ONE launch with a pointer table (block ranges select the
+// tensor).  In-place updates stay valid: every other read of those parameters is now earlier.
+void Graph::sink_parameter_updates(std::vector<Cluster>& clusters) {
+    auto cons = ops_.consumers();
+    int last_level = 0;
+    for (const Cluster& c : clusters)
+        if (!c.members.empty()) last_level = std::max(last_level, c.level);
+    for (size_t ci = 0; ci < clusters.size(); ++ci) {
+        Cluster& c = clusters[ci];
+        if (c.kind != ClusterKind::PerElement || c.members.empty() || c.outputs.empty()) continue;
+        bool only_parameter_writes = true;
+        for (int out : c.outputs)
+            for (auto [dst, k] : cons[out]) {
+                const OpNode& d = ops_.nodes[dst];
+                if (d.alive && d.op.kind != OpKind::Output && d.cluster_id != (int)ci) only_parameter_writes = false;  // members read each other in registers
+            }
+        if (only_parameter_writes) c.level = last_level + 1;
+    }
+}
+
 void Graph::group_small_per_element(std::vector<Cluster>& clusters) {
     constexpr int64_t kSmall = 1 << 18;  // elements
-    constexpr size_t kMaxBuffers = 40;
+    int final_level = 0;
+    for (const Cluster& c : clusters)
+        if (!c.members.empty()) final_level = std::max(final_level, c.level);
     auto cons = ops_.consumers();
     auto params_read = [&](const Cluster& c) {
         std::set<int> ids;
@@ -670,6 +697,8 @@ void Graph::group_small_per_element(std::vector<Cluster>& clusters) {
         if (c.kind == ClusterKind::PerElement && !c.members.empty() && c.group.empty() && c.element_count <= kSmall) by_level[c.level].push_back(i);
     }
     for (auto& [level, ids] : by_level) {
+        // the final level holds the sunk parameter updates (~8 buffers per tensor): one launch for up to ~24 tensors
+        const size_t kMaxBuffers = level == final_level ? 200 : 40;
         std::vector<size_t> open;  // indices of group heads at this level
         for (size_t i : ids) {
             const auto reads = params_read(clusters[i]), writes = params_written(clusters[i]);
@@ -1020,6 +1049,7 @@ void Graph::build_clusters() {
         if (c.kind == ClusterKind::PerElement) build_per_element_program(c);
     absorb_per_element_epilogues(clusters);
     absorb_column_sums(clusters);
+    sink_parameter_updates(clusters);
     group_small_per_element(clusters);
 
     // levels are a topological order of clusters: fusable edges stay inside a cluster, all others climb

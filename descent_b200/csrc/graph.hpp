@@ -114,6 +114,7 @@ private:
     void sink_permutations_into_per_element();
     void absorb_per_element_epilogues(std::vector<Cluster>& clusters);
     void absorb_column_sums(std::vector<Cluster>& clusters);
+    void sink_parameter_updates(std::vector<Cluster>& clusters);
     void group_small_per_element(std::vector<Cluster>& clusters);
     bool absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     bool absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);

@@ -383,11 +383,11 @@ int dsc_kernel_set_max_dynamic_smem(dsc_kernel kernel, int bytes) {
 
 int dsc_launch(dsc_ctx* ctx, dsc_kernel kernel, uint32_t gx, uint32_t gy, uint32_t gz, uint32_t block_x, uint32_t smem,
                const uint64_t* buffers, int num_buffers) {
-    if (num_buffers < 0 || num_buffers > 62) return set_error(DSC_ERR_INVALID, "too many kernel buffers (%d)", num_buffers);
+    if (num_buffers < 0 || num_buffers > 254) return set_error(DSC_ERR_INVALID, "too many kernel buffers (%d)", num_buffers);
     if (gx == 0 || gy == 0 || gz == 0) return DSC_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    uint64_t values[64];
-    void* params[64];
+    uint64_t values[256];  // 4 KB of kernel parameters hold 512 pointers; multi-tensor optimiser launches bind ~8 per tensor
+    void* params[256];
     for (int i = 0; i < num_buffers; ++i) {
         values[i] = buffers[i];
         params[i] = &values[i];

@@ -280,6 +280,17 @@ struct Program {
     // (10 explicit mantissa bits, interp.tf32_operand "trunc": what tcgen05 kind::tf32 does to FP32 operands).
     bool f64_accumulate = false;
     std::vector<int> tf32_nodes;
+    // Near-tie resolution (checker mode).  Two correct FP32 evaluations of the same step differ in the last bits of
+    // every sum, so a CompareAndSelect whose operands are closer than that noise (a pre-activation within 1e-6 of zero
+    // in leaky_relu's `x > 0`, a runner-up within 1e-6 of the window maximum in max_pool2d's `a == max`) may legitimately
+    // resolve either way; in a mini-batch of thousands of samples a few always do.  For the Select nodes listed in
+    // tie_nodes, elements with a != b and |a - b| <= tie_margin * max(|a|_inf, |b|_inf) are resolved as
+    // tie_resolution says (0: as computed, 1: condition true, 2: condition false) and counted, so a test can evaluate
+    // the band of outputs that every resolution of those ties spans.
+    std::vector<int> tie_nodes;
+    float tie_margin = 0.f;
+    int tie_resolution = 0;
+    std::atomic<int64_t> ties_seen{0};
 };
 
 thread_local std::string g_error;
@@ -505,6 +516,26 @@ struct Runner {
             out.resize((size_t)n.count);
             float* o = out.data();
             const bool eq = n.kind == "Eq";
+            if (prog.tie_margin > 0.f && std::find(prog.tie_nodes.begin(), prog.tie_nodes.end(), n.id) != prog.tie_nodes.end()) {
+                float scale = 0.f;
+                for (int64_t i = 0; i < n.count; ++i) scale = std::max(scale, std::max(std::fabs(a[i]), std::fabs(b[i])));
+                const float band = prog.tie_margin * scale;
+                const int resolution = prog.tie_resolution;
+                pool.run(n.count, 4096, [&](int64_t s, int64_t e) {
+                    int64_t ties = 0;
+                    for (int64_t i = s; i < e; ++i) {
+                        bool cond = eq ? a[i] == b[i] : a[i] > b[i];
+                        if (a[i] != b[i] && std::fabs(a[i] - b[i]) <= band) {
+                            ++ties;
+                            if (resolution == 1) cond = true;
+                            if (resolution == 2) cond = false;
+                        }
+                        o[i] = cond ? p[i] : q[i];
+                    }
+                    prog.ties_seen += ties;
+                });
+                return;
+            }
             pool.run(n.count, 4096, [&](int64_t s, int64_t e) { for (int64_t i = s; i < e; ++i) o[i] = (eq ? a[i] == b[i] : a[i] > b[i]) ? p[i] : q[i]; });
             return;
         }
@@ -704,6 +735,15 @@ int cpu_ref_set_checker_mode(void* h, int f64_accumulate, const int* tf32_nodes,
     p->tf32_nodes.assign(tf32_nodes, tf32_nodes + tf32_node_count);
     return 0;
 }
+int cpu_ref_set_tie_resolution(void* h, const int* select_nodes, int count, float margin, int resolution) {
+    auto* p = static_cast<Program*>(h);
+    p->tie_nodes.assign(select_nodes, select_nodes + count);
+    p->tie_margin = margin;
+    p->tie_resolution = resolution;
+    p->ties_seen = 0;
+    return 0;
+}
+long long cpu_ref_ties_seen(void* h) { return (long long)static_cast<Program*>(h)->ties_seen.load(); }
 // One Environment::run of the graph on `threads` host threads; returns the wall time in seconds, or -1.
 double cpu_ref_run(void* h, uint32_t rand_seed, int threads) {
     try {

@@ -42,6 +42,9 @@ def lib():
         _lib.cpu_ref_run.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int]
         _lib.cpu_ref_error.restype = ctypes.c_char_p
         _lib.cpu_ref_set_checker_mode.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        _lib.cpu_ref_set_tie_resolution.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int]
+        _lib.cpu_ref_ties_seen.restype = ctypes.c_longlong
+        _lib.cpu_ref_ties_seen.argtypes = [ctypes.c_void_p]
     return _lib
 
 
@@ -63,6 +66,13 @@ class Program:
     def set_checker_mode(self, f64_accumulate=True, tf32_nodes=()):
         ids = np.asarray(sorted(int(i) for i in tf32_nodes), dtype=np.int32)
         self._lib.cpu_ref_set_checker_mode(self._h, int(f64_accumulate), ids.ctypes.data if ids.size else None, int(ids.size))
+
+    def set_tie_resolution(self, select_nodes, margin, resolution):
+        ids = np.asarray(sorted(int(i) for i in select_nodes), dtype=np.int32)
+        self._lib.cpu_ref_set_tie_resolution(self._h, ids.ctypes.data if ids.size else None, int(ids.size), float(margin), int(resolution))
+
+    def ties_seen(self):
+        return int(self._lib.cpu_ref_ties_seen(self._h))
 
     def run(self, params, seed=0, threads=0):
         threads = threads or hardware_threads()
@@ -104,5 +114,58 @@ def check_graph(graph, params, seed=0, tf32_nodes=(), threads=0):
     try:
         prog.set_checker_mode(True, tf32_nodes)
         return prog.run(params, seed, threads)[0]
+    finally:
+        prog.close()
+
+
+def order_sensitive_selects(graph):
+    """Ids of the CompareAndSelect nodes whose compared operands (a, b) depend on a MatMul or a Reduce(Sum): their last
+    bits depend on the order of additions, so near-ties may resolve either way in a correct implementation.  Selects on
+    exact data (labels, one_hot, the dropout hash) are not in the list."""
+    nodes = {n["id"]: n for n in graph["nodes"]}
+    memo = {}
+
+    def sensitive(i):
+        stack = [i]
+        while stack:
+            j = stack[-1]
+            if j in memo:
+                stack.pop()
+                continue
+            n = nodes[j]
+            if n["op"] == "MatMul" or (n["op"] == "Reduce" and n.get("kind") == "Sum"):
+                memo[j] = True
+                stack.pop()
+                continue
+            todo = [a["src"] for a in n["args"] if a["src"] not in memo]
+            if todo:
+                stack.extend(todo)
+                continue
+            memo[j] = any(memo[a["src"]] for a in n["args"])
+            stack.pop()
+        return memo[i]
+
+    return [n["id"] for n in graph["nodes"] if n["op"] == "Select" and (sensitive(n["args"][0]["src"]) or sensitive(n["args"][1]["src"]))]
+
+
+def check_graph_with_tie_band(graph, params, seed=0, tf32_nodes=(), margin=1e-6, threads=0):
+    """check_graph plus the band its near-tie selects span: returns (outputs, band, ties) where band[pid] is the largest
+    absolute difference, over the step's outputs, between the natural evaluation and the evaluations that resolve every
+    near-tie (order_sensitive_selects, relative margin `margin`) as true resp. as false, and `ties` counts those elements."""
+    selects = order_sensitive_selects(graph)
+    prog = Program(graph)
+    try:
+        prog.set_checker_mode(True, tf32_nodes)
+        natural = prog.run(params, seed, threads)[0]
+        natural = {pid: v.copy() for pid, v in natural.items()}
+        band = {pid: 0.0 for pid in natural}
+        ties = 0
+        for resolution in (1, 2):
+            prog.set_tie_resolution(selects, margin, resolution)
+            forced = prog.run(params, seed, threads)[0]
+            ties = max(ties, prog.ties_seen())
+            for pid, v in forced.items():
+                band[pid] = max(band[pid], float(np.abs(v.astype(np.float64) - natural[pid]).max()))
+        return natural, band, ties
     finally:
         prog.close()

@@ -24,6 +24,20 @@ from test_gpu_conv_kernels import FP32_TOL, SHAPES, TF32_TOL
 pytestmark = pytest.mark.gpu
 
 
+# Near-tie band.  Two correct FP32 evaluations of one step differ in the last bits of every sum (order of additions), so a
+# CompareAndSelect whose operands are closer than that noise -- leaky_relu's `x > 0` for a pre-activation within ~1e-7 of
+# zero, max_pool2d's `a == max` for a runner-up within ~1e-7 of the winner -- resolves either way, and each such flip moves a
+# mean-over-the-batch gradient by one sample's full contribution (measured: up to 3e-2 of a bias gradient at m = 1000).  At
+# mini-batches of thousands of samples (2e7 ... 1.6e8 select elements per step) a few flips always happen; small batches
+# (every other parity test) rarely see one.  oracle.cpu_ref.check_graph_with_tie_band evaluates the step three times --
+# as computed, and with every order-sensitive select that is within `margin` of a tie forced true resp. false -- and
+# returns the band those resolutions span per output.  The assertion is  |gpu - oracle| <= tol * max|oracle| + 3 * band.
+# margin = the forward noise between the two evaluations: 2e-7 of the tensor's maximum for strict FP32; 1e-5 for TF32
+# operands, where a last-bit difference in one layer's output can cross a truncation boundary of the next layer's
+# operand (2^-11 of that element; measured 2.4e-6 of max|z| at the first dense layer).
+TIE_MARGIN = {"strict": 2e-7, "tf32": 1e-5}
+
+
 def tensor_core_nodes(env, ex):
     clusters = ex.train_graph.export_json()["clusters"]
     nodes, labels = set(), []
@@ -91,19 +105,29 @@ def test_network_step_many_tiles_per_cta(env, network, m, precision):
     fill_missing_inputs(env, ex.train_graph_json, params)
     seed = int(rng.integers(0, 2 ** 32))
     env.run(ex.train_graph, seed)
-    want = run_graph(ex.train_graph_json, params, seed, tf32=("trunc", nodes) if nodes else None)
+    want, band, ties = cpu_ref.check_graph_with_tie_band(ex.train_graph_json, params, seed, tf32_nodes=nodes, margin=TIE_MARGIN[precision])
     tol = 1e-5 if precision == "strict" else (3e-4 if network == "multi-hash" else 1e-4)
     theta = {p.id for p in ex.parameters} if optimizer == "adam" else set()  # Adam's first step: see test_gpu_networks.check_adam_update
-    worst = {pid: max_rel_err(env.read(env.parameter(pid)), w) for pid, w in want.items() if pid not in theta}
-    print(network, m, precision, worst)
-    assert max(worst.values()) <= tol, worst
+    worst, failed = {}, {}
+    for pid, w in want.items():
+        if pid in theta:
+            continue
+        err = max_rel_err(env.read(env.parameter(pid)), w)
+        worst[pid] = err
+        if not err <= tol + 3.0 * band[pid] / max(float(np.abs(w).max()), 1e-30):  # near-tie band: see TIE_MARGIN below
+            failed[pid] = err
+    print(network, m, precision, "ties", ties, worst)
+    assert not failed, (failed, worst)
+
+
 
 
 @pytest.mark.parametrize("precision", ["strict", "tf32"])
 @pytest.mark.parametrize("m", [1000, 8192])
 def test_conv_net_step_at_benchmark_batch(env, m, precision):
     """bench.py's workload at the reference's default batch and at the benchmark's: one SGD step of conv-net, every output
-    (loss / accuracy sums, all 8 parameter tensors = all gradients) against oracle.cpu_ref in checker mode."""
+    (loss / accuracy sums, momentum state = gradients, all 8 parameter tensors) against oracle.cpu_ref in checker mode.
+    Loss and accuracy sums do not depend on any select resolution: 1e-5 / exact in both precisions."""
     env.set_tf32(precision == "tf32")
     ex = env.example("conv-net", m, optimizer="descent")
     rng = np.random.default_rng(SEED_BASE + m)
@@ -115,14 +139,18 @@ def test_conv_net_step_at_benchmark_batch(env, m, precision):
     upload(env, params)
     seed = int(rng.integers(0, 2 ** 32))
     env.run(ex.train_graph, seed)
-    want = cpu_ref.check_graph(ex.train_graph_json, params, seed, tf32_nodes=nodes)
+    want, band, ties = cpu_ref.check_graph_with_tie_band(ex.train_graph_json, params, seed, tf32_nodes=nodes, margin=TIE_MARGIN[precision])
     tol = 1e-5 if precision == "strict" else 1e-4
-    worst = {env.parameter(pid).name() + "#%d" % pid: max_rel_err(env.read(env.parameter(pid)), w) for pid, w in want.items()}
-    print("conv-net m=%d %s:" % (m, precision), worst)
-    assert max(worst.values()) <= tol, worst
-    # gradients, not just parameters: the update theta' - theta = -lr * g is 2-10 % of max|theta| for the weight tensors
-    # (so the 1e-5 above already bounds it at <= 6e-4) and IS the parameter for the zero-initialised biases (1e-5 direct)
-    for p in ex.parameters:
-        upd_got = env.read(p).astype(np.float64) - params[p.id]
-        upd_want = want[p.id].astype(np.float64) - params[p.id]
-        assert max_rel_err(upd_got, upd_want) <= (1e-3 if precision == "strict" else 5e-3), (p.name(), p.id, max_rel_err(upd_got, upd_want))
+    report, failed = {}, {}
+    for pid, w in want.items():
+        name = env.parameter(pid).name() + "#%d" % pid
+        scale = max(float(np.abs(w).max()), 1e-30)
+        err = max_rel_err(env.read(env.parameter(pid)), w)
+        allowed = tol + 3.0 * band[pid] / scale
+        report[name] = "%.2g (band %.2g)" % (err, band[pid] / scale)
+        if not err <= allowed:
+            failed[name] = (err, allowed)
+    print("conv-net m=%d %s: %d near-tie select elements at margin %g; error vs oracle (tie band):" % (m, precision, ties, TIE_MARGIN[precision]), report)
+    assert not failed, failed
+    assert max_rel_err(env.read(ex.loss_sum), want[ex.loss_sum.id]) <= 1e-5
+    np.testing.assert_array_equal(env.read(ex.accuracy_sum), want[ex.accuracy_sum.id])
