@@ -36,14 +36,14 @@ def init_example_params(ex, rng, siren=False):
     return params
 
 
-def synthetic_batch(ex, rng):
+def synthetic_batch(ex, rng, image_width=512):
     xs, ys = ex.x.shape(), ex.y.shape()
     if len(xs) == 3:  # sentiment: word indices as f32, 0 = padding; labels 0..2 (examples/sentiment/main.rs:176-190)
         vocab = [p for p in ex.parameters if p.name() == "em"][0].shape()[0]
         return rng.integers(0, vocab, xs).astype(np.float32), rng.integers(0, 3, ys).astype(np.float32)
     if len(xs) == 4:  # fashion_mnist: x in [0,1), integer labels as f32 (main.rs:56,69)
         return rng.random(xs, dtype=np.float32), rng.integers(0, 10, ys).astype(np.float32)
-    w = 512
+    w = image_width  # image_fit: random pixels of a synthetic w x w image (BASELINE.json configs 4 / 5: 512 and 1024)
     px = rng.integers(0, w, (xs[0], 2))
     x = ((px + 0.5) * (2.0 / w) - 1.0).astype(np.float32)  # pixel centres (image_fit/main.rs:379-382)
     return x, rng.random(ys, dtype=np.float32)
