@@ -598,7 +598,7 @@ ClusterCode gen_reduce(const Graph& g, const Cluster& c, int ci, const CodegenOp
 
 const char* kMatMulTemplate = R"(
 // {{LABEL}}
-extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, const float* B, float* C, const unsigned* dsc_step) {
+{{PRO_FUNCS}}extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, const float* B, float* C, {{PRO_PARAMS}}const unsigned* dsc_step) {
     constexpr int BM = {{BM}}, BN = {{BN}}, BK = {{BK}}, TM = {{TM}}, TN = {{TN}}, NT = {{NT}};
     constexpr int TX = BN / TN, TY = BM / TM, NC = TX * TY;
     constexpr int M = {{M}}, N = {{N}}, K = {{K}}, KC = {{KC}}, BC = {{BC}};
@@ -629,7 +629,7 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
             float v = 0.f;
             if ((BM * BK % NT == 0 || i < BM * BK) && gm < M && gk < k_end && ({{A_VALID}})) {
 {{A_CHAIN}}
-                v = A[{{A_IDX}}];
+                v = {{A_LOAD1}};
             }
             ra[j] = v;
         }
@@ -641,7 +641,7 @@ extern "C" __global__ void __launch_bounds__({{NT}}) {{NAME}}(const float* A, co
             float v = 0.f;
             if ((BK * BN % NT == 0 || i < BK * BN) && gn < N && gk < k_end) {
 {{B_CHAIN}}
-                v = B[{{B_IDX}}];
+                v = {{B_LOAD1}};
             }
             rb[j] = v;
         }
@@ -847,6 +847,107 @@ EpilogueCode gen_epilogue(const Graph& g, const Cluster& c, const std::string& k
     return code;
 }
 
+// ---- operand prologues of GEMM kernels ---------------------------------------------------------------
+// How a GEMM kernel fetches operand k (0 = A, 1 = B) at element index `idx` of the operand's source array.  Plain
+// operands are loaded from memory.  When a PrologueRequest names a per-element producer for the operand (graph.hpp
+// OperandPrologue), the source array does not exist: `<kernel>_op<A|B>4(idx, ...)` / `...1(idx, ...)` evaluate the
+// producer's program for the four consecutive elements starting at idx / for element idx, loading the producer's own
+// inputs instead (128-bit where they are plain arrays or their chains keep aligned groups of four together).
+PrologueRequest* g_prologue = nullptr;  // set by generate_cluster_code for the duration of one cluster's generation
+
+bool prologue_requested(int operand) { return g_prologue && g_prologue->producer[operand]; }
+
+struct OperandLoad {
+    bool fused = false;
+    std::string funcs;    // device functions, emitted ahead of the kernel
+    std::string params;   // extra kernel parameters ("const float* pa0, const float* pa1, ")
+    std::string call;     // the same names as call arguments (", pa0, pa1")
+    std::string ptr;      // "A" / "B"
+    std::string kernel;
+    std::vector<KernelArg> launch_args;
+    std::vector<int> reads;
+    double bytes = 0;
+    std::string load4(const std::string& idx) const {
+        return fused ? kernel + "_op" + ptr + "4((unsigned)(" + idx + ")" + call + ")" : "*reinterpret_cast<const float4*>(" + ptr + " + " + idx + ")";
+    }
+    std::string load1(const std::string& idx) const {
+        return fused ? kernel + "_op" + ptr + "1((unsigned)(" + idx + ")" + call + ")" : ptr + "[" + idx + "]";
+    }
+};
+
+// Call only when the generator is certain to emit its kernel (after every `return false`): it marks the request fused.
+OperandLoad operand_load(const Graph& g, int operand, const std::string& kernel, const ClusterInput& in, const CodegenOptions& opt) {
+    OperandLoad o;
+    o.ptr = operand == 0 ? "A" : "B";
+    o.kernel = kernel;
+    o.bytes = chain_bytes(g, in);
+    if (!prologue_requested(operand)) return o;
+    const Cluster& p = *g_prologue->producer[operand];
+    DSC_CHECK(p.outputs.size() == 1 && p.outputs[0] == in.node_id, "operand prologue does not produce this operand");
+    g_prologue->fused[operand] = true;
+    o.fused = true;
+    o.bytes = 0;
+    const std::string prefix = operand == 0 ? "pa" : "pb";
+    std::ostringstream params, call, fparams;
+    std::vector<bool> is_loaded(p.inputs.size(), false);
+    for (const auto& op : p.ops)
+        if (op.kind == PerElementOp::Load) is_loaded[op.input_index] = true;
+    for (size_t i = 0; i < p.inputs.size(); ++i) {
+        params << "const float* " << prefix << i << ", ";
+        call << ", " << prefix << i;
+        fparams << ", const float* in" << i;
+        o.launch_args.push_back({KernelArg::NodeBuffer, p.inputs[i].node_id, 0});
+        o.reads.push_back(p.inputs[i].node_id);
+        if (is_loaded[i]) o.bytes += chain_bytes(g, p.inputs[i]);
+    }
+    o.params = params.str();
+    o.call = call.str();
+    std::ostringstream os;
+    os << "// operand " << o.ptr << " computed while loading: " << p.label << "\n";
+    {   // four consecutive elements
+        os << "__device__ __forceinline__ float4 " << kernel << "_op" << o.ptr << "4(unsigned base" << fparams.str() << ") {\n";
+        std::vector<bool> vector_load(p.inputs.size(), false);
+        int uniq = 0;
+        for (size_t i = 0; i < p.inputs.size(); ++i) {
+            if (!is_loaded[i]) continue;
+            const ViewChain& chain = p.inputs[i].chain;
+            if (chain.is_identity()) {
+                os << "    const float4 q" << i << " = *reinterpret_cast<const float4*>(in" << i << " + base);\n";
+            } else if (chain_vector_run(chain, p.inputs[i].arg_shape.at(-1)) == 4) {
+                std::string idx = emit_chain(os, chain, "base", uniq);
+                os << "    const float4 q" << i << " = *reinterpret_cast<const float4*>(in" << i << " + " << idx << ");\n";
+            } else {
+                continue;
+            }
+            vector_load[i] = true;
+            os << "    const float vin" << i << "[4] = {q" << i << ".x, q" << i << ".y, q" << i << ".z, q" << i << ".w};\n";
+        }
+        os << "    float r[4];\n    #pragma unroll\n    for (int v = 0; v < 4; ++v) {\n    const unsigned e = base + v; (void)e;\n";
+        emit_per_element_ops(os, p, opt, uniq, vector_load, -1);
+        os << "    r[v] = t" << p.output_ops[0] << ";\n    }\n    return make_float4(r[0], r[1], r[2], r[3]);\n}\n";
+    }
+    {   // one element
+        os << "__device__ __forceinline__ float " << kernel << "_op" << o.ptr << "1(unsigned e" << fparams.str() << ") {\n";
+        std::vector<bool> vector_load(p.inputs.size(), false);
+        int uniq = 0;
+        emit_per_element_ops(os, p, opt, uniq, vector_load, -1);
+        os << "    return t" << p.output_ops[0] << ";\n}\n";
+    }
+    o.funcs = os.str();
+    return o;
+}
+
+// after a kernel's own arguments: bind the producers' inputs, and give the never-materialised operand a valid address
+void bind_operand_loads(KernelLaunch& l, ClusterCode* code, const OperandLoad* a, const OperandLoad* b) {
+    const OperandLoad* ops[2] = {a, b};
+    for (int k = 0; k < 2; ++k) {
+        if (!ops[k] || !ops[k]->fused) continue;
+        l.args[k] = ops[k]->launch_args[0];  // the kernel never dereferences A / B itself
+        l.args.insert(l.args.end(), ops[k]->launch_args.begin(), ops[k]->launch_args.end());
+        code->extra_reads.insert(code->extra_reads.end(), ops[k]->reads.begin(), ops[k]->reads.end());
+    }
+}
+
 // ---- stride-1 convolutions as halo-tiled implicit GEMMs (halo_conv_template.inc) ---------------------
 struct HaloConv {
     bool backward_input = false;
@@ -914,16 +1015,18 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
     }
     const std::string name = "k" + num(ci);
     if (!c.epilogue.empty() && (h.backward_input || !h.rows_mode || G * NG % 4 != 0)) return false;
+    if (prologue_requested(1)) return false;  // the weights are staged once per CTA, element by element: no producer there
     const EpilogueCode epi = gen_epilogue(g, c, name, opt);
+    const OperandLoad la = operand_load(g, 0, name, a, opt);
     out->source = subst(kHaloConvTemplate,
-                        {{"LABEL", c.label}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args}, {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)},
+                        {{"LABEL", c.label + (la.fused ? "  [A = " + g_prologue->producer[0]->label + "]" : "")}, {"PRO_FUNCS", la.funcs}, {"PRO_PARAMS", la.params}, {"A_LOAD4", la.load4(ia)}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args}, {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)},
                          {"FW", num(FW)}, {"KG", num(KG)}, {"NG", num(NG)}, {"BN", num(BN)}, {"LEAD", num(lead)}, {"TMEM_COLS", num(tmem_cols)}, {"NPIX", num(npix)},
                          {"PY", num(h.unpad_h)}, {"PX", num(h.unpad_w)}, {"STAGE_OUT", stage_out ? "true" : "false"}, {"OUT_W", num(OW)},
                          // loading the next halo before the drain pays for the forward kernel (0.125 -> 0.117 ms) and costs the
                          // backward one, whose epilogue is the longer Unpad pass (0.136 -> 0.175 ms): measured, conv-net m=8192
                          {"PREFETCH", h.backward_input ? "false" : "true"}, {"ROWS_FIRST", h.unpad_rows_first ? "true" : "false"},
                          {"A_COORDS", a_coords.str()}, {"B_COORDS", b_coords.str()}, {"TAP_PIXEL", tap_pixel.str()}, {"OUT_OK", out_ok.str()},
-                         {"OUT_INDEX", out_index.str()}, {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
+                         {"OUT_INDEX", out_index.str()}, {"A_CHAIN", ca.str()}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
     KernelLaunch l;
     l.entry = name;
     const int64_t resident = std::max<int64_t>(1, std::min<int64_t>({8, (200 * 1024) / smem, 512 / tmem_cols}));
@@ -934,8 +1037,9 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
     l.args.insert(l.args.end(), epi.launch_args.begin(), epi.launch_args.end());
+    bind_operand_loads(l, out, &la, nullptr);
     const int64_t out_pixels = h.images * (rows - 2 * h.unpad_h) * ((h.backward_input ? W : OW) - 2 * h.unpad_w);
-    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(out_pixels * G * NG) : epi.bytes);
+    l.algorithmic_bytes = la.bytes + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(out_pixels * G * NG) : epi.bytes);
     l.flops = 2.0 * (double)(out_pixels * G * NG) * (double)(FH * FW * KG);
     out->launches.push_back(l);
     return true;
@@ -1061,10 +1165,12 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     std::string ia = emit_chain(ca, a.chain, {{"batch", KW * MPIX, G}, {"gm", MPIX, KW}, {"gk", 1, MPIX}}, uniq, "                ");
     std::string ib = emit_chain(cb, b.chain, {{"batch", MPIX * NCO, G}, {"gk", NCO, MPIX}, {"gn", 1, NCO}}, uniq, "                ");
     const std::string name = "k" + num(ci);
-    out->source = subst(kHaloWgradTemplate, {{"LABEL", c.label}, {"NAME", name}, {"G", num(G)}, {"IMAGES", num(B)}, {"OH", num(OH)}, {"OW", num(OW)},
+    const OperandLoad la = operand_load(g, 0, name, a, opt), lb = operand_load(g, 1, name, b, opt);
+    out->source = subst(kHaloWgradTemplate, {{"LABEL", c.label + (lb.fused ? "  [B = " + g_prologue->producer[1]->label + "]" : "")}, {"NAME", name},
+                                             {"PRO_FUNCS", la.funcs + lb.funcs}, {"PRO_PARAMS", la.params + lb.params}, {"A_LOAD4", la.load4(ia)}, {"B_LOAD4", lb.load4(ib)}, {"G", num(G)}, {"IMAGES", num(B)}, {"OH", num(OH)}, {"OW", num(OW)},
                                              {"FH", num(FH)}, {"FW", num(FW)}, {"CG", num(C)}, {"NCO", num(NCO)}, {"TMEM_COLS", num(tmem_cols)}, {"MROWS", num(m_rows)}, {"WIDE", wide ? "true" : "false"},
                                              {"COLSUM", colsum ? "true" : "false"},
-                                             {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
+                                             {"A_CHAIN", ca.str()}, {"B_CHAIN", cb.str()}});
     const int64_t out_count = G * KW * NCO;
     const int64_t colsum_offset = div_round_up(S * out_count * 4, 256) * 256;
     KernelLaunch l;
@@ -1076,7 +1182,8 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::Scratch, -1, 0},
               {KernelArg::Scratch, -1, colsum ? colsum_offset : 0}};
-    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)out_count;
+    bind_operand_loads(l, out, &la, &lb);
+    l.algorithmic_bytes = la.bytes + lb.bytes + 4.0 * (double)out_count;
     l.flops = 2.0 * (double)G * (double)KW * (double)NCO * (double)MPIX;
     out->launches.push_back(l);
     out->scratch_bytes = S * out_count * 4;
@@ -1125,7 +1232,7 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
     l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)(BC * M * N);
     l.flops = 2.0 * (double)BC * (double)M * (double)N * (double)K;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
-    if (K <= 32 && N <= 32 && M >= 65536) {
+    if (K <= 32 && N <= 32 && M >= 65536 && !prologue_requested(0) && !prologue_requested(1)) {
         std::string ia = emit_chain(ca, a.chain, {{"batch", M * K, BC}, {"gm", K, M}, {"gk", 1, K}}, uniq, "            ");
         std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, BC}, {"gk", N, K}, {"gn", 1, N}}, uniq, "            ");
         if (!c.epilogue.empty() && (N % 4 != 0 || !(rows_mode ? true : BC == 1))) return false;
@@ -1140,7 +1247,7 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
         out->launches.push_back(l);
         return true;
     }
-    if (M <= 16 && M * N <= 288 && K >= 65536 && c.epilogue.empty()) {
+    if (M <= 16 && M * N <= 288 && K >= 65536 && c.epilogue.empty() && !prologue_requested(0)) {
         int64_t nsplit = 1;
         // at most 80 accumulators per thread; splitting further re-reads A and measured slower (0.133 -> 0.234 ms at 36)
         while (M * (N / nsplit) > 80 && nsplit < 32 && (N / nsplit) % 2 == 0) nsplit *= 2;
@@ -1150,10 +1257,13 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
         std::string ia = emit_chain(ca, a.chain, {{"batch", M * K, BC}, {"gm", K, M}, {"gk", 1, K}}, uniq, "            ");
         std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, BC}, {"gk", N, K}, {"gn", 1, N}}, uniq, "                ");
         const bool colsum = !c.column_sum.empty();
-        out->source = subst(kThinReduceTemplate, {{"LABEL", c.label}, {"NAME", name}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"BC", num(BC)},
-                                                 {"COLSUM", colsum ? "true" : "false"},
+        const OperandLoad lb = operand_load(g, 1, name, b, opt);
+        out->source = subst(kThinReduceTemplate, {{"LABEL", c.label + (lb.fused ? "  [B = " + g_prologue->producer[1]->label + "]" : "")}, {"NAME", name}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"BC", num(BC)},
+                                                 {"COLSUM", colsum ? "true" : "false"}, {"PRO_FUNCS", lb.funcs}, {"PRO_PARAMS", lb.params},
+                                                 {"B_LOAD4", lb.load4(ib)}, {"B_LOAD1", lb.load1(ib)},
                                                  {"NSPLIT", num(nsplit)}, {"B_VEC", b_vec ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
-                                                 {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
+                                                 {"B_CHAIN", cb.str()}, {"C_ROW", c_row}});
+        l.algorithmic_bytes = chain_bytes(g, a) + lb.bytes + 4.0 * (double)(BC * M * N);
         const int64_t rows_per_cta = 256 / nsplit;
         const int64_t S = std::max<int64_t>(1, std::min<int64_t>((int64_t)opt.sm_count * 2 / BC, K / (rows_per_cta * 8)));
         l.grid_x = (uint32_t)S;
@@ -1167,6 +1277,7 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
         if (S > 1) {
             l.args.push_back({KernelArg::Scratch, -1, 0});
             l.args.push_back(colsum_arg);
+            bind_operand_loads(l, out, nullptr, &lb);
             out->launches.push_back(l);
             out->scratch_bytes = S * out_count * 4;
             if (colsum) {
@@ -1193,6 +1304,7 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
         } else {
             l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
             l.args.push_back(colsum_arg);
+            bind_operand_loads(l, out, nullptr, &lb);
             out->launches.push_back(l);
         }
         return true;
@@ -1401,13 +1513,22 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
                              {"B_MN", b_mn ? "true" : "false"}, {"A_LAYOUT", a_mn ? "MN-major" : "K-major"}, {"B_LAYOUT", b_mn ? "MN-major" : "K-major"},
                              {"A_VEC", a_vec ? "true" : "false"}, {"B_VEC", b_vec ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
                              {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}, {"A_VALID", a_valid}});
-    else
+    OperandLoad la, lb;
+    la.ptr = "A"; lb.ptr = "B";
+    la.bytes = chain_bytes(g, a); lb.bytes = chain_bytes(g, b);
+    if (!tc) {  // the strict-FP32 SIMT kernel evaluates operand producers element by element while gathering its tiles
+        la = operand_load(g, 0, name, a, opt);
+        lb = operand_load(g, 1, name, b, opt);
+    }
+    if (!tc)
     code.source = subst(kMatMulTemplate,
-                        {{"LABEL", c.label}, {"NAME", name}, {"NT", num(t.nt)}, {"BM", num(t.bm)}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"TM", num(t.tm)},
+                        {{"LABEL", c.label + (la.fused ? "  [A = " + g_prologue->producer[0]->label + "]" : "") + (lb.fused ? "  [B = " + g_prologue->producer[1]->label + "]" : "")},
+                         {"PRO_FUNCS", la.funcs + lb.funcs}, {"PRO_PARAMS", la.params + lb.params}, {"A_LOAD1", la.load1(ia)}, {"B_LOAD1", lb.load1(ib)},
+                         {"NAME", name}, {"NT", num(t.nt)}, {"BM", num(t.bm)}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"TM", num(t.tm)},
                          {"TN", num(t.tn)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"KC", num(KC)}, {"BC", num(BC)},
                          {"A_DECODE", decode("lm", "BM", t.bm, "lk", "BK", t.bk, a_m_fast)},
                          {"B_DECODE", decode("ln", "BN", t.bn, "lk", "BK", t.bk, !b_k_fast)},
-                         {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}, {"A_VALID", a_valid}});
+                         {"A_CHAIN", ca.str()}, {"B_CHAIN", cb.str()}, {"C_ROW", c_row}, {"A_VALID", a_valid}});
     KernelLaunch l;
     l.entry = name;
     l.grid_x = (uint32_t)(div_round_up(M, t.bm) * div_round_up(N, t.bn));
@@ -1430,7 +1551,8 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
     if (via_scratch) l.args.push_back({KernelArg::Scratch, -1, 0});
     else l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
-    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)out_count;
+    bind_operand_loads(l, &code, &la, &lb);
+    l.algorithmic_bytes = la.bytes + lb.bytes + 4.0 * (double)out_count;
     l.flops = 2.0 * (double)BC * (double)M * (double)N * (double)K;
     code.launches.push_back(l);
     if (via_scratch) {
@@ -1883,13 +2005,22 @@ __device__ __forceinline__ float dsc_rand(unsigned uid, unsigned index, unsigned
 )";
 }
 
-ClusterCode generate_cluster_code(const Graph& graph, int ci, const CodegenOptions& opt) {
+ClusterCode generate_cluster_code(const Graph& graph, int ci, const CodegenOptions& opt, PrologueRequest* prologue) {
     const Cluster& c = graph.clusters()[ci];
+    struct Scoped {  // the request is visible to the generators of this one cluster only
+        explicit Scoped(PrologueRequest* r) { g_prologue = r; }
+        ~Scoped() { g_prologue = nullptr; }
+    } scoped(c.kind == ClusterKind::MatMul ? prologue : nullptr);
+    if (prologue) prologue->fused[0] = prologue->fused[1] = false;
     switch (c.kind) {
         case ClusterKind::PerElement: return gen_per_element(graph, c, ci, opt);
         case ClusterKind::Reduce: return gen_reduce(graph, c, ci, opt);
         case ClusterKind::MatMul: {
             ClusterCode code = gen_matmul(graph, c, ci, opt);
+            if (prologue && prologue->fused[1] && !c.column_sum.empty() && !code.column_sum_done) {
+                prologue->fused[1] = false;  // the absorbed column sums would read B from memory, where it no longer exists
+                return code;
+            }
             if (!c.column_sum.empty() && !code.column_sum_done) {
                 // the GEMM kernel chosen for this shape does not produce the column sums: run the absorbed Reduce chain
                 // after it, intermediate results in scratch

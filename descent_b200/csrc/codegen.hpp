@@ -34,6 +34,18 @@ struct ClusterCode {
     std::vector<KernelLaunch> launches;
     int64_t scratch_bytes = 0;
     bool column_sum_done = false;  // the GEMM kernel also produced Cluster::column_sum's result (outputs[1])
+    // operand prologues (graph.hpp OperandPrologue): nodes this cluster's kernels read although no graph edge says so
+    // (the inputs of a producer evaluated inside the operand loader): the planner keeps them alive until this cluster
+    std::vector<int> extra_reads;
+    bool skipped = false;  // a producer every consumer evaluates on the fly: no kernel, its output is never materialised
+};
+
+// Request to evaluate per-element producers inside a MatMul cluster's operand loaders.  `fused[k]` is set by the kernel
+// generator that honours it; a request that comes back unfused means the chosen kernel cannot (the caller then
+// generates the cluster again without the request and the producer runs as its own kernel).
+struct PrologueRequest {
+    const Cluster* producer[2] = {nullptr, nullptr};  // operand A / B
+    bool fused[2] = {false, false};
 };
 
 struct CodegenOptions {
@@ -43,7 +55,7 @@ struct CodegenOptions {
 };
 
 std::string kernel_prelude();
-ClusterCode generate_cluster_code(const Graph& graph, int cluster_index, const CodegenOptions& options);
+ClusterCode generate_cluster_code(const Graph& graph, int cluster_index, const CodegenOptions& options, PrologueRequest* prologue = nullptr);
 
 // host-side evaluation of a chain (tests, layout heuristics): consumer element -> producer element
 int64_t eval_chain(const ViewChain& chain, int64_t e);

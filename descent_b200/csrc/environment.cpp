@@ -44,7 +44,42 @@ std::string rename_kernels(const std::string& text, const std::string& from, con
 std::string generate_graph_source(const Graph& graph, const CodegenOptions& options, std::vector<ClusterCode>* per_cluster) {
     std::string src = kernel_prelude();
     std::map<std::string, int> first_with_body;
-    for (int ci = 0; ci < (int)graph.clusters().size(); ++ci) {
+    const int nc = (int)graph.clusters().size();
+
+    // Operand prologues (graph.hpp OperandPrologue): a per-element producer is evaluated inside the operand loaders of
+    // the GEMMs that consume it when EVERY consumer's kernel can do that under these options; then the producer has no
+    // kernel and its output is never written.  Otherwise nothing changes for that producer.
+    std::vector<PrologueRequest> accepted(nc);
+    std::vector<ClusterCode> pregenerated(nc);
+    std::vector<char> has_pregenerated(nc, 0), skipped(nc, 0);
+    for (const OperandPrologue& cand : graph.operand_prologues()) {
+        std::vector<std::pair<int, PrologueRequest>> requests;  // one per consumer cluster (A and B may both name this producer)
+        for (const auto& use : cand.uses) {
+            auto it = std::find_if(requests.begin(), requests.end(), [&](const auto& r) { return r.first == use.cluster; });
+            if (it == requests.end()) {
+                requests.push_back({use.cluster, accepted[use.cluster]});
+                it = requests.end() - 1;
+            }
+            it->second.producer[use.operand] = &graph.clusters()[cand.producer];
+        }
+        std::vector<ClusterCode> codes;
+        bool all_fused = true;
+        for (auto& [ci, request] : requests) {
+            codes.push_back(generate_cluster_code(graph, ci, options, &request));
+            for (int k = 0; k < 2; ++k)
+                if (request.producer[k] && !request.fused[k]) all_fused = false;
+            if (!all_fused) break;
+        }
+        if (!all_fused) continue;
+        for (size_t i = 0; i < requests.size(); ++i) {
+            accepted[requests[i].first] = requests[i].second;
+            pregenerated[requests[i].first] = std::move(codes[i]);
+            has_pregenerated[requests[i].first] = 1;
+        }
+        skipped[cand.producer] = 1;
+    }
+
+    for (int ci = 0; ci < nc; ++ci) {
         {
             // generated kernels index with 32-bit integers: refuse anything they could not address instead of wrapping
             const Cluster& c = graph.clusters()[ci];
@@ -64,11 +99,13 @@ std::string generate_graph_source(const Graph& graph, const CodegenOptions& opti
             for (const Cluster& sub : c.epilogue) check_cluster(sub);
             for (const Cluster& sub : c.column_sum) check_cluster(sub);
         }
-        ClusterCode code = generate_cluster_code(graph, ci, options);
+        ClusterCode code;
+        if (skipped[ci]) code.skipped = true;
+        else if (has_pregenerated[ci]) code = std::move(pregenerated[ci]);
+        else code = generate_cluster_code(graph, ci, options);
         const std::string name = "k" + std::to_string(ci);
         if (!code.source.empty()) {
             std::string body = rename_kernels(code.source, name, "k@");
-            const std::string label = "// " + graph.clusters()[ci].label;  // labels carry shapes but also node-specific text: keep them out of the key
             auto it = first_with_body.find(body);
             if (it == first_with_body.end()) {
                 first_with_body.emplace(std::move(body), ci);
@@ -79,7 +116,6 @@ std::string generate_graph_source(const Graph& graph, const CodegenOptions& opti
                     if (!l.entry.empty()) l.entry = rename_kernels(l.entry, name, original);
                 code.source.clear();
             }
-            (void)label;
         }
         if (per_cluster) per_cluster->push_back(std::move(code));
     }
@@ -406,6 +442,8 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
             if (c >= 0) death[id] = std::max(death[id], c);
         }
     }
+    for (int ci = 0; ci < nc; ++ci)  // producers evaluated inside this cluster's operand loaders: their inputs live until here
+        for (int id : codes[ci].extra_reads) death[id] = std::max(death[id], ci);
     std::vector<int64_t> scratch_offset(nc, 0);
     std::vector<std::vector<int>> dying_at(nc + 1);
     for (int ci = 0; ci < nc; ++ci) {
@@ -413,6 +451,7 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
         if (ci > 0)
             for (int id : dying_at[ci - 1]) arena.release(storage[id].offset, ops.nodes[id].shape.buffer_size());
         for (int out : clusters[ci].outputs) {
+            if (codes[ci].skipped) continue;  // computed on the fly by its consumers: never in memory
             if (alias[out] >= 0) {
                 storage[out] = storage[alias[out]];
                 continue;

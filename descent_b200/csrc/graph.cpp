@@ -1066,6 +1066,49 @@ void Graph::build_clusters() {
     }
     for (auto& node : ops_.nodes)
         if (node.alive && node.cluster_id >= 0) node.cluster_id = new_index[node.cluster_id];
+    find_operand_prologues();
+}
+
+// See OperandPrologue (graph.hpp).  Candidates: ungrouped per-element clusters with one output X, a straight-line
+// program without Gather / built-ins, where every reader of X is a MatMul cluster that takes X as its A or B operand
+// (its absorbed bias column sums, which read X inside the same cluster, included).
+void Graph::find_operand_prologues() {
+    operand_prologues_.clear();
+    auto cons = ops_.consumers();
+    std::set<int> written_parameters;  // a parameter the step overwrites may change between the producer's slot and the GEMM's
+    for (int id : output_nodes()) written_parameters.insert(ops_.nodes[id].op.parameter_id);
+    for (int pi = 0; pi < (int)clusters_.size(); ++pi) {
+        const Cluster& p = clusters_[pi];
+        if (p.kind != ClusterKind::PerElement || !p.group.empty() || p.outputs.size() != 1 || p.element_count < (1 << 16)) continue;
+        bool ok = true;
+        for (const auto& op : p.ops)
+            if (op.kind == PerElementOp::Gather || op.kind == PerElementOp::BuiltIn) ok = false;
+        for (const auto& in : p.inputs) {
+            const OpNode& src = ops_.nodes[in.node_id];
+            if (src.op.kind == OpKind::Input && written_parameters.count(src.op.parameter_id)) ok = false;
+        }
+        const int x = p.outputs[0];
+        OperandPrologue cand;
+        cand.producer = pi;
+        for (auto [dst, k] : cons[x]) {
+            (void)k;
+            const OpNode& d = ops_.nodes[dst];
+            if (!d.alive) continue;
+            if (d.op.kind == OpKind::Output || d.cluster_id < 0 || d.cluster_id == pi) { ok = false; break; }
+            const Cluster& mc = clusters_[d.cluster_id];
+            if (mc.kind != ClusterKind::MatMul || !mc.epilogue.empty()) { ok = false; break; }
+            bool as_operand = false;
+            for (int operand = 0; operand < 2; ++operand) {
+                if (mc.inputs[operand].node_id != x) continue;
+                as_operand = true;
+                bool seen = false;
+                for (const auto& u : cand.uses) seen |= u.cluster == d.cluster_id && u.operand == operand;
+                if (!seen) cand.uses.push_back({d.cluster_id, operand});
+            }
+            if (!as_operand) { ok = false; break; }  // read by the cluster in some other role only
+        }
+        if (ok && !cand.uses.empty()) operand_prologues_.push_back(cand);
+    }
 }
 
 void Graph::write_dot_file(KernelDotOutput mode, const std::string& path) const {

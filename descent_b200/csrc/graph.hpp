@@ -86,12 +86,25 @@ struct Cluster {
     std::string label;                 // as the reference's Kernel::label_name (kernel.rs)
 };
 
+// A per-element cluster whose single result is needed only as an operand of MatMul clusters (conv2d's backward pass:
+// dY = max-pool backward o activation backward feeds the weight-gradient GEMM, its bias column sums and the
+// backward-input GEMM and nothing else).  The code generator may evaluate that cluster's program inside the GEMMs'
+// operand loaders instead of running it as a kernel: the array is then never written or read back.  The decision is
+// the code generator's (it depends on which GEMM kernels the options select, environment.cpp generate_graph_source);
+// the graph only records who could.
+struct OperandPrologue {
+    int producer = -1;  // index of the per-element cluster
+    struct Use { int cluster; int operand; };  // MatMul cluster index, 0 = A / 1 = B
+    std::vector<Use> uses;
+};
+
 class Graph {
 public:
     Graph(SharedParameters parameters, const OpGraph& ops, DataParallel dp);
 
     const OpGraph& ops() const { return ops_; }
     const std::vector<Cluster>& clusters() const { return clusters_; }  // already in execution order
+    const std::vector<OperandPrologue>& operand_prologues() const { return operand_prologues_; }
     const SharedParameters& parameters() const { return parameters_; }
     const DataParallel& dp() const { return dp_; }
     std::vector<int> input_nodes() const;
@@ -120,11 +133,13 @@ private:
     bool absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
     void build_clusters();
     void build_per_element_program(Cluster& c);
+    void find_operand_prologues();
 
     SharedParameters parameters_;
     OpGraph ops_;
     DataParallel dp_;
     std::vector<Cluster> clusters_;
+    std::vector<OperandPrologue> operand_prologues_;
 };
 
 std::string export_ops_json(const OpGraph& ops, const std::vector<ParameterStorage>& parameters, const std::vector<Cluster>* clusters);
