@@ -736,6 +736,7 @@ const char* kMatMulTemplate = R"(
 #include "gemm_tc_template.inc"
 #include "gemm_tc_async_template.inc"
 #include "halo_conv_template.inc"
+#include "halo_conv_pipelined_template.inc"
 #include "thin_gemm_template.inc"
 #include "halo_wgrad_template.inc"
 
@@ -949,6 +950,16 @@ void bind_operand_loads(KernelLaunch& l, ClusterCode* code, const OperandLoad* a
 }
 
 // ---- stride-1 convolutions as halo-tiled implicit GEMMs (halo_conv_template.inc) ---------------------
+// measurement hooks (environment variables, read once): CTAs per SM of the halo kernels, ring depth of the pipelined form
+// (0 = use the one-tile-at-a-time form)
+int halo_ctas_per_sm() {
+    static const int v = [] { const char* e = std::getenv("DSC_HALO_CTAS"); return e ? std::atoi(e) : 5; }();
+    return v;
+}
+int halo_pipeline_stages() {
+    static const int v = [] { const char* e = std::getenv("DSC_HALO_STAGES"); return e ? std::atoi(e) : 2; }();
+    return v;
+}
 struct HaloConv {
     bool backward_input = false;
     int64_t groups, images, out_h, out_w, filter_h, filter_w;
@@ -1014,12 +1025,97 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
         else out_index << "((size_t)g * " << M << " + (image * ROWS + y) * " << OW << " + x) * NG";
     }
     const std::string name = "k" + num(ci);
+    // CTAs per SM: shared memory, TMEM columns and registers all bound it.  The kernel needs ~50 registers; asking the
+    // compiler for 5 CTAs (48 registers) keeps the persistent grid a single wave (7 were assumed from shared memory alone in
+    // round 1 while the register file admitted 4: 1.75 waves, a quarter of the SM time idle in the tail).
+    const int64_t resident = std::max<int64_t>(1, std::min<int64_t>({(int64_t)halo_ctas_per_sm(), (200 * 1024) / smem, 512 / tmem_cols}));
     if (!c.epilogue.empty() && (h.backward_input || !h.rows_mode || G * NG % 4 != 0)) return false;
     if (prologue_requested(1)) return false;  // the weights are staged once per CTA, element by element: no producer there
     const EpilogueCode epi = gen_epilogue(g, c, name, opt);
+    const int64_t out_pixels = h.images * (rows - 2 * h.unpad_h) * ((h.backward_input ? W : OW) - 2 * h.unpad_w);
+
+    // The software-pipelined form (halo_conv_pipelined_template.inc) addresses the operand through per-axis tables:
+    // evaluate the chain for every (row, column, channel chunk) of the halo grid and check that the source index is
+    // image * stride + ytab[py] + xtab[px] + ctab[q] -- true whenever padding, windows and group slices act per axis.
+    // Measured on B200 (conv-net m = 8192, profiles/r2_halo_pipeline.md): forward 110 -> 103 us with a 2-deep ring at 4 CTAs per
+    // SM.  Backward-input is paced by the tensor core's operand reads from shared memory (36 MMAs x 4 KB of A per 128 pixels:
+    // the im2col expansion is read from shared memory whichever way the loads arrive), so it only loses the CTAs the ring's
+    // shared memory costs (133 us at 5 CTAs with the one-tile form; 144 / 170 / 291 us at 3 / 2 / 1 CTAs with the ring):
+    // it keeps the first form unless DSC_HALO_PIPELINE_BACKWARD=1.
+    static const bool pipeline_backward = [] { const char* e = std::getenv("DSC_HALO_PIPELINE_BACKWARD"); return e && std::atoi(e) != 0; }();
+    const int64_t stages = halo_pipeline_stages();
+    if (stages >= 2 && !prologue_requested(0) && (!h.backward_input || pipeline_backward)) {
+        const int64_t tiles_per_image = div_round_up(rows, TH), YT = tiles_per_image * TH + FH - 1;
+        auto src_index = [&](int64_t image, int64_t py, int64_t px, int64_t q) -> int64_t {
+            const int64_t batch = (q * 4) / KG, kin = (q * 4) % KG;
+            int64_t gm, gk;
+            if (h.backward_input) {
+                const int64_t oy = py - (FH - 1);
+                if (!(px < OW && oy >= 0 && oy < OH)) return -1;
+                gk = kin;
+                gm = (image * OH + oy) * OW + px;
+            } else {
+                if (py >= PH) return -1;
+                const int64_t fy = std::max<int64_t>(py - (OH - 1), 0), fx = std::max<int64_t>(px - (OW - 1), 0);
+                gk = (fy * FW + fx) * KG + kin;
+                gm = (image * OH + py - fy) * OW + px - fx;
+            }
+            return eval_chain(a.chain, batch * M * K + gm * K + gk);
+        };
+        const int64_t py0 = h.backward_input ? FH - 1 : 0;
+        const int64_t origin = src_index(0, py0, 0, 0);
+        const int64_t image_stride = h.images > 1 ? src_index(1, py0, 0, 0) - origin : 0;
+        std::vector<int64_t> ytab(YT), xtab(W), ctab(Q);
+        for (int64_t py = 0; py < YT; ++py) ytab[py] = src_index(0, py, 0, 0);
+        for (int64_t px = 0; px < W; ++px) { const int64_t v = src_index(0, py0, px, 0); xtab[px] = v < 0 ? -1 : v - origin; }
+        for (int64_t q = 0; q < Q; ++q) ctab[q] = src_index(0, py0, 0, q) - origin;
+        bool separable = origin >= 0;
+        for (int64_t image : {(int64_t)0, std::min<int64_t>(1, h.images - 1), h.images - 1})
+            for (int64_t py = 0; py < YT && separable; ++py)
+                for (int64_t px = 0; px < W && separable; ++px)
+                    for (int64_t q = 0; q < Q; ++q) {
+                        const int64_t want = src_index(image, py, px, q);
+                        const int64_t got = (ytab[py] < 0 || xtab[px] < 0) ? -1 : image * image_stride + ytab[py] + xtab[px] + ctab[q];
+                        if (want != got || (want >= 0 && want % 4 != 0)) { separable = false; break; }
+                    }
+        int64_t acc_cols = 32;
+        while (acc_cols < G * BN) acc_cols *= 2;
+        const int64_t a_stage = div_round_up(Q * npix * 16, 128) * 128;
+        const int64_t so_bytes = (unpad || stage_out) ? 128 * (G * NG + 4) * 4 : 0;
+        const int64_t smem2 = stages * a_stage + b_bytes + so_bytes + 64 + YT * 4 + 128;
+        if (separable && 2 * acc_cols <= 512 && smem2 <= 200 * 1024) {
+            const int64_t resident2 = std::max<int64_t>(1, std::min<int64_t>({(int64_t)halo_ctas_per_sm(), (220 * 1024) / (smem2 + 1024), 512 / (2 * acc_cols)}));
+            auto list = [](const std::vector<int64_t>& v) {
+                std::string t;
+                for (size_t i = 0; i < v.size(); ++i) t += (i ? ", " : "") + num(v[i]);
+                return t;
+            };
+            out->source = subst(kHaloConvPipelinedTemplate,
+                                {{"LABEL", c.label}, {"MIN_CTAS", num(resident2)}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args},
+                                 {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)}, {"FW", num(FW)}, {"KG", num(KG)},
+                                 {"NG", num(NG)}, {"BN", num(BN)}, {"LEAD", num(lead)}, {"TMEM_COLS", num(2 * acc_cols)}, {"NPIX", num(npix)}, {"STAGES", num(stages)},
+                                 {"PY", num(h.unpad_h)}, {"PX", num(h.unpad_w)}, {"STAGE_OUT", stage_out ? "true" : "false"}, {"OUT_W", num(OW)},
+                                 {"ROWS_FIRST", h.unpad_rows_first ? "true" : "false"}, {"YT", num(YT)}, {"YTAB", list(ytab)}, {"XTAB", list(xtab)}, {"CTAB", list(ctab)},
+                                 {"IMG_STRIDE", num(image_stride)}, {"B_COORDS", b_coords.str()}, {"TAP_PIXEL", tap_pixel.str()}, {"OUT_OK", out_ok.str()},
+                                 {"OUT_INDEX", out_index.str()}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
+            KernelLaunch l;
+            l.entry = name;
+            l.grid_x = (uint32_t)std::min<int64_t>(tiles, (int64_t)opt.sm_count * resident2);  // persistent over tiles: exactly one wave
+            l.block = 256;
+            l.smem = (uint32_t)smem2;
+            l.label = "TensorCore" + c.label;
+            l.cluster = ci;
+            l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+            l.args.insert(l.args.end(), epi.launch_args.begin(), epi.launch_args.end());
+            l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(out_pixels * G * NG) : epi.bytes);
+            l.flops = 2.0 * (double)(out_pixels * G * NG) * (double)(FH * FW * KG);
+            out->launches.push_back(l);
+            return true;
+        }
+    }
     const OperandLoad la = operand_load(g, 0, name, a, opt);
     out->source = subst(kHaloConvTemplate,
-                        {{"LABEL", c.label + (la.fused ? "  [A = " + g_prologue->producer[0]->label + "]" : "")}, {"PRO_FUNCS", la.funcs}, {"PRO_PARAMS", la.params}, {"A_LOAD4", la.load4(ia)}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args}, {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)},
+                        {{"LABEL", c.label + (la.fused ? "  [A = " + g_prologue->producer[0]->label + "]" : "")}, {"PRO_FUNCS", la.funcs}, {"PRO_PARAMS", la.params}, {"A_LOAD4", la.load4(ia)}, {"MIN_CTAS", num(resident)}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args}, {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)},
                          {"FW", num(FW)}, {"KG", num(KG)}, {"NG", num(NG)}, {"BN", num(BN)}, {"LEAD", num(lead)}, {"TMEM_COLS", num(tmem_cols)}, {"NPIX", num(npix)},
                          {"PY", num(h.unpad_h)}, {"PX", num(h.unpad_w)}, {"STAGE_OUT", stage_out ? "true" : "false"}, {"OUT_W", num(OW)},
                          // loading the next halo before the drain pays for the forward kernel (0.125 -> 0.117 ms) and costs the
@@ -1029,8 +1125,7 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
                          {"OUT_INDEX", out_index.str()}, {"A_CHAIN", ca.str()}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
     KernelLaunch l;
     l.entry = name;
-    const int64_t resident = std::max<int64_t>(1, std::min<int64_t>({8, (200 * 1024) / smem, 512 / tmem_cols}));
-    l.grid_x = (uint32_t)std::min<int64_t>(tiles, (int64_t)opt.sm_count * resident);  // persistent over tiles
+    l.grid_x = (uint32_t)std::min<int64_t>(tiles, (int64_t)opt.sm_count * resident);  // persistent over tiles: exactly one wave
     l.block = 256;
     l.smem = (uint32_t)smem;
     l.label = "TensorCore" + c.label;
@@ -1038,7 +1133,6 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
     l.args.insert(l.args.end(), epi.launch_args.begin(), epi.launch_args.end());
     bind_operand_loads(l, out, &la, nullptr);
-    const int64_t out_pixels = h.images * (rows - 2 * h.unpad_h) * ((h.backward_input ? W : OW) - 2 * h.unpad_w);
     l.algorithmic_bytes = la.bytes + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(out_pixels * G * NG) : epi.bytes);
     l.flops = 2.0 * (double)(out_pixels * G * NG) * (double)(FH * FW * KG);
     out->launches.push_back(l);
