@@ -183,6 +183,7 @@ struct ResolvedLaunch {
     size_t bytes = 0;  // ZeroScratch / Copy bytes, AllReduce element count
     uint32_t fill_bits = 0;
     bool is_copy = false, is_fill = false;
+    bool async_collective = false, join_collectives = false;  // AllReduce: on the side stream / wait for the side stream first
     std::string label, entry;
     int cluster = -1;
     double algorithmic_bytes = 0, flops = 0;
@@ -417,6 +418,10 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
     ArenaAllocator arena;
     std::vector<int> bucket_nodes;
     int64_t bucket_bytes = 0;
+    // clusters are in level order, and the graph pins AllReduce nodes to at most two levels (graph.cpp build_clusters):
+    // each level is one contiguous range of the bucket = one collective
+    struct BucketRange { int level; int64_t begin, end; };
+    std::vector<BucketRange> bucket_ranges;
     for (int ci = 0; ci < nc; ++ci) {
         if (clusters[ci].kind != ClusterKind::AllReduce) continue;
         const int a = clusters[ci].outputs[0], x = clusters[ci].inputs[0].node_id;
@@ -425,7 +430,9 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
         storage[x] = {Storage::Arena, -1, bucket_bytes};
         alias[a] = x;
         bucket_nodes.push_back(x);
+        if (bucket_ranges.empty() || bucket_ranges.back().level != clusters[ci].level) bucket_ranges.push_back({clusters[ci].level, bucket_bytes, bucket_bytes});
         bucket_bytes += align_up(ops.nodes[x].shape.buffer_size(), 16);
+        bucket_ranges.back().end = bucket_bytes;
     }
     if (bucket_bytes) arena.top = align_up(bucket_bytes);
 
@@ -502,7 +509,8 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
         exec.launches.push_back(r);
     };
     for (const auto& eo : begin_ops) add_copy_or_fill(eo);
-    bool bucket_done = false;
+    size_t buckets_emitted = 0;
+    int last_bucket_level = -1;
     for (int ci = 0; ci < nc; ++ci) {
         for (const KernelLaunch& l : codes[ci].launches) {
             ResolvedLaunch r;
@@ -516,11 +524,17 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
                 r.ptr = exec.arena + (uint64_t)(scratch_offset[ci] + l.zero_offset);
                 r.bytes = (size_t)l.zero_bytes;
             } else if (l.kind == KernelLaunch::AllReduce) {
-                if (bucket_done) continue;
-                bucket_done = true;
-                r.ptr = exec.arena;
-                r.bytes = (size_t)(bucket_bytes / 4);
-                r.label = "AllReduce bucket [" + std::to_string(bucket_bytes / 4) + "]";
+                if (clusters[ci].level == last_bucket_level) continue;  // one collective per level: emitted at its first cluster
+                last_bucket_level = clusters[ci].level;
+                const BucketRange& range = bucket_ranges.at(buckets_emitted++);
+                DSC_CHECK(range.level == clusters[ci].level, "gradient bucket ranges out of step with the cluster order");
+                r.ptr = exec.arena + (uint64_t)range.begin;
+                r.bytes = (size_t)((range.end - range.begin) / 4);
+                // every bucket but the last runs on the side stream under the rest of the backward pass; the last one
+                // first joins the side stream, so whatever follows it sees all gradients reduced
+                r.async_collective = buckets_emitted < bucket_ranges.size();
+                r.join_collectives = !r.async_collective;
+                r.label = std::string(r.async_collective ? "AllReduce early bucket [" : "AllReduce bucket [") + std::to_string(r.bytes) + "]";
             } else if (l.kind == KernelLaunch::TensorGemm) {
                 for (const auto& a : l.args)
                     r.buffers.push_back(a.kind == KernelArg::NodeBuffer ? device_address(a.node_id)
@@ -566,7 +580,11 @@ void Environment::launch_all(GraphExec& exec, std::vector<float>* per_launch_ms)
         if (r.is_copy) check(dsc_copy(ctx_, r.ptr, r.src, r.bytes));
         else if (r.is_fill) check(dsc_fill_u32(ctx_, r.ptr, 0, r.fill_bits, r.bytes / 4));
         else if (r.kind == KernelLaunch::ZeroScratch) check(dsc_fill_u32(ctx_, r.ptr, 0, 0, r.bytes / 4));
-        else if (r.kind == KernelLaunch::AllReduce) check(dsc_dp_allreduce_sum_f32(ctx_, r.ptr, r.bytes));
+        else if (r.kind == KernelLaunch::AllReduce) {
+            if (r.join_collectives) check(dsc_dp_allreduce_join(ctx_));
+            if (r.async_collective) check(dsc_dp_allreduce_sum_f32_async(ctx_, r.ptr, r.bytes));
+            else check(dsc_dp_allreduce_sum_f32(ctx_, r.ptr, r.bytes));
+        }
         else if (r.kind == KernelLaunch::TensorGemm)
             check(dsc_gemm_tf32_split_k(ctx_, r.buffers[0], r.buffers[1], r.buffers[2], r.gemm_m, r.gemm_n, r.gemm_k, r.gemm_a_is_mk, r.gemm_b_is_kn, r.gemm_splits));
         else check(dsc_launch(ctx_, r.kernel, r.gx, r.gy, r.gz, r.block, r.smem, r.buffers.data(), (int)r.buffers.size()));

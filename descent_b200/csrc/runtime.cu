@@ -144,6 +144,9 @@ struct dsc_ctx {
     cudaEvent_t staged_read = nullptr;    // recorded on stream after a commit read the staging buffer
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
+    cudaStream_t comm_stream = nullptr;   // early gradient bucket: all-reduced here while the backward pass continues on `stream`
+    cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
+    bool comm_pending = false;
     bool capturing = false;
 };
 struct dsc_module {
@@ -188,6 +191,9 @@ int dsc_ctx_create(int device, dsc_ctx** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->prefetch_done, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->staged_read, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->comm_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->comm_join, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;  // keep freed memory cached in the pool: alloc/free cost no driver calls
@@ -215,6 +221,10 @@ int dsc_ctx_destroy(dsc_ctx* ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaEventDestroy(ctx->prefetch_done);
     cudaEventDestroy(ctx->staged_read);
+    cudaStreamSynchronize(ctx->comm_stream);
+    cudaEventDestroy(ctx->comm_fork);
+    cudaEventDestroy(ctx->comm_join);
+    cudaStreamDestroy(ctx->comm_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -494,6 +504,27 @@ int dsc_dp_allreduce_sum_f32(dsc_ctx* ctx, uint64_t id, size_t count) {
     if (!ctx->comm) return set_error(DSC_ERR_NCCL, "data-parallel communicator not initialised");
     CUDA_TRY(cudaSetDevice(ctx->device));
     NCCL_TRY(g_nccl.AllReduce((const void*)id, (void*)id, count, ncclFloat32, ncclSum, ctx->comm, ctx->stream));
+    return DSC_OK;
+}
+// The same all-reduce on the context's side stream: it starts once everything issued so far on the context's stream has
+// finished and runs beside whatever is issued next; dsc_dp_allreduce_join makes the context's stream wait for it.
+// Both are capturable: inside dsc_graph_begin_capture / end_capture they become a fork and a join of the CUDA graph.
+int dsc_dp_allreduce_sum_f32_async(dsc_ctx* ctx, uint64_t id, size_t count) {
+    if (ctx->world == 1 || count == 0) return DSC_OK;
+    if (!ctx->comm) return set_error(DSC_ERR_NCCL, "data-parallel communicator not initialised");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaEventRecord(ctx->comm_fork, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_fork, 0));
+    NCCL_TRY(g_nccl.AllReduce((const void*)id, (void*)id, count, ncclFloat32, ncclSum, ctx->comm, ctx->comm_stream));
+    CUDA_TRY(cudaEventRecord(ctx->comm_join, ctx->comm_stream));
+    ctx->comm_pending = true;
+    return DSC_OK;
+}
+int dsc_dp_allreduce_join(dsc_ctx* ctx) {
+    if (!ctx->comm_pending) return DSC_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->comm_join, 0));
+    ctx->comm_pending = false;
     return DSC_OK;
 }
 int dsc_dp_world(dsc_ctx* ctx, int* world, int* rank) {

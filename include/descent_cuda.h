@@ -121,6 +121,9 @@ int dsc_gemm_tf32_split_k(dsc_ctx* ctx, uint64_t a, uint64_t b, uint64_t c, int6
 int dsc_dp_unique_id(void* out128);                                  /* ncclGetUniqueId; 128 bytes */
 int dsc_dp_init(dsc_ctx* ctx, const void* unique_id128, int world, int rank);
 int dsc_dp_allreduce_sum_f32(dsc_ctx* ctx, uint64_t id, size_t count); /* in place, on the context's stream */
+/* the same on a side stream behind the work issued so far; the context's stream continues and waits at the join (both capturable) */
+int dsc_dp_allreduce_sum_f32_async(dsc_ctx* ctx, uint64_t id, size_t count);
+int dsc_dp_allreduce_join(dsc_ctx* ctx);
 int dsc_dp_world(dsc_ctx* ctx, int* world, int* rank);
 
 #ifdef __cplusplus

@@ -193,17 +193,14 @@ def test_invalid_shapes_are_errors_not_crashes(host_env):
 
 def test_conv_backward_producers_are_evaluated_inside_the_gemm_loaders(built_library, host_env):
     """Operand prologues (graph.hpp OperandPrologue): max-pool backward o leaky-relu backward, the per-element kernel
-    that used to write dY for each convolution (reference: select_eq + leaky backward clusters, array.rs:1049-1059), is
-    evaluated inside the operand loaders of the weight-gradient and backward-input GEMMs when their kernels support it;
-    the [m, 28, 28, 16] and [m, 14, 14, 32] gradient arrays are then never written.  With TF32 off the second
-    convolution's GEMMs run on the generic SIMT kernel, whose bias column sums read dY from memory: that producer stays
-    a kernel (the decision is per producer and all-or-nothing)."""
+    that writes dY of the first convolution (reference: select_eq + leaky backward clusters, array.rs:1049-1059), has
+    one consumer -- the weight-gradient GEMM with its bias column sums -- and is evaluated inside that kernel's operand
+    loader: the [m, 28, 28, 16] gradient array is never written.  The second convolution's dY feeds two GEMMs (weight
+    gradient and backward-input); evaluating it twice measured slower, so it stays a kernel (graph.cpp)."""
     ex = host_env.example("conv-net", 1024)
-    tf32 = ex.train_graph.kernel_source(tf32=True)
-    assert tf32.count("computed while loading: PerElement (9 ops) [12845056]") == 1   # conv1 dY -> thin weight-gradient kernel
-    assert tf32.count("computed while loading: PerElement (9 ops) [6422528]") == 2    # conv2 dY -> halo weight gradient + halo backward-input
-    assert "\n// PerElement (9 ops) [12845056]\n" not in tf32 and "\n// PerElement (9 ops) [6422528]\n" not in tf32
-    strict = ex.train_graph.kernel_source(tf32=False)
-    assert strict.count("computed while loading: PerElement (9 ops) [12845056]") == 1
-    assert "\n// PerElement (9 ops) [6422528]\n" in strict and "computed while loading: PerElement (9 ops) [6422528]" not in strict
-    assert built_library.nvrtc_compile(tf32) > 0 and built_library.nvrtc_compile(strict) > 0
+    for tf32 in (True, False):
+        source = ex.train_graph.kernel_source(tf32=tf32)
+        assert source.count("computed while loading: PerElement (9 ops) [12845056]") == 1   # conv1 dY -> thin weight-gradient kernel
+        assert "\n// PerElement (9 ops) [12845056]\n" not in source
+        assert "\n// PerElement (9 ops) [6422528]\n" in source and "computed while loading: PerElement (9 ops) [6422528]" not in source
+        assert built_library.nvrtc_compile(source) > 0

@@ -19,6 +19,7 @@ from oracle import run_graph
 pytestmark = pytest.mark.gpu
 TF32_LOSS_TOL = 2e-3  # measured 3.2e-4
 TF32_PARAM_TOL = 1.5e-1  # measured 1.4e-2 .. 5.3e-2 (Adam steps of near-zero gradients flip sign)
+CONV_NET_TF32_PARAM_TOL = 1.5e-1  # conv-net, 100 steps: calibrated below
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -115,3 +116,41 @@ def test_tf32_view_chain_gemms_match_tf32_oracle(env, network, m, tol):
     print(network, worst)
     assert max(worst.values()) <= tol, worst
     assert abs(env.read_parameter_scalar(ex.loss_sum) - float(want[ex.loss_sum.id][0])) <= 1e-5 * abs(float(want[ex.loss_sum.id][0]))
+
+
+def test_tf32_conv_net_100_steps_within_stated_tolerance(env):
+    """BASELINE.json: "within a stated TF32 tolerance on loss and parameters after N steps for tensor-core GEMMs", stated on
+    the headline network.  N = 100 Adam steps of conv-net at m = 256 (fresh synthetic batch and dropout seed every step)
+    on the tensor-core path, against the STRICT oracle (oracle.cpu_ref: float32 sums like the reference's kernels) fed the
+    same batches and seeds.  Tolerances (measured values are printed):
+      * accumulated loss over the 100 steps: 2e-3 relative (SURVEY.md section 8d proposal);
+      * every parameter tensor: CONV_NET_TF32_PARAM_TOL * max|theta|.  Adam normalises each step to ~lr whatever the
+        gradient's size, so an entry whose gradient is a cancellation residue moves by +-lr per step in either
+        implementation: after 100 steps of lr = 0.005 the two trajectories may differ by a sizeable fraction of 100 * lr on
+        such entries while the loss agrees to 1e-3 -- which is why the bound is stated relative to max|theta| and is not 5e-3."""
+    from oracle import cpu_ref
+    env.set_tf32(True)
+    m, steps = 256, 100
+    ex = env.example("conv-net", m)
+    rng = np.random.default_rng(77)
+    params = init_example_params(ex, rng)
+    upload(env, params)
+    program = cpu_ref.Program(ex.train_graph_json)
+    state = {pid: np.ascontiguousarray(v, np.float32) for pid, v in params.items()}
+    for step in range(steps):
+        x, y = synthetic_batch(ex, rng)
+        seed = int(rng.integers(0, 2 ** 32))
+        env.write(ex.x, x)
+        env.write(ex.y, y)
+        env.run(ex.train_graph, seed)
+        state[ex.x.id], state[ex.y.id] = x, y
+        out, _ = program.run(state, seed)
+        state.update({pid: v.copy() for pid, v in out.items()})
+    program.close()
+    got, want = env.read_parameter_scalar(ex.loss_sum), float(state[ex.loss_sum.id].reshape(-1)[0])
+    drift = {p.name() + "#%d" % p.id: max_rel_err(env.read(p), state[p.id]) for p in ex.parameters}
+    acc_got, acc_want = env.read_parameter_scalar(ex.accuracy_sum), float(state[ex.accuracy_sum.id].reshape(-1)[0])
+    print("conv-net tf32 vs strict oracle after %d steps: loss %.6g vs %.6g (rel %.3g), accuracy sum %g vs %g, parameter drift / max|theta| %s"
+          % (steps, got, want, abs(got - want) / abs(want), acc_got, acc_want, {k: "%.3g" % v for k, v in drift.items()}))
+    assert abs(got - want) <= TF32_LOSS_TOL * abs(want), (got, want)
+    assert max(drift.values()) <= CONV_NET_TF32_PARAM_TOL, drift
