@@ -6,6 +6,7 @@
 #include "codegen.hpp"
 
 #include <cmath>
+#include <functional>
 #include <map>
 #include <cstdlib>
 #include <cstdio>
@@ -220,6 +221,47 @@ double chain_bytes(const Graph& g, const ClusterInput& in) {
 
 // ---- per-element (reference: PerElementKernel, kernel.rs:195-383) -------------------------------
 
+// The value of a Unary / Binary / Select op as a CUDA expression; A(k) names argument k (kernel.rs:281-333 semantics:
+// IEEE f32 per-element ops, u32 ops on the raw bits).
+std::string op_expression(const PerElementOp& op, const std::function<std::string(int)>& A) {
+    std::ostringstream os;
+    switch (op.kind) {
+        case PerElementOp::Unary:
+            switch (op.op.unary) {
+                case UnaryOp::Mov: os << A(0); break;
+                case UnaryOp::Neg: os << "-" << A(0); break;
+                case UnaryOp::Sqrt: os << "sqrtf(" << A(0) << ")"; break;
+                case UnaryOp::Exp: os << "expf(" << A(0) << ")"; break;
+                case UnaryOp::Log: os << "logf(" << A(0) << ")"; break;
+                case UnaryOp::Sin: os << "sinf(" << A(0) << ")"; break;
+                case UnaryOp::Cos: os << "cosf(" << A(0) << ")"; break;
+                case UnaryOp::UintToFloat: os << "__uint2float_rn(__float_as_uint(" << A(0) << "))"; break;
+                case UnaryOp::FloatToUint: os << "__uint_as_float(__float2uint_rz(" << A(0) << "))"; break;
+            }
+            break;
+        case PerElementOp::Binary: {
+            auto U = [&](const char* o) { os << "__uint_as_float(__float_as_uint(" << A(0) << ") " << o << " __float_as_uint(" << A(1) << "))"; };
+            switch (op.op.binary) {
+                case BinaryOp::Add: os << A(0) << " + " << A(1); break;
+                case BinaryOp::Sub: os << A(0) << " - " << A(1); break;
+                case BinaryOp::Mul: os << A(0) << " * " << A(1); break;
+                case BinaryOp::Div: os << A(0) << " / " << A(1); break;
+                case BinaryOp::Pow: os << "powf(" << A(0) << ", " << A(1) << ")"; break;
+                case BinaryOp::UAdd: U("+"); break;
+                case BinaryOp::UMul: U("*"); break;
+                case BinaryOp::URem: U("%"); break;
+                case BinaryOp::UBitXor: U("^"); break;
+            }
+            break;
+        }
+        case PerElementOp::Select:
+            os << "(" << A(0) << (op.op.compare == CompareMode::Eq ? " == " : " > ") << A(1) << ") ? " << A(2) << " : " << A(3);
+            break;
+        default: fail("not an expression op");
+    }
+    return os.str();
+}
+
 // The straight-line program of a per-element cluster for element `e` (statements `const float t<i> = ...;`).
 // Inputs flagged in `vector_load` were fetched as `vin<i>[v]`; input `register_input` (if >= 0) is not in memory
 // at all: its value for this element is `acc[v]` (a GEMM epilogue evaluating the cluster on its accumulator).
@@ -228,7 +270,7 @@ void emit_per_element_ops(std::ostringstream& os, const Cluster& c, const Codege
     for (size_t oi = 0; oi < c.ops.size(); ++oi) {
         const PerElementOp& op = c.ops[oi];
         const std::string t = "t" + num(oi);
-        auto A = [&](int k) { return "t" + num(op.args[k]); };
+        std::function<std::string(int)> A = [&](int k) { return "t" + num(op.args[k]); };
         switch (op.kind) {
             case PerElementOp::Load: {
                 const auto& in = c.inputs[op.input_index];
@@ -258,43 +300,12 @@ void emit_per_element_ops(std::ostringstream& os, const Cluster& c, const Codege
                 }
                 break;
             }
-            case PerElementOp::Unary: {
-                os << "    const float " << t << " = ";
-                switch (op.op.unary) {
-                    case UnaryOp::Mov: os << A(0); break;
-                    case UnaryOp::Neg: os << "-" << A(0); break;
-                    case UnaryOp::Sqrt: os << "sqrtf(" << A(0) << ")"; break;
-                    case UnaryOp::Exp: os << "expf(" << A(0) << ")"; break;
-                    case UnaryOp::Log: os << "logf(" << A(0) << ")"; break;
-                    case UnaryOp::Sin: os << "sinf(" << A(0) << ")"; break;
-                    case UnaryOp::Cos: os << "cosf(" << A(0) << ")"; break;
-                    case UnaryOp::UintToFloat: os << "__uint2float_rn(__float_as_uint(" << A(0) << "))"; break;
-                    case UnaryOp::FloatToUint: os << "__uint_as_float(__float2uint_rz(" << A(0) << "))"; break;
-                }
-                os << ";\n";
-                break;
-            }
-            case PerElementOp::Binary: {
-                os << "    const float " << t << " = ";
-                auto U = [&](const char* o) { os << "__uint_as_float(__float_as_uint(" << A(0) << ") " << o << " __float_as_uint(" << A(1) << "))"; };
-                switch (op.op.binary) {
-                    case BinaryOp::Add: os << A(0) << " + " << A(1); break;
-                    case BinaryOp::Sub: os << A(0) << " - " << A(1); break;
-                    case BinaryOp::Mul: os << A(0) << " * " << A(1); break;
-                    case BinaryOp::Div: os << A(0) << " / " << A(1); break;
-                    case BinaryOp::Pow: os << "powf(" << A(0) << ", " << A(1) << ")"; break;
-                    case BinaryOp::UAdd: U("+"); break;
-                    case BinaryOp::UMul: U("*"); break;
-                    case BinaryOp::URem: U("%"); break;
-                    case BinaryOp::UBitXor: U("^"); break;
-                }
-                os << ";\n";
-                break;
-            }
+            case PerElementOp::Unary:
+            case PerElementOp::Binary:
             case PerElementOp::Select:
-                os << "    const float " << t << " = (" << A(0) << (op.op.compare == CompareMode::Eq ? " == " : " > ") << A(1) << ") ? " << A(2)
-                   << " : " << A(3) << ";\n";
+                os << "    const float " << t << " = " << op_expression(op, A) << ";\n";
                 break;
+            case PerElementOp::Reduce: fail("reductions only appear in row clusters");
             case PerElementOp::Gather: {
                 // out[.., i, ..] = values[.., F2I(index[i]), ..]  (kernel.rs:336-351)
                 const int axis = op.op.axis;
@@ -398,6 +409,97 @@ ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const Code
     else account(c);
     for (const auto& in : c.inputs) l.args.push_back({KernelArg::NodeBuffer, in.node_id, 0});
     for (int out : c.outputs) l.args.push_back({KernelArg::NodeBuffer, out, 0});
+    code.launches.push_back(l);
+    return code;
+}
+
+// ---- row clusters (graph.cpp fuse_rows): softmax cross-entropy & co as one kernel ---------------------
+// One thread per row.  A wide op is an unrolled loop over the row's K elements writing a register array, a narrow op a
+// scalar, a reduction a sequential loop in ascending k (the order of the reference's ReduceKernel).  Operands from
+// outside keep their view chains (element index r * K + k for wide values, r for narrow ones).
+ClusterCode gen_row(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
+    const int64_t R = c.rows, K = c.row_length;
+    std::ostringstream os;
+    const std::string name = "k" + num(ci);
+    os << "// " << c.label << "  [one thread per row, row in registers]\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(128) " << name << "(";
+    for (size_t i = 0; i < c.inputs.size(); ++i) os << "const float* in" << i << ", ";
+    for (size_t i = 0; i < c.outputs.size(); ++i) os << "float* out" << i << ", ";
+    os << "const unsigned* dsc_step) {\n";
+    os << "    const unsigned dsc_seed = dsc_step[0]; (void)dsc_seed;\n";
+    os << "    constexpr unsigned K = " << K << "u;\n";
+    os << "    const unsigned r = blockIdx.x * 128u + threadIdx.x;\n    if (r >= " << unum(R) << ") return;\n";
+    int uniq = 0;
+    for (size_t oi = 0; oi < c.ops.size(); ++oi) {
+        const PerElementOp& op = c.ops[oi];
+        const std::string t = "t" + num((int64_t)oi);
+        // argument k as seen from an element of this op: wide values by [k], narrow ones (and constants) as scalars
+        std::function<std::string(int)> A = [&](int a) {
+            const PerElementOp& src = c.ops[op.args[a]];
+            return "t" + num(op.args[a]) + ((src.wide && op.wide) ? "[k]" : "");
+        };
+        if (op.kind == PerElementOp::Literal) {
+            os << "    const float " << t << " = __uint_as_float(" << op.op.literal_bits << "u);\n";
+            continue;
+        }
+        if (op.kind == PerElementOp::Reduce) {
+            const bool is_max = op.op.reduce == ReduceOp::Max;
+            const std::string a = "t" + num(op.args[0]);
+            os << "    float " << t << " = " << (is_max ? "__uint_as_float(0xff800000u)" : "0.f") << ";\n";
+            os << "    #pragma unroll\n    for (unsigned k = 0; k < K; ++k) " << t << " = " << (is_max ? "fmaxf(" + t + ", " + a + "[k])" : t + " + " + a + "[k]") << ";\n";
+            continue;
+        }
+        if (op.wide) os << "    float " << t << "[K];\n    #pragma unroll\n    for (unsigned k = 0; k < K; ++k) {\n    const unsigned e = r * K + k; (void)e;\n";
+        else os << "    float " << t << ";\n    {\n    const unsigned e = r; (void)e;\n";
+        const std::string lhs = op.wide ? t + "[k]" : t;
+        switch (op.kind) {
+            case PerElementOp::Load: {
+                std::string idx = emit_chain(os, c.inputs[op.input_index].chain, "e", uniq);
+                os << "    " << lhs << " = in" << op.input_index << "[" << idx << "];\n";
+                break;
+            }
+            case PerElementOp::BuiltIn: {
+                std::string idx = emit_chain(os, op.chain, "e", uniq);
+                if (op.op.built_in == BuiltInOp::Coord) {
+                    os << "    " << lhs << " = (float)(int)(" << idx << ");\n";
+                } else {
+                    const int64_t offset = (int64_t)opt.dp_rank * op.arg_shape.element_count();
+                    os << "    " << lhs << " = dsc_rand(" << op.op.rand_uid << "u, " << idx << " + " << unum(offset) << ", dsc_seed);\n";
+                }
+                break;
+            }
+            case PerElementOp::Unary:
+            case PerElementOp::Binary:
+            case PerElementOp::Select:
+                os << "    " << lhs << " = " << op_expression(op, A) << ";\n";
+                break;
+            default: fail("unexpected op in a row cluster");
+        }
+        os << "    }\n";
+    }
+    for (size_t i = 0; i < c.outputs.size(); ++i) {
+        const PerElementOp& op = c.ops[c.output_ops[i]];
+        const std::string t = "t" + num(c.output_ops[i]);
+        if (op.wide) os << "    #pragma unroll\n    for (unsigned k = 0; k < K; ++k) out" << i << "[r * K + k] = " << t << "[k];\n";
+        else os << "    out" << i << "[r] = " << t << ";\n";
+    }
+    os << "}\n\n";
+    ClusterCode code;
+    code.source = os.str();
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)div_round_up(R, 128);
+    l.block = 128;
+    l.label = c.label;
+    l.cluster = ci;
+    for (const auto& in : c.inputs) {
+        l.args.push_back({KernelArg::NodeBuffer, in.node_id, 0});
+        l.algorithmic_bytes += chain_bytes(g, in);
+    }
+    for (size_t i = 0; i < c.outputs.size(); ++i) {
+        l.args.push_back({KernelArg::NodeBuffer, c.outputs[i], 0});
+        l.algorithmic_bytes += 4.0 * (double)g.ops().nodes[c.outputs[i]].shape.element_count();
+    }
     code.launches.push_back(l);
     return code;
 }
@@ -828,15 +930,23 @@ EpilogueCode gen_epilogue(const Graph& g, const Cluster& c, const std::string& k
     std::vector<bool> vector_load(p.inputs.size(), false), is_loaded(p.inputs.size(), false);
     for (const auto& op : p.ops)
         if (op.kind == PerElementOp::Load) is_loaded[op.input_index] = true;
+    int uniq = 0;
     for (size_t i = 0; i < p.inputs.size(); ++i) {
-        if ((int)i == product || !is_loaded[i] || !p.inputs[i].chain.is_identity()) continue;
+        if ((int)i == product || !is_loaded[i]) continue;
+        if (p.inputs[i].chain.is_identity()) {
+            os << "    const float4 q" << i << " = *reinterpret_cast<const float4*>(in" << i << " + base);\n";
+        } else if (chain_vector_run(p.inputs[i].chain, p.inputs[i].arg_shape.at(-1)) == 4) {
+            // e.g. the bias, broadcast along every axis but the channels: the four channels of this group are adjacent
+            std::string idx = emit_chain(os, p.inputs[i].chain, "base", uniq);
+            os << "    const float4 q" << i << " = *reinterpret_cast<const float4*>(in" << i << " + " << idx << ");\n";
+        } else {
+            continue;
+        }
         vector_load[i] = true;
-        os << "    const float4 q" << i << " = *reinterpret_cast<const float4*>(in" << i << " + base);\n";
         os << "    const float vin" << i << "[4] = {q" << i << ".x, q" << i << ".y, q" << i << ".z, q" << i << ".w};\n";
     }
     for (size_t i = 0; i < p.outputs.size(); ++i) os << "    float vout" << i << "[4];\n";
     os << "    #pragma unroll\n    for (int v = 0; v < 4; ++v) {\n    const unsigned e = base + v;\n";
-    int uniq = 0;
     emit_per_element_ops(os, p, opt, uniq, vector_load, product);
     for (size_t i = 0; i < p.outputs.size(); ++i) os << "    vout" << i << "[v] = t" << p.output_ops[i] << ";\n";
     os << "    }\n";
@@ -2109,6 +2219,7 @@ ClusterCode generate_cluster_code(const Graph& graph, int ci, const CodegenOptio
     switch (c.kind) {
         case ClusterKind::PerElement: return gen_per_element(graph, c, ci, opt);
         case ClusterKind::Reduce: return gen_reduce(graph, c, ci, opt);
+        case ClusterKind::Row: return gen_row(graph, c, ci, opt);
         case ClusterKind::MatMul: {
             ClusterCode code = gen_matmul(graph, c, ci, opt);
             if (prologue && prologue->fused[1] && !c.column_sum.empty() && !code.column_sum_done) {

@@ -647,6 +647,228 @@ void Graph::absorb_column_sums(std::vector<Cluster>& clusters) {
 // programs are independent by construction of the levels.  A program that reads a parameter is never grouped with
 // one that writes the same parameter: the planner lets a kernel update a parameter in place when it reads the old
 // value at the same element, which only holds inside one program.
+// Row fusion (north_star (c): softmax cross-entropy as one kernel).  loss.rs:4-34 builds softmax cross-entropy, its
+// accuracy and its gradient from per-element ops on [m, classes] / [m, 1] arrays joined by reductions along the class
+// axis (max, sum of exponentials, the picked log-probability, argmax): each reduction is a level boundary, so the
+// level schedule runs it as ten kernels of a few microseconds.  Here every maximal set of
+//   * per-element clusters whose nodes all have shape [R, K] ("wide") or [R, 1] ("narrow"), K <= 32, and
+//   * Reduce clusters over the last axis of a [R, K] array,
+// connected by identity edges, by broadcasts of a narrow value along the row, or by a reduction's own input edge, becomes
+// ONE Row cluster: one thread per row, the row's K values in registers, reductions as sequential loops in ascending k
+// (the reference kernel's own order, kernel.rs:559-642).  External operands keep their view chains.  The set must be
+// convex (no operand of the fused kernel may depend on one of its results); consumers are pushed to later levels.
+void Graph::fuse_rows(std::vector<Cluster>& clusters) {
+    auto cons = ops_.consumers();
+    const int nc = (int)clusters.size();
+    // candidate reductions define the (R, K) families
+    std::set<std::pair<int64_t, int64_t>> families;
+    for (const Cluster& c : clusters) {
+        if (c.kind != ClusterKind::Reduce || c.members.size() != 1) continue;
+        const OpNode& r = ops_.nodes[c.node_id];
+        const OpEdge& e = r.in[0];
+        const int64_t K = e.arg_shape.at(-1);
+        if (r.op.axis != e.arg_shape.len() - 1 || K < 2 || K > 32 || !e.chain.is_identity()) continue;
+        families.insert({e.arg_shape.element_count() / K, K});
+    }
+    for (auto [R, K] : families) {
+        if (R < 2) continue;
+        auto width_of = [&, R = R, K = K](const OpNode& n) {  // 2 wide, 1 narrow, 0 neither
+            if (n.shape.element_count() == R * K && n.shape.at(-1) == K) return 2;
+            if (n.shape.element_count() == R && n.shape.at(-1) == 1) return 1;
+            return 0;
+        };
+        auto broadcast_along_row = [&, K = K](const OpEdge& e) {  // consumer element e reads producer element e / K
+            if (e.chain.is_identity() || e.chain.output_count % K != 0 || e.chain.input_count != e.chain.output_count / K) return false;
+            const int64_t count = e.chain.output_count;
+            for (int64_t i = 0; i < count; i += std::max<int64_t>(1, count / 997))
+                if (eval_chain(e.chain, i) != i / K) return false;
+            for (int64_t i = std::max<int64_t>(0, count - 2 * K); i < count; ++i)
+                if (eval_chain(e.chain, i) != i / K) return false;
+            return true;
+        };
+        // eligible clusters
+        std::vector<char> eligible(nc, 0);
+        for (int ci = 0; ci < nc; ++ci) {
+            const Cluster& c = clusters[ci];
+            if (c.members.empty()) continue;
+            if (c.kind == ClusterKind::Reduce && c.members.size() == 1) {
+                const OpNode& r = ops_.nodes[c.node_id];
+                const OpEdge& e = r.in[0];
+                eligible[ci] = r.op.axis == e.arg_shape.len() - 1 && e.arg_shape.at(-1) == K && e.arg_shape.element_count() == R * K && width_of(r) == 1;
+            } else if (c.kind == ClusterKind::PerElement && c.group.empty()) {
+                bool ok = true;
+                for (int id : c.members) {
+                    const OpNode& n = ops_.nodes[id];
+                    ok = ok && width_of(n) != 0 && n.op.kind != OpKind::Gather;
+                }
+                for (const auto& op : c.ops) ok = ok && op.kind != PerElementOp::Gather;
+                eligible[ci] = ok;
+            }
+        }
+        // union clusters across fusable internal edges
+        std::vector<int> parent(nc);
+        std::iota(parent.begin(), parent.end(), 0);
+        std::function<int(int)> find = [&](int x) { return parent[x] == x ? x : parent[x] = find(parent[x]); };
+        auto internal_edge_ok = [&](int dst, const OpEdge& e) {
+            const OpNode& d = ops_.nodes[dst];
+            const OpNode& src = ops_.nodes[e.src];
+            const int ws = width_of(src), wd = width_of(d);
+            if (d.op.kind == OpKind::Reduce) return ws == 2 && e.chain.is_identity();
+            if (ws == wd && e.chain.is_identity()) return true;
+            return ws == 1 && wd == 2 && broadcast_along_row(e);
+        };
+        for (int ci = 0; ci < nc; ++ci) {
+            if (!eligible[ci]) continue;
+            for (int id : clusters[ci].members)
+                for (const auto& e : ops_.nodes[id].in) {
+                    const int sc = ops_.nodes[e.src].cluster_id;
+                    if (sc < 0 || sc == ci || !eligible[sc]) continue;
+                    if (ops_.nodes[id].op.is_gather_arg(e.arg)) continue;
+                    if (internal_edge_ok(id, e)) parent[find(ci)] = find(sc);
+                }
+        }
+        std::map<int, std::vector<int>> components;
+        for (int ci = 0; ci < nc; ++ci)
+            if (eligible[ci]) components[find(ci)].push_back(ci);
+        for (auto& [root, ids] : components) {
+            (void)root;
+            bool has_reduce = false;
+            for (int ci : ids) has_reduce |= clusters[ci].kind == ClusterKind::Reduce;
+            if (!has_reduce || ids.size() < 3) continue;
+            std::set<int> member_clusters(ids.begin(), ids.end());
+            std::vector<int> members;  // nodes, topological (node ids are created in topological order per cluster; merge by order below)
+            for (int id : ops_.topo_order())
+                if (ops_.nodes[id].alive && ops_.nodes[id].cluster_id >= 0 && member_clusters.count(ops_.nodes[id].cluster_id)) members.push_back(id);
+            std::set<int> member_nodes(members.begin(), members.end());
+            // every edge between two members must be one the kernel can keep in registers
+            bool ok = true;
+            for (int id : members)
+                for (const auto& e : ops_.nodes[id].in)
+                    if (member_nodes.count(e.src) && !internal_edge_ok(id, e)) ok = false;
+            // convexity: no external operand may depend on a member
+            int min_level = INT32_MAX, max_level = 0;
+            for (int ci : ids) { min_level = std::min(min_level, clusters[ci].level); max_level = std::max(max_level, clusters[ci].level); }
+            std::set<int> visited;
+            std::function<bool(int)> reaches_member = [&](int id) {
+                if (member_nodes.count(id)) return true;
+                if (!visited.insert(id).second) return false;
+                const OpNode& n = ops_.nodes[id];
+                if (n.cluster_id >= 0 && clusters[n.cluster_id].level < min_level) return false;  // scheduled before any member
+                for (const auto& e : n.in)
+                    if (reaches_member(e.src)) return true;
+                return false;
+            };
+            for (int id : members)
+                for (const auto& e : ops_.nodes[id].in)
+                    if (!member_nodes.count(e.src) && reaches_member(e.src)) ok = false;
+            if (!ok) continue;
+
+            // build the program
+            Cluster row;
+            row.kind = ClusterKind::Row;
+            row.level = max_level;
+            row.rows = R;
+            row.row_length = K;
+            row.members = members;
+            std::map<int, int> op_of;  // member node -> op index
+            struct Loaded { int src; ViewChain chain; Shape arg_shape; bool wide; int op_index; };
+            std::vector<Loaded> loaded;
+            auto find_input = [&](const ClusterInput& in) {
+                for (size_t i = 0; i < row.inputs.size(); ++i)
+                    if (row.inputs[i] == in) return (int)i;
+                row.inputs.push_back(in);
+                return (int)row.inputs.size() - 1;
+            };
+            for (int id : members) {
+                const OpNode& node = ops_.nodes[id];
+                PerElementOp pe;
+                pe.op = node.op;
+                pe.shape = node.shape;
+                pe.wide = width_of(node) == 2;
+                for (int a = 0; a < node.arg_count(); ++a) {
+                    const OpEdge* e = node.arg_edge(a);
+                    DSC_CHECK(e != nullptr, "missing argument");
+                    auto m = op_of.find(e->src);
+                    if (m != op_of.end()) { pe.args[a] = m->second; continue; }
+                    const OpNode& src = ops_.nodes[e->src];
+                    const bool arg_wide = node.op.kind == OpKind::Reduce ? true : pe.wide;
+                    int op_index = -1;
+                    for (const auto& l : loaded)
+                        if (l.src == e->src && l.chain == e->chain && l.arg_shape == e->arg_shape && l.wide == arg_wide) op_index = l.op_index;
+                    if (op_index < 0) {
+                        PerElementOp ld;
+                        ld.wide = arg_wide;
+                        if (src.op.kind == OpKind::Literal) {
+                            ld.kind = PerElementOp::Literal;
+                            ld.op = src.op;
+                            ld.wide = false;  // a constant
+                        } else if (src.op.kind == OpKind::BuiltIn) {
+                            ld.kind = PerElementOp::BuiltIn;
+                            ld.op = src.op;
+                            ld.chain = e->chain;
+                            ld.arg_shape = src.shape;
+                        } else {
+                            ld.kind = PerElementOp::Load;
+                            ld.input_index = find_input({e->src, e->chain, e->arg_shape});
+                        }
+                        op_index = (int)row.ops.size();
+                        row.ops.push_back(ld);
+                        loaded.push_back({e->src, e->chain, e->arg_shape, arg_wide, op_index});
+                    }
+                    pe.args[a] = op_index;
+                }
+                switch (node.op.kind) {
+                    case OpKind::Unary: pe.kind = PerElementOp::Unary; break;
+                    case OpKind::Binary: pe.kind = PerElementOp::Binary; break;
+                    case OpKind::CompareAndSelect: pe.kind = PerElementOp::Select; break;
+                    case OpKind::Reduce: pe.kind = PerElementOp::Reduce; pe.wide = false; break;
+                    default: fail("unexpected op in row cluster");
+                }
+                const int op_index = (int)row.ops.size();
+                row.ops.push_back(pe);
+                op_of[id] = op_index;
+                bool needs_store = false;
+                for (auto [dst, k] : cons[id]) {
+                    (void)k;
+                    if (ops_.nodes[dst].alive && !member_nodes.count(dst)) needs_store = true;
+                }
+                if (needs_store) {
+                    row.outputs.push_back(id);
+                    row.output_ops.push_back(op_index);
+                }
+            }
+            std::ostringstream label;
+            label << "Row (" << row.ops.size() << " ops, " << ids.size() << " fused kernels) [" << R << ", " << K << "]";
+            row.label = label.str();
+            // the first member cluster becomes the row cluster, the others are emptied (dropped by the caller)
+            const int keep = ids[0];
+            for (int ci : ids) {
+                clusters[ci].members.clear();
+                clusters[ci].outputs.clear();
+            }
+            clusters[keep] = row;
+            for (int id : members) ops_.nodes[id].cluster_id = keep;
+        }
+    }
+    // consumers of a fused kernel's results must sit on later levels than the fused kernel itself
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        int ar_level = -1;
+        for (const auto& node : ops_.nodes) {
+            if (!node.alive || node.cluster_id < 0) continue;
+            Cluster& dc = clusters[node.cluster_id];
+            for (const auto& e : node.in) {
+                const OpNode& src = ops_.nodes[e.src];
+                if (!src.alive || src.cluster_id < 0 || src.cluster_id == node.cluster_id) continue;
+                const Cluster& sc = clusters[src.cluster_id];
+                if (dc.level <= sc.level) { dc.level = sc.level + 1; changed = true; }
+            }
+        }
+        (void)ar_level;
+    }
+}
+
 // Multi-tensor optimiser step (north_star (c): SGD / Adam as one hand-scheduled kernel, optimizer.rs:62-112).  The
 // reference's optimisers emit one per-element update per parameter tensor, which the level schedule places right
 // behind that tensor's gradient: eight (conv-net) or sixteen (multi-hash) launches of a few microseconds each spread
@@ -1076,6 +1298,7 @@ void Graph::build_clusters() {
         if (c.kind == ClusterKind::PerElement) build_per_element_program(c);
     absorb_per_element_epilogues(clusters);
     absorb_column_sums(clusters);
+    fuse_rows(clusters);
     sink_parameter_updates(clusters);
     group_small_per_element(clusters);
 

@@ -20,7 +20,7 @@
 
 namespace descent {
 
-enum class ClusterKind { PerElement, Reduce, MatMul, Unpad, WindowsToImage, ScatterAdd, AllReduce };
+enum class ClusterKind { PerElement, Reduce, MatMul, Unpad, WindowsToImage, ScatterAdd, AllReduce, Row };
 
 // one buffer argument of a kernel: a producer node read through a chain
 struct ClusterInput {
@@ -32,7 +32,8 @@ struct ClusterInput {
 
 // straight-line program of a per-element kernel (reference: PerElementKernelOp, kernel.rs:8-35)
 struct PerElementOp {
-    enum Kind { Load, Literal, BuiltIn, Unary, Binary, Select, Gather } kind = Load;
+    enum Kind { Load, Literal, BuiltIn, Unary, Binary, Select, Gather, Reduce } kind = Load;  // Reduce: Row clusters only (over the row, args[0])
+    bool wide = true;            // Row clusters: one value per (row, k) -- false: one value per row
     int input_index = -1;        // Load / Gather: index into Cluster::inputs
     Op op;                       // Literal / BuiltIn / Unary / Binary / Select / Gather payload
     ViewChain chain;             // BuiltIn: chain from the built-in's own index space
@@ -83,6 +84,10 @@ struct Cluster {
     // updates of all parameter tensors, the per-level bookkeeping of a hash grid) launched as ONE kernel; block ranges
     // select the program.  inputs / outputs are the concatenation of the sub-clusters' in order.
     std::vector<Cluster> group;
+    // Row: per-element ops on [rows, row_length] / [rows, 1] arrays and the reductions along the row that connect them
+    // (softmax cross-entropy with its accuracy and gradient, loss.rs:4-34: max, exp, sum, divide, log, pick, subtract)
+    // as ONE kernel, one thread per row, the row in registers; `ops` is the program (PerElementOp::wide / Reduce).
+    int64_t rows = 0, row_length = 0;
     std::string label;                 // as the reference's Kernel::label_name (kernel.rs)
 };
 
@@ -127,6 +132,7 @@ private:
     void sink_permutations_into_per_element();
     void absorb_per_element_epilogues(std::vector<Cluster>& clusters);
     void absorb_column_sums(std::vector<Cluster>& clusters);
+    void fuse_rows(std::vector<Cluster>& clusters);
     void sink_parameter_updates(std::vector<Cluster>& clusters);
     void group_small_per_element(std::vector<Cluster>& clusters);
     bool absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id);
