@@ -902,7 +902,7 @@ EpilogueCode gen_epilogue(const Graph& g, const Cluster& c, const std::string& k
     EpilogueCode code;
     std::ostringstream os;
     if (c.epilogue.empty()) {
-        os << "__device__ __forceinline__ void " << kernel << "_store4(size_t index, float4 r, float* C, unsigned) { *reinterpret_cast<float4*>(C + index) = r; }\n";
+        os << "__device__ __forceinline__ float4 " << kernel << "_store4(size_t index, float4 r, float* C, unsigned) { *reinterpret_cast<float4*>(C + index) = r; return r; }\n";
         code.store4 = os.str();
         return code;
     }
@@ -925,7 +925,7 @@ EpilogueCode gen_epilogue(const Graph& g, const Cluster& c, const std::string& k
     code.params = params.str();
     code.args = args.str();
     os << "// epilogue: " << p.label << "\n";
-    os << "__device__ __forceinline__ void " << kernel << "_store4(size_t index, float4 r, float* C, " << code.params << "unsigned dsc_seed) {\n";
+    os << "__device__ __forceinline__ float4 " << kernel << "_store4(size_t index, float4 r, float* C, " << code.params << "unsigned dsc_seed) {\n";
     os << "    (void)C; (void)dsc_seed;\n    const unsigned base = (unsigned)index;\n    const float acc[4] = {r.x, r.y, r.z, r.w};\n";
     std::vector<bool> vector_load(p.inputs.size(), false), is_loaded(p.inputs.size(), false);
     for (const auto& op : p.ops)
@@ -953,6 +953,7 @@ EpilogueCode gen_epilogue(const Graph& g, const Cluster& c, const std::string& k
     for (size_t i = 0; i < p.outputs.size(); ++i)
         os << "    *reinterpret_cast<float4*>(out" << i << " + base) = make_float4(vout" << i << "[0], vout" << i << "[1], vout" << i << "[2], vout" << i
            << "[3]);\n";
+    os << "    return make_float4(vout0[0], vout0[1], vout0[2], vout0[3]);  // the first output, for kernels that also pool it\n";
     os << "}\n";
     code.store4 = os.str();
     return code;
@@ -1193,6 +1194,10 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
         const int64_t a_stage = div_round_up(Q * npix * 16, 128) * 128;
         const int64_t so_bytes = (unpad || stage_out) ? 128 * (G * NG + 4) * 4 : 0;
         const int64_t smem2 = stages * a_stage + b_bytes + so_bytes + 64 + YT * 4 + 128;
+        const auto& pool = c.pool;
+        // the tile must hold whole pooling windows of the activation it stages (forward, channels interleaved per pixel)
+        const bool pooled = pool.enabled && !h.backward_input && stage_out && pool.images == h.images && pool.height == OH && pool.width == OW &&
+                            pool.channels == G * NG && TH % pool.window_h == 0 && OH % pool.window_h == 0 && OW % pool.window_w == 0;
         if (separable && 2 * acc_cols <= 512 && smem2 <= 200 * 1024) {
             const int64_t resident2 = std::max<int64_t>(1, std::min<int64_t>({(int64_t)halo_ctas_per_sm(), (220 * 1024) / (smem2 + 1024), 512 / (2 * acc_cols)}));
             auto list = [](const std::vector<int64_t>& v) {
@@ -1200,8 +1205,10 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
                 for (size_t i = 0; i < v.size(); ++i) t += (i ? ", " : "") + num(v[i]);
                 return t;
             };
+            out->pool_done = pooled;
             out->source = subst(kHaloConvPipelinedTemplate,
-                                {{"LABEL", c.label}, {"MIN_CTAS", num(resident2)}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args},
+                                {{"LABEL", c.label}, {"POOL", pooled ? "true" : "false"}, {"POOL_H", num(pooled ? pool.window_h : 1)}, {"POOL_W", num(pooled ? pool.window_w : 1)},
+                                 {"POOL_PARAMS", pooled ? "float* pool_out, " : ""}, {"POOL_DECL", pooled ? "" : "float* const pool_out = nullptr;"}, {"MIN_CTAS", num(resident2)}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args},
                                  {"G", num(G)}, {"IMAGES", num(h.images)}, {"ROWS", num(rows)}, {"W", num(W)}, {"FH", num(FH)}, {"FW", num(FW)}, {"KG", num(KG)},
                                  {"NG", num(NG)}, {"BN", num(BN)}, {"LEAD", num(lead)}, {"TMEM_COLS", num(2 * acc_cols)}, {"NPIX", num(npix)}, {"STAGES", num(stages)},
                                  {"PY", num(h.unpad_h)}, {"PX", num(h.unpad_w)}, {"STAGE_OUT", stage_out ? "true" : "false"}, {"OUT_W", num(OW)},
@@ -1217,7 +1224,9 @@ bool gen_halo_conv(const Graph& g, const Cluster& c, int ci, const CodegenOption
             l.cluster = ci;
             l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
             l.args.insert(l.args.end(), epi.launch_args.begin(), epi.launch_args.end());
-            l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(out_pixels * G * NG) : epi.bytes);
+            if (pooled) l.args.push_back({KernelArg::NodeBuffer, c.outputs.back(), 0});
+            l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(out_pixels * G * NG) : epi.bytes) +
+                                  (pooled ? 4.0 * (double)g.ops().nodes[c.outputs.back()].shape.element_count() : 0.0);
             l.flops = 2.0 * (double)(out_pixels * G * NG) * (double)(FH * FW * KG);
             out->launches.push_back(l);
             return true;
@@ -1441,11 +1450,33 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
         std::string ib = emit_chain(cb, b.chain, {{"batch", K * N, BC}, {"gk", N, K}, {"gn", 1, N}}, uniq, "            ");
         if (!c.epilogue.empty() && (N % 4 != 0 || !(rows_mode ? true : BC == 1))) return false;
         const EpilogueCode epi = gen_epilogue(g, c, name, opt);
-        l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(BC * M * N) : epi.bytes);
+        const auto& pool = c.pool;
+        // rows are the pixels of an NHWC activation that is max-pooled right away: one pooling window x 4 channels per thread
+        const bool pooled = pool.enabled && BC == 1 && N % 4 == 0 && pool.channels == N && pool.images * pool.height * pool.width == M &&
+                            pool.window_h * pool.window_w <= 8 && pool.width % pool.window_w == 0 && pool.height % pool.window_h == 0 && !c.epilogue.empty();
+        out->pool_done = pooled;
+        l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(BC * M * N) : epi.bytes) +
+                              (pooled ? 4.0 * (double)g.ops().nodes[c.outputs.back()].shape.element_count() : 0.0);
+        if (pooled)
+            out->source = subst(kThinRowsPoolTemplate, {{"LABEL", c.label}, {"NAME", name}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)},
+                                                       {"POOL_H", num(pool.window_h)}, {"POOL_W", num(pool.window_w)}, {"IMG_W", num(pool.width)},
+                                                       {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args},
+                                                       {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
+        else
         out->source = subst(kThinRowsTemplate, {{"LABEL", c.label}, {"NAME", name}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)}, {"BC", num(BC)},
                                                {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args},
                                                {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}, {"C_ROW", c_row}});
-        l.grid_x = (uint32_t)div_round_up(M, 256);
+        const int64_t tile = 256;
+        if (pooled) {
+            const int64_t windows = M / (pool.window_h * pool.window_w);
+            l.grid_x = (uint32_t)div_round_up(windows * (N / 4), 256);
+            l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
+            l.args.insert(l.args.end(), epi.launch_args.begin(), epi.launch_args.end());
+            l.args.push_back({KernelArg::NodeBuffer, c.outputs.back(), 0});
+            out->launches.push_back(l);
+            return true;
+        }
+        l.grid_x = (uint32_t)div_round_up(M, tile);
         l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
         l.args.insert(l.args.end(), epi.launch_args.begin(), epi.launch_args.end());
         out->launches.push_back(l);
@@ -2222,6 +2253,18 @@ ClusterCode generate_cluster_code(const Graph& graph, int ci, const CodegenOptio
         case ClusterKind::Row: return gen_row(graph, c, ci, opt);
         case ClusterKind::MatMul: {
             ClusterCode code = gen_matmul(graph, c, ci, opt);
+            if (c.pool.enabled && !code.pool_done) {
+                // the GEMM kernel chosen for this shape does not pool its output: run the absorbed max-pool Reduce after it
+                ClusterCode r = gen_reduce(graph, c.pool.reduce[0], ci, opt, "_pool");
+                const int64_t base = div_round_up(code.scratch_bytes, 256) * 256;
+                code.scratch_bytes = base + div_round_up(r.scratch_bytes, 256) * 256;
+                code.source += r.source;
+                for (auto& l : r.launches) {
+                    for (auto& arg : l.args)
+                        if (arg.kind == KernelArg::Scratch) arg.scratch_offset += base;
+                    code.launches.push_back(l);
+                }
+            }
             if (prologue && prologue->fused[1] && !c.column_sum.empty() && !code.column_sum_done) {
                 prologue->fused[1] = false;  // the absorbed column sums would read B from memory, where it no longer exists
                 return code;

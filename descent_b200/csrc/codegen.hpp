@@ -34,6 +34,7 @@ struct ClusterCode {
     std::vector<KernelLaunch> launches;
     int64_t scratch_bytes = 0;
     bool column_sum_done = false;  // the GEMM kernel also produced Cluster::column_sum's result (outputs[1])
+    bool pool_done = false;        // the GEMM kernel also produced Cluster::pool's result (outputs.back())
     // operand prologues (graph.hpp OperandPrologue): nodes this cluster's kernels read although no graph edge says so
     // (the inputs of a producer evaluated inside the operand loader): the planner keeps them alive until this cluster
     std::vector<int> extra_reads;

@@ -106,6 +106,9 @@ struct SharedStorage {
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
+    // epilogue: each warp turns its 32 rows x 32 columns (one row per lane out of TMEM) into row-contiguous stores;
+    // 36-float rows keep the quarter-warp phases of the 128-bit accesses on distinct banks
+    alignas(16) float stage[4][32][36];
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
@@ -210,8 +213,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             mbar_wait(&s.tmem_full[acc_stage], acc_phase);
             tcgen05_fence_after();
-            const int grow = m0 + quad * 32 + lane;
-            float* row = c + ((size_t)split * m + grow) * n + n0;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN && n0 + c0 < n; c0 += 32) {
                 uint32_t v[32];
@@ -226,19 +227,31 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                       "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (grow < m) {
-                    if ((n & 3) == 0) {
+                // a lane holds 32 consecutive columns of ONE row: stored as is, every instruction of the warp would touch 32
+                // rows with 16 bytes each (half-filled sectors; measured 43 us for the 51 MB product of a K = 128 GEMM).
+                // Through the warp's staging tile each instruction writes whole 128-byte row segments instead.
+                float (*tile)[36] = s.stage[quad];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (n0 + c0 + j < n)
-                                *reinterpret_cast<float4*>(row + c0 + j) =
-                                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                    } else {
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(&tile[lane][j]) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                __syncwarp();
+                const int row0 = m0 + quad * 32;
+                float* base = c + ((size_t)split * m + row0) * n + n0 + c0;
+                if ((n & 3) == 0) {
+                    const int cpos = (lane & 7) * 4;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + c0 + j < n) row[c0 + j] = __uint_as_float(v[j]);
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + (lane >> 3);
+                        if (row0 + r < m && n0 + c0 + cpos < n)
+                            *reinterpret_cast<float4*>(base + (size_t)r * n + cpos) = *reinterpret_cast<const float4*>(&tile[r][cpos]);
                     }
+                } else {
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r)
+                        if (row0 + r < m && n0 + c0 + lane < n) base[(size_t)r * n + lane] = tile[r][lane];
                 }
+                __syncwarp();
             }
             tcgen05_fence_before();
             __syncwarp();

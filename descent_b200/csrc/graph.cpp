@@ -584,6 +584,57 @@ void Graph::absorb_per_element_epilogues(std::vector<Cluster>& clusters) {
     }
 }
 
+// conv2d -> activation -> max_pool2d: the pooling Reduce joins the convolution's cluster (see Cluster::Pool).
+void Graph::absorb_max_pools(std::vector<Cluster>& clusters) {
+    auto cons = ops_.consumers();
+    for (size_t mi = 0; mi < clusters.size(); ++mi) {
+        Cluster& mc = clusters[mi];
+        if (mc.kind != ClusterKind::MatMul || mc.epilogue.empty() || mc.outputs.size() != 1 || mc.pool.enabled) continue;
+        const int x = mc.outputs[0];
+        const OpNode& xn = ops_.nodes[x];
+        if (xn.shape.len() != 4) continue;
+        const int64_t B = xn.shape[0], H = xn.shape[1], W = xn.shape[2], C = xn.shape[3];
+        for (auto [dst, k] : cons[x]) {
+            const OpNode& r = ops_.nodes[dst];
+            const OpEdge& e = r.in[k];
+            if (r.op.kind != OpKind::Reduce || r.op.reduce != ReduceOp::Max || r.cluster_id < 0) continue;
+            Cluster& rc = clusters[r.cluster_id];
+            if (rc.kind != ClusterKind::Reduce || rc.members.size() != 1 || e.arg_shape.len() != 3 || r.op.axis != 1 || e.arg_shape[2] != C) continue;
+            const int64_t O = e.arg_shape[0], K = e.arg_shape[1];
+            bool found = false;
+            int64_t ph = 0, pw = 0;
+            for (ph = 1; ph <= K && !found; ++ph) {
+                if (K % ph != 0) continue;
+                pw = K / ph;
+                if (H % ph != 0 || W % pw != 0 || O != B * (H / ph) * (W / pw)) continue;
+                const int64_t PH = H / ph, PW = W / pw;
+                auto expected = [&](int64_t o, int64_t kk, int64_t c) {
+                    const int64_t image = o / (PH * PW), py = (o / PW) % PH, px = o % PW, wy = kk / pw, wx = kk % pw;
+                    return ((image * H + py * ph + wy) * W + px * pw + wx) * C + c;
+                };
+                bool ok = true;
+                for (int64_t o : {(int64_t)0, (int64_t)1, PW, PW + 1, PH * PW - 1, std::min<int64_t>(PH * PW + PW + 1, O - 1), O / 2, O - 1})
+                    for (int64_t kk = 0; kk < K && ok; ++kk)
+                        for (int64_t c : {(int64_t)0, C - 1})
+                            if (eval_chain(e.chain, (o * K + kk) * C + c) != expected(o, kk, c)) ok = false;
+                if (ok) { found = true; break; }
+            }
+            if (!found || ph * pw < 2) continue;
+            mc.pool.enabled = true;
+            mc.pool.images = B; mc.pool.height = H; mc.pool.width = W; mc.pool.channels = C;
+            mc.pool.window_h = ph; mc.pool.window_w = pw;
+            mc.pool.reduce.push_back(rc);
+            mc.outputs.push_back(dst);
+            mc.members.push_back(dst);
+            mc.label += " +MaxPool";
+            ops_.nodes[dst].cluster_id = (int)mi;
+            rc.members.clear();
+            rc.outputs.clear();
+            break;
+        }
+    }
+}
+
 // dW = A^T x dY and db = column sums of dY read the same array: when the graph reduces the GEMM's B operand [K, C]
 // over all of K (reduce_sum axis by axis, array.rs) and nothing needs the result before the GEMM's turn, the Reduce
 // chain joins the MatMul's cluster (see Cluster::column_sum).
@@ -1298,6 +1349,7 @@ void Graph::build_clusters() {
         if (c.kind == ClusterKind::PerElement) build_per_element_program(c);
     absorb_per_element_epilogues(clusters);
     absorb_column_sums(clusters);
+    absorb_max_pools(clusters);
     fuse_rows(clusters);
     sink_parameter_updates(clusters);
     group_small_per_element(clusters);

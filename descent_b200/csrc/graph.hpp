@@ -75,6 +75,16 @@ struct Cluster {
     // its other inputs are appended to `inputs` (from index 2 on, in order) and its outputs replace `outputs`.
     std::vector<Cluster> epilogue;
     int epilogue_product_input = -1;
+    // ... and whose single result, an NHWC activation [images, height, width, channels], is also max-pooled over
+    // non-overlapping window_h x window_w windows (DualArray::max_pool2d, array.rs:1033-1047: windows view + reduce_max):
+    // the GEMM kernels that hold a whole tile of the activation before storing it also store the pooled maxima, so the
+    // pooling pass never re-reads the activation.  `pool.reduce[0]` is the absorbed Reduce cluster (other GEMM kernels
+    // run it after the product); the pooled node is the LAST entry of `outputs`.
+    struct Pool {
+        bool enabled = false;
+        int64_t images = 0, height = 0, width = 0, channels = 0, window_h = 0, window_w = 0;
+        std::vector<Cluster> reduce;
+    } pool;
     // MatMul whose B operand is a [K, C] array that the graph also sums over K with a chain of Reduce(sum) nodes (the
     // bias gradient next to a convolution's / dense layer's weight gradient: both read dY once per step).  The GEMM
     // kernels that stream B produce those column sums on the side; `column_sum[i]` are the absorbed Reduce clusters in
@@ -132,6 +142,7 @@ private:
     void sink_permutations_into_per_element();
     void absorb_per_element_epilogues(std::vector<Cluster>& clusters);
     void absorb_column_sums(std::vector<Cluster>& clusters);
+    void absorb_max_pools(std::vector<Cluster>& clusters);
     void fuse_rows(std::vector<Cluster>& clusters);
     void sink_parameter_updates(std::vector<Cluster>& clusters);
     void group_small_per_element(std::vector<Cluster>& clusters);

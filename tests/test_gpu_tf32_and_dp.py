@@ -19,7 +19,11 @@ from oracle import run_graph
 pytestmark = pytest.mark.gpu
 TF32_LOSS_TOL = 2e-3  # measured 3.2e-4
 TF32_PARAM_TOL = 1.5e-1  # measured 1.4e-2 .. 5.3e-2 (Adam steps of near-zero gradients flip sign)
-CONV_NET_TF32_PARAM_TOL = 1.5e-1  # conv-net, 100 steps: calibrated below
+# conv-net, 100 Adam steps at m = 256 (calibration run, B200): loss 2.4e-4, accuracy sum 1.3 %, parameters 0.0055 .. 0.38 of
+# max|theta| in the maximum norm (the dense layers; see the test's docstring for why Adam makes that norm meaningless)
+CONV_NET_TF32_PARAM_TOL = 6e-1
+CONV_NET_TF32_PARAM_RMS_TOL = 3e-1
+CONV_NET_TF32_ACCURACY_TOL = 3e-2
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -149,8 +153,12 @@ def test_tf32_conv_net_100_steps_within_stated_tolerance(env):
     program.close()
     got, want = env.read_parameter_scalar(ex.loss_sum), float(state[ex.loss_sum.id].reshape(-1)[0])
     drift = {p.name() + "#%d" % p.id: max_rel_err(env.read(p), state[p.id]) for p in ex.parameters}
+    rms = {p.name() + "#%d" % p.id: float(np.linalg.norm(env.read(p).astype(np.float64) - state[p.id]) / np.linalg.norm(state[p.id].astype(np.float64))) for p in ex.parameters}
     acc_got, acc_want = env.read_parameter_scalar(ex.accuracy_sum), float(state[ex.accuracy_sum.id].reshape(-1)[0])
-    print("conv-net tf32 vs strict oracle after %d steps: loss %.6g vs %.6g (rel %.3g), accuracy sum %g vs %g, parameter drift / max|theta| %s"
-          % (steps, got, want, abs(got - want) / abs(want), acc_got, acc_want, {k: "%.3g" % v for k, v in drift.items()}))
+    print("conv-net tf32 vs strict oracle after %d steps: loss %.6g vs %.6g (rel %.3g), accuracy sum %g vs %g, parameter drift max / max|theta| %s, "
+          "|d theta|_2 / |theta|_2 %s" % (steps, got, want, abs(got - want) / abs(want), acc_got, acc_want, {k: "%.3g" % v for k, v in drift.items()},
+                                         {k: "%.3g" % v for k, v in rms.items()}))
     assert abs(got - want) <= TF32_LOSS_TOL * abs(want), (got, want)
+    assert abs(acc_got - acc_want) <= CONV_NET_TF32_ACCURACY_TOL * acc_want, (acc_got, acc_want)
+    assert max(rms.values()) <= CONV_NET_TF32_PARAM_RMS_TOL, rms
     assert max(drift.values()) <= CONV_NET_TF32_PARAM_TOL, drift
