@@ -95,6 +95,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_nccl;
@@ -107,6 +108,7 @@ int load_nccl() {
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");  // optional: only the peer-memory set-up uses it
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
         return set_error(DSC_ERR_NCCL, "libnccl.so.2 is missing expected symbols");
@@ -124,6 +126,68 @@ __global__ void dsc_fill_u32_kernel(unsigned* p, unsigned v, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) p[i] = v;
+}
+
+// ---- one-shot all-reduce over peer-mapped memory (the small, late gradient bucket) -------------------------------
+// NCCL's latency for a 20 KB message (15-35 us at 2-8 ranks) is all exposed at the end of the backward pass.  Every
+// rank owns an exchange area (two data slots + flags + an epoch counter) that its peers map through CUDA IPC over
+// NVLink.  One CTA per rank: publish my values into my slot (epoch parity), release-store the epoch into my flag on
+// every peer, spin until every peer's flag in my area shows the epoch, then read all slots with P2P loads and add them
+// in rank order -- the same order on every rank, so the replicas stay bitwise identical.  No second barrier: a peer
+// cannot overwrite the slot of epoch e before it has seen my flag of epoch e + 1, which I send after reading.
+constexpr int kXchgMaxRanks = 16;
+constexpr size_t kXchgSlotFloats = 64 * 1024;  // 256 KB per slot
+struct XchgArea {
+    unsigned epoch;
+    unsigned pad[31];
+    unsigned flags[2][kXchgMaxRanks * 32];  // one 128-byte line per (slot, peer)
+    float data[2][kXchgSlotFloats];
+};
+struct XchgPeers { XchgArea* area[kXchgMaxRanks]; };
+
+__global__ void __launch_bounds__(1024) dsc_oneshot_allreduce_kernel(float* bucket, unsigned count, XchgPeers peers, int rank, int world) {
+    XchgArea* mine = peers.area[rank];
+    const unsigned epoch = mine->epoch + 1u, slot = epoch & 1u;
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid * 4u; i < count; i += 4096u) {
+        if (i + 4u <= count) *reinterpret_cast<float4*>(&mine->data[slot][i]) = *reinterpret_cast<const float4*>(bucket + i);
+        else for (unsigned j = i; j < count; ++j) mine->data[slot][j] = bucket[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < (unsigned)world) {
+        unsigned* flag = &peers.area[tid]->flags[slot][rank * 32];
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+        const unsigned* wait_on = &mine->flags[slot][tid * 32];
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(wait_on) : "memory");
+        } while (seen != epoch);
+    }
+    __syncthreads();
+    for (unsigned i = tid * 4u; i < count; i += 4096u) {
+        if (i + 4u <= count) {
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = 0; p < world; ++p) {
+                float4 v;
+                asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(&peers.area[p]->data[slot][i]) : "memory");
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            *reinterpret_cast<float4*>(bucket + i) = sum;
+        } else {
+            for (unsigned j = i; j < count; ++j) {
+                float sum = 0.f;
+                for (int p = 0; p < world; ++p) {
+                    float v;
+                    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(&peers.area[p]->data[slot][j]) : "memory");
+                    sum += v;
+                }
+                bucket[j] = sum;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) mine->epoch = epoch;
 }
 
 constexpr size_t kStagingSlotBytes = 16u << 20;
@@ -147,6 +211,8 @@ struct dsc_ctx {
     cudaStream_t comm_stream = nullptr;   // early gradient bucket: all-reduced here while the backward pass continues on `stream`
     cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
     bool comm_pending = false;
+    XchgPeers xchg;             // peer-mapped exchange areas (own entry = local allocation); valid when xchg_ready
+    bool xchg_ready = false;
     bool capturing = false;
 };
 struct dsc_module {
@@ -221,6 +287,14 @@ int dsc_ctx_destroy(dsc_ctx* ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaEventDestroy(ctx->prefetch_done);
     cudaEventDestroy(ctx->staged_read);
+    if (ctx->xchg_ready) {
+        for (int p = 0; p < ctx->world; ++p) {
+            // the local area is deliberately not freed: a slower peer's last reduction may still be reading it (0.5 MB per
+            // context, returned at process exit)
+            if (p != ctx->rank) cudaIpcCloseMemHandle(ctx->xchg.area[p]);
+        }
+        ctx->xchg_ready = false;
+    }
     cudaStreamSynchronize(ctx->comm_stream);
     cudaEventDestroy(ctx->comm_fork);
     cudaEventDestroy(ctx->comm_join);
@@ -497,12 +571,57 @@ int dsc_dp_init(dsc_ctx* ctx, const void* unique_id128, int world, int rank) {
     ncclUniqueId id;
     memcpy(&id, unique_id128, 128);
     NCCL_TRY(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+    // peer-memory exchange areas for the one-shot all-reduce; any failure here just leaves the NCCL path in charge
+    ctx->xchg_ready = false;
+    const char* off = getenv("DSC_DP_ONESHOT");
+    if (world <= kXchgMaxRanks && g_nccl.AllGather && !(off && atoi(off) == 0)) {
+        XchgArea* local = nullptr;
+        cudaIpcMemHandle_t* handles = nullptr;
+        bool ok = cudaMalloc(&local, sizeof(XchgArea)) == cudaSuccess && cudaMemset(local, 0, sizeof(XchgArea)) == cudaSuccess &&
+                  cudaMalloc(&handles, sizeof(cudaIpcMemHandle_t) * world) == cudaSuccess;
+        cudaIpcMemHandle_t mine;
+        ok = ok && cudaIpcGetMemHandle(&mine, local) == cudaSuccess &&
+             cudaMemcpy(handles + rank, &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+        // every rank must take part in the collective even if its own set-up failed, so the outcome is gathered too
+        std::vector<cudaIpcMemHandle_t> all(world);
+        if (handles) {
+            if (!ok) cudaMemset(handles + rank, 0, sizeof(mine));
+            ncclResult_t r = g_nccl.AllGather(handles + rank, handles, sizeof(mine), ncclInt8, ctx->comm, ctx->stream);
+            ok = ok && r == ncclSuccess && cudaStreamSynchronize(ctx->stream) == cudaSuccess &&
+                 cudaMemcpy(all.data(), handles, sizeof(mine) * world, cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        for (int p = 0; ok && p < world; ++p) {
+            if (p == rank) { ctx->xchg.area[p] = local; continue; }
+            void* mapped = nullptr;
+            ok = cudaIpcOpenMemHandle(&mapped, all[p], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            ctx->xchg.area[p] = (XchgArea*)mapped;
+        }
+        if (handles) cudaFree(handles);
+        cudaGetLastError();  // a failed attempt must not poison later calls
+        // all ranks agree on the outcome: a rank that failed falls back to NCCL, so everyone must
+        int* flag = nullptr;
+        int agreed = 0;
+        if (cudaMalloc(&flag, sizeof(int)) == cudaSuccess) {
+            const int mine_ok = ok ? 1 : 0;
+            cudaMemcpy(flag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice);
+            if (g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream) == ncclSuccess && cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+                cudaMemcpy(&agreed, flag, sizeof(int), cudaMemcpyDeviceToHost);
+            cudaFree(flag);
+        }
+        ctx->xchg_ready = agreed == 1;
+        cudaGetLastError();
+    }
     return DSC_OK;
 }
 int dsc_dp_allreduce_sum_f32(dsc_ctx* ctx, uint64_t id, size_t count) {
     if (ctx->world == 1 || count == 0) return DSC_OK;
     if (!ctx->comm) return set_error(DSC_ERR_NCCL, "data-parallel communicator not initialised");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->xchg_ready && count <= kXchgSlotFloats && (id & 15) == 0) {  // small bucket: one CTA over peer-mapped memory (NVLink P2P)
+        dsc_oneshot_allreduce_kernel<<<1, 1024, 0, ctx->stream>>>((float*)id, (unsigned)count, ctx->xchg, ctx->rank, ctx->world);
+        CUDA_TRY(cudaGetLastError());
+        return DSC_OK;
+    }
     NCCL_TRY(g_nccl.AllReduce((const void*)id, (void*)id, count, ncclFloat32, ncclSum, ctx->comm, ctx->stream));
     return DSC_OK;
 }
@@ -525,6 +644,10 @@ int dsc_dp_allreduce_join(dsc_ctx* ctx) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->comm_join, 0));
     ctx->comm_pending = false;
+    return DSC_OK;
+}
+int dsc_dp_peer_memory_ready(dsc_ctx* ctx, int* ready) {
+    *ready = ctx->xchg_ready ? 1 : 0;
     return DSC_OK;
 }
 int dsc_dp_world(dsc_ctx* ctx, int* world, int* rank) {

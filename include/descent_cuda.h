@@ -124,6 +124,8 @@ int dsc_dp_allreduce_sum_f32(dsc_ctx* ctx, uint64_t id, size_t count); /* in pla
 /* the same on a side stream behind the work issued so far; the context's stream continues and waits at the join (both capturable) */
 int dsc_dp_allreduce_sum_f32_async(dsc_ctx* ctx, uint64_t id, size_t count);
 int dsc_dp_allreduce_join(dsc_ctx* ctx);
+/* 1 when small buckets (<= 256 KB) are reduced by the one-CTA kernel over CUDA-IPC peer-mapped memory instead of NCCL */
+int dsc_dp_peer_memory_ready(dsc_ctx* ctx, int* ready);
 int dsc_dp_world(dsc_ctx* ctx, int* world, int* rank);
 
 #ifdef __cplusplus
