@@ -117,7 +117,7 @@ class Graph:
         _check(lib.dsc_graphdef_write_dot_file(self._h, {"none": 0, "cluster": 1, "color": 2}[mode], path.encode()))
 
     def __del__(self):
-        if getattr(self, "_owned", False) and self._h:
+        if getattr(self, "_owned", False) and self._h and lib is not None:  # `lib` is None while the interpreter shuts down
             lib.dsc_graphdef_destroy(self._h)
             self._h = None
 
@@ -272,7 +272,7 @@ class Scope:
         self.env, self._h = env, handle
 
     def __del__(self):
-        if self._h:
+        if self._h and lib is not None:
             lib.dsc_scope_destroy(self._h)
             self._h = None
 

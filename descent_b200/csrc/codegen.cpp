@@ -1457,8 +1457,51 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
         out->pool_done = pooled;
         l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + (c.epilogue.empty() ? 4.0 * (double)(BC * M * N) : epi.bytes) +
                               (pooled ? 4.0 * (double)g.ops().nodes[c.outputs.back()].shape.element_count() : 0.0);
+        // the pooled kernel's input patch: is A a stride-1 window view over a (padded) image with per-axis address tables?
+        bool patch = false;
+        int64_t fh = 1, fw = 1, cin = 1, img_stride = 0, c_stride = 0;
+        std::vector<int64_t> ytab, xtab;
+        if (pooled) {
+            const int64_t H = pool.height, W = pool.width;
+            for (cin = 1; cin <= K && !patch; ++cin) {
+                if (K % cin != 0) continue;
+                for (fh = 1; fh <= K / cin && !patch; ++fh) {
+                    if ((K / cin) % fh != 0) continue;
+                    fw = K / cin / fh;
+                    if (fh * fw < 2 || (pool.window_h + fh - 1) * (pool.window_w + fw - 1) * cin > 64) continue;
+                    auto index = [&](int64_t image, int64_t y, int64_t x, int64_t fy, int64_t fx, int64_t ch) {
+                        return eval_chain(a.chain, ((image * H + y) * W + x) * K + (fy * fw + fx) * cin + ch);
+                    };
+                    const int64_t origin = index(0, 0, 0, 0, 0, 0);
+                    img_stride = pool.images > 1 ? index(1, 0, 0, 0, 0, 0) - origin : 0;
+                    c_stride = cin > 1 ? index(0, 0, 0, 0, 0, 1) - origin : 0;
+                    ytab.assign(H + fh - 1, 0);
+                    xtab.assign(W + fw - 1, 0);
+                    for (int64_t t = 0; t < H + fh - 1; ++t) ytab[t] = index(0, std::min(t, H - 1), 0, t - std::min(t, H - 1), 0, 0);
+                    for (int64_t t = 0; t < W + fw - 1; ++t) xtab[t] = index(0, 0, std::min(t, W - 1), 0, t - std::min(t, W - 1), 0) - origin;
+                    bool ok = true;
+                    for (int64_t image : {(int64_t)0, pool.images - 1})
+                        for (int64_t y = 0; y < H && ok; ++y)
+                            for (int64_t x = 0; x < W && ok; ++x)
+                                for (int64_t gk = 0; gk < K; ++gk) {
+                                    const int64_t fy = gk / (fw * cin), fx = (gk / cin) % fw, ch = gk % cin;
+                                    if (index(image, y, x, fy, fx, ch) != image * img_stride + ytab[y + fy] + xtab[x + fx] + ch * c_stride) { ok = false; break; }
+                                }
+                    if (ok) { patch = true; break; }
+                }
+                if (patch) break;
+            }
+        }
+        auto list = [](const std::vector<int64_t>& v) {
+            std::string t;
+            for (size_t i = 0; i < v.size(); ++i) t += (i ? ", " : "") + num(v[i]);
+            return t.empty() ? std::string("0") : t;
+        };
         if (pooled)
             out->source = subst(kThinRowsPoolTemplate, {{"LABEL", c.label}, {"NAME", name}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)},
+                                                       {"PATCH", patch ? "true" : "false"}, {"FH", num(patch ? fh : 1)}, {"FW", num(patch ? fw : 1)}, {"CIN", num(patch ? cin : 1)},
+                                                       {"IMG_H", num(pool.height)}, {"YTAB", patch ? list(ytab) : list(std::vector<int64_t>(pool.height, 0))},
+                                                       {"XTAB", patch ? list(xtab) : list(std::vector<int64_t>(pool.width, 0))}, {"IMG_STRIDE", num(img_stride)}, {"C_STRIDE", num(c_stride)},
                                                        {"POOL_H", num(pool.window_h)}, {"POOL_W", num(pool.window_w)}, {"IMG_W", num(pool.width)},
                                                        {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args},
                                                        {"A_CHAIN", ca.str()}, {"A_IDX", ia}, {"B_CHAIN", cb.str()}, {"B_IDX", ib}});
