@@ -204,3 +204,32 @@ def test_conv_backward_producers_are_evaluated_inside_the_gemm_loaders(built_lib
         assert "\n// PerElement (9 ops) [12845056]\n" not in source
         assert "\n// PerElement (9 ops) [6422528]\n" in source and "computed while loading: PerElement (9 ops) [6422528]" not in source
         assert built_library.nvrtc_compile(source) > 0
+
+
+def test_round2_fusions_in_the_conv_net_step(host_env):
+    """Cluster-level rewrites of round 2 on conv-net's training step: softmax cross-entropy is ONE row
+    kernel, every parameter update and running sum is ONE grouped launch on the last level, both max-pool forwards ride in
+    their convolution's cluster, and the step has at most 25 clusters (34 in round 1)."""
+    ex = host_env.example("conv-net", 1000)
+    clusters = ex.train_graph.export_json()["clusters"]
+    labels = [c["label"] for c in clusters]
+    rows = [l for l in labels if l.startswith("Row (")]
+    assert len(rows) == 1 and "[1000, 10]" in rows[0], labels
+    assert not any(l.startswith("Reduce (k=10)") for l in labels), labels           # the class-axis reductions are inside the row kernel
+    assert sum("+MaxPool" in l for l in labels) == 2 and not any(l.startswith("Reduce (k=4)") for l in labels), labels
+    last = max(c["level"] for c in clusters)
+    tail = [c for c in clusters if c["level"] == last]
+    assert len(tail) == 1 and tail[0]["label"].startswith("PerElementGroup (10 programs)"), [c["label"] for c in tail]  # 8 tensors + loss + accuracy
+    assert len(clusters) <= 25, len(clusters)
+    # the same pass on multi-hash: Adam's 16 tensors and the loss sum in one launch (the four 4096-row tables share a program)
+    mh = host_env.example("multi-hash", 4096).train_graph.export_json()["clusters"]
+    last = max(c["level"] for c in mh)
+    assert [c["label"].split(" [")[0] for c in mh if c["level"] == last] == ["PerElementGroup (14 programs)"]
+
+
+def test_kernels_refuse_arrays_beyond_32_bit_indexing(built_library, host_env):
+    """Generated kernels index with 32-bit integers: a per-GPU mini-batch whose activations exceed 2^31 elements
+    is refused with a message instead of wrapping."""
+    ex = host_env.example("conv-net", 200000)  # [m, 28, 28, 16] = 2.5e9 elements
+    with pytest.raises(built_library.DescentError, match="index with 32 bits"):
+        ex.train_graph.kernel_source()

@@ -154,3 +154,27 @@ def test_conv_net_step_at_benchmark_batch(env, m, precision):
     assert not failed, failed
     assert max_rel_err(env.read(ex.loss_sum), want[ex.loss_sum.id]) <= 1e-5
     np.testing.assert_array_equal(env.read(ex.accuracy_sum), want[ex.accuracy_sum.id])
+
+
+def test_options_changed_after_a_run_replan_the_graph(env):
+    """set_tf32 / set_sm_count after a graph has run used to be ignored silently (the plan was cached).  The
+    executor now plans the graph again under the new options: the kernel set changes, and both results match their oracle."""
+    ex = env.example("conv-net", 32, optimizer="descent")
+    rng = np.random.default_rng(3)
+    params = init_example_params(ex, rng)
+    params[ex.x.id], params[ex.y.id] = synthetic_batch(ex, rng)
+    upload(env, params)
+    env.run(ex.train_graph, 9)
+    strict_labels = [t["label"] for t in env.profile(ex.train_graph, 0, 1)]
+    assert not any(l.startswith("TensorCore") for l in strict_labels)
+    env.set_tf32(True)
+    nodes, tf32_labels = tensor_core_nodes(env, ex)
+    assert any(l.startswith("TensorCore") for l in tf32_labels), tf32_labels
+    env.set_sm_count(3)
+    grids = {t["label"]: t["grid"][0] for t in env.profile(ex.train_graph, 0, 1) if t["label"].startswith("TensorCore") and t["grid"][0] > 1}
+    assert grids and max(grids.values()) <= 3 * 8, grids  # persistent grids follow the overridden SM count
+    upload(env, params)
+    env.run(ex.train_graph, 9)
+    want = run_graph(ex.train_graph_json, params, 9, tf32=("trunc", nodes))
+    worst = {pid: max_rel_err(env.read(env.parameter(pid)), w) for pid, w in want.items()}
+    assert max(worst.values()) <= 1e-4, worst
