@@ -2131,17 +2131,17 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part({{SRC_PARAMS}}fl
 }
 
 // {{LABEL}}: accumulator + chunk partials in ascending chunk order
-extern "C" __global__ void __launch_bounds__(256) {{NAME}}_sum({{ACC_PARAM}}const float* partial, float* out0, const unsigned* dsc_step) {
-    // 32 table elements x 8 chunk lanes per CTA: lane g adds chunks g, g+8, ... in ascending order, then the eight
-    // lane sums are added to the accumulator in lane order -- a fixed order, independent of timing
+extern "C" __global__ void __launch_bounds__(1024) {{NAME}}_sum({{ACC_PARAM}}const float* partial, float* out0, const unsigned* dsc_step) {
+    // 32 table elements x 32 chunk lanes per CTA: lane g adds chunks g, g+32, ... in ascending order, then the lane sums
+    // are added to the accumulator in lane order -- a fixed order, independent of timing
     constexpr unsigned TOTAL = {{TOTAL}}u, NCHUNK = {{NBLOCKS}}u;
-    __shared__ float red[8][32];
+    __shared__ float red[32][33];
     const unsigned tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
     const unsigned e = blockIdx.x * 32u + tx;
     float part = 0.f;
     if (e < TOTAL) {
         #pragma unroll 4
-        for (unsigned c = ty; c < NCHUNK; c += 8u) part += partial[c * TOTAL + e];
+        for (unsigned c = ty; c < NCHUNK; c += 32u) part += partial[c * TOTAL + e];
     }
     red[ty][tx] = part;
     __syncthreads();
@@ -2149,8 +2149,102 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}_sum({{ACC_PARAM}}cons
 {{ACC_CHAIN}}
     float acc = {{ACC_VALUE}};
     #pragma unroll
-    for (unsigned g = 0; g < 8u; ++g) acc += red[g][tx];
+    for (unsigned g = 0; g < 32u; ++g) acc += red[g][tx];
     out0[e] = acc;
+}
+)";
+
+// Small tables (the hash-grid levels of image_fit: <= 4096 rows of 2 floats): the whole table lives in shared memory and
+// the sort shrinks from 1024 keys per CTA (55 compare-exchange stages, a dozen block barriers) to 32 keys per WARP (15
+// shuffle stages, no barrier).  Per round of 256 consecutive positions: every warp sorts its 32 (row, lane) keys, permutes
+// the values along, runs a segmented inclusive scan over the sorted lanes (equal rows are adjacent; a fixed shuffle tree),
+// and the last lane of each run holds that row's sum; the eight warps then add their sums to the table one warp after
+// the other (eight barriers), so every row sees the additions in (round, warp, position) order: run-to-run reproducible.
+// The next round's indices and values are loaded before the current one is processed.
+const char* kScatterWarpTemplate = R"(
+// {{LABEL}}: per-warp sorted partial sums into a shared-memory table ({{NSRC}} chained source(s))
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part({{SRC_PARAMS}}float* partial, const unsigned* dsc_step) {
+    constexpr unsigned ROWS = {{ROWS}}u, INNER = {{INNER}}u, OUTER = {{OUTER}}u;
+    constexpr unsigned NROUND = {{NROUND}}u, RPB = {{RPB}}u;  // rounds of 256 positions in total (every source padded to whole rounds), rounds per CTA
+    constexpr unsigned RPI = 4u;  // rounds sorted per iteration: the eight ordered accumulation phases (block barriers) are paid once for all of them
+    constexpr unsigned NONE = 0xffffffffu;
+    __shared__ float table[ROWS * INNER];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, outer = blockIdx.y;
+    for (unsigned i = tid; i < ROWS * INNER; i += 256u) table[i] = 0.f;
+    __syncthreads();
+    // index and values of this thread's position in `round` (both loads are issued together; a row outside the table drops the position)
+    auto load_round = [&](unsigned round, unsigned& row, float (&val)[INNER]) {
+        row = NONE;
+        #pragma unroll
+        for (unsigned w = 0; w < INNER; ++w) val[w] = 0.f;
+        if (round >= NROUND) return;
+{{LOAD}}
+        if (row >= ROWS) row = NONE;
+    };
+    const unsigned first = blockIdx.x * RPB, last = min(NROUND, first + RPB);
+    unsigned row[RPI], next_row[RPI];
+    float val[RPI][INNER], next_val[RPI][INNER];
+    #pragma unroll
+    for (unsigned i = 0; i < RPI; ++i) load_round(first + i < last ? first + i : NROUND, row[i], val[i]);
+    for (unsigned round = first; round < last; round += RPI) {
+        #pragma unroll
+        for (unsigned i = 0; i < RPI; ++i) load_round(round + RPI + i < last ? round + RPI + i : NROUND, next_row[i], next_val[i]);
+        unsigned srow[RPI];
+        float v[RPI][INNER];
+        bool tail[RPI];
+        #pragma unroll
+        for (unsigned i = 0; i < RPI; ++i) {
+            // sort the warp's (row, lane) keys: unique, so the order is fully determined (row, then position)
+            unsigned key = row[i] == NONE ? NONE : row[i] * 32u + lane;
+            #pragma unroll
+            for (unsigned k = 2; k <= 32u; k <<= 1) {
+                #pragma unroll
+                for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                    const unsigned other = __shfl_xor_sync(0xffffffffu, key, j);
+                    const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+                    key = keep_min ? min(key, other) : max(key, other);
+                }
+            }
+            srow[i] = key == NONE ? NONE : key >> 5;
+            const unsigned src = key & 31u;
+            #pragma unroll
+            for (unsigned w = 0; w < INNER; ++w) v[i][w] = __shfl_sync(0xffffffffu, val[i][w], src);
+            // segmented inclusive scan over the sorted lanes (equal rows are adjacent)
+            #pragma unroll
+            for (unsigned d = 1; d < 32u; d <<= 1) {
+                const unsigned r_up = __shfl_up_sync(0xffffffffu, srow[i], d);
+                #pragma unroll
+                for (unsigned w = 0; w < INNER; ++w) {
+                    const float v_up = __shfl_up_sync(0xffffffffu, v[i][w], d);
+                    if (lane >= d && r_up == srow[i]) v[i][w] += v_up;
+                }
+            }
+            const unsigned r_down = __shfl_down_sync(0xffffffffu, srow[i], 1);
+            tail[i] = srow[i] != NONE && (lane == 31u || r_down != srow[i]);
+        }
+        // warps add their run sums one warp after the other, rounds in order inside a warp's turn: a fixed order per table row
+        #pragma unroll
+        for (unsigned phase = 0; phase < 8u; ++phase) {
+            if (warp == phase) {
+                #pragma unroll
+                for (unsigned i = 0; i < RPI; ++i) {
+                    if (tail[i]) {
+                        #pragma unroll
+                        for (unsigned w = 0; w < INNER; ++w) table[srow[i] * INNER + w] += v[i][w];
+                    }
+                    __syncwarp();  // two rounds of one warp may end runs of the same row
+                }
+            }
+            __syncthreads();
+        }
+        #pragma unroll
+        for (unsigned i = 0; i < RPI; ++i) {
+            row[i] = next_row[i];
+            #pragma unroll
+            for (unsigned w = 0; w < INNER; ++w) val[i][w] = next_val[i][w];
+        }
+    }
+    for (unsigned i = tid; i < ROWS * INNER; i += 256u) partial[(blockIdx.x * OUTER + outer) * ROWS * INNER + i] = table[i];
 }
 )";
 
@@ -2194,6 +2288,29 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
         bytes += chain_bytes(g, values) + chain_bytes(g, indices);
     }
     const int64_t nchunk_total = chunk_base;
+    // warp-sorted form for tables that fit in shared memory (see kScatterWarpTemplate)
+    const bool warp_form = rows * inner <= 8192 && inner <= 8 && rows * 32 < (int64_t)0xffffffffLL;
+    std::ostringstream warp_load;
+    int64_t nround_total = 0;
+    if (warp_form) {
+        int wuniq = 0;
+        for (int s = 0; s < nsrc; ++s) {
+            const ClusterInput& values = c.inputs[2 * s];
+            const ClusterInput& indices = c.inputs[2 * s + 1];
+            const int64_t count = values.arg_shape[axis];
+            const int64_t nround = div_round_up(count, 256);
+            warp_load << "        if (round >= " << unum(nround_total) << " && round < " << unum(nround_total + nround) << ") {\n"
+                      << "            const unsigned pos = (round - " << unum(nround_total) << ") * 256u + tid;\n"
+                      << "            if (pos < " << unum(count) << ") {\n                const unsigned e = pos;\n";
+            std::string ii = emit_chain(warp_load, indices.chain, "e", wuniq, "                ");
+            warp_load << "                row = (unsigned)__float_as_int(indices" << s << "[" << ii << "]);\n"
+                      << "                #pragma unroll\n                for (unsigned w = 0; w < INNER; ++w) {\n"
+                      << "                    const unsigned e = (outer * " << unum(count) << " + pos) * INNER + w;\n";
+            std::string vi = emit_chain(warp_load, values.chain, "e", wuniq, "                    ");
+            warp_load << "                    val[w] = values" << s << "[" << vi << "];\n                }\n            }\n        }\n";
+            nround_total += nround;
+        }
+    }
     std::ostringstream ac;
     std::string acc_value;
     if (acc_literal) acc_value = "__uint_as_float(" + num(acc_node.op.literal_bits) + "u)";
@@ -2201,9 +2318,29 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
     const std::string name = "k" + num(ci);
     // small tables are accumulated in shared memory, several chunks per CTA (two waves of CTAs at least)
     const bool table = rows * inner <= 8192;
-    const int64_t cpb = table ? std::max<int64_t>(1, std::min<int64_t>(8, nchunk_total / (2 * opt.sm_count))) : 1;
-    const int64_t nblocks = div_round_up(nchunk_total, cpb);
+    int64_t cpb = table ? std::max<int64_t>(1, std::min<int64_t>(8, nchunk_total / (2 * opt.sm_count))) : 1;
+    int64_t nblocks = div_round_up(nchunk_total, cpb);
     ClusterCode code;
+    if (warp_form) {
+        // CTAs: enough to fill the machine, but each writes a whole table as its partial, so no more than the operands weigh
+        const int64_t data_bytes = (int64_t)(bytes - 2.0 * 4.0 * (double)total);
+        int64_t want = std::max<int64_t>(opt.sm_count, std::min<int64_t>(4 * (int64_t)opt.sm_count, data_bytes / std::max<int64_t>(1, total * 4)));
+        want = std::min<int64_t>(want, nround_total);
+        const int64_t rpb = div_round_up(nround_total, std::max<int64_t>(1, want));
+        nblocks = div_round_up(nround_total, rpb);
+        cpb = rpb;
+        code.source = subst(kScatterWarpTemplate, {{"LABEL", c.label}, {"NAME", name}, {"NSRC", num(nsrc)}, {"SRC_PARAMS", params.str()}, {"ROWS", num(rows)},
+                                                   {"INNER", num(inner)}, {"OUTER", num(outer)}, {"NROUND", num(nround_total)}, {"RPB", num(rpb)}, {"LOAD", warp_load.str()}});
+        // the ordered sum of the partials is the second kernel of the other template: emit only that half
+        std::string both = subst(kScatterTemplate,
+                        {{"LABEL", c.label}, {"NAME", name}, {"NSRC", num(nsrc)}, {"SRC_PARAMS", params.str()}, {"CH", num(ch)}, {"ROWS", num(rows)},
+                         {"INNER", num(inner)}, {"OUTER", num(outer)}, {"LOAD_KEYS", load_keys.str()}, {"LOAD_VALUES", load_values.str()},
+                         {"ACC_PARAM", acc_literal ? "" : "const float* acc_in, "}, {"TOTAL", num(total)}, {"NCHUNK", num(nchunk_total)}, {"NBLOCKS", num(nblocks)},
+                         {"CPB", num(cpb)}, {"TABLE", "true"}, {"ACC_CHAIN", ac.str()}, {"ACC_VALUE", acc_value}});
+        const size_t at = both.find("// " + c.label + ": accumulator + chunk partials");
+        DSC_CHECK(at != std::string::npos, "scatter template layout changed");
+        code.source += both.substr(at);
+    } else
     code.source = subst(kScatterTemplate,
                         {{"LABEL", c.label}, {"NAME", name}, {"NSRC", num(nsrc)}, {"SRC_PARAMS", params.str()}, {"CH", num(ch)}, {"ROWS", num(rows)},
                          {"INNER", num(inner)}, {"OUTER", num(outer)}, {"LOAD_KEYS", load_keys.str()}, {"LOAD_VALUES", load_values.str()},
@@ -2236,6 +2373,7 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
     KernelLaunch sm;
     sm.entry = name + "_sum";
     sm.grid_x = (uint32_t)div_round_up(total, 32);
+    sm.block = 1024;
     sm.label = "ScatterSum " + node.shape.str();
     sm.cluster = ci;
     if (!acc_literal) sm.args.push_back({KernelArg::NodeBuffer, c.copy_from, 0});
