@@ -865,6 +865,56 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws, floa
 }
 )";
 
+// The same for TWO independent sets of partials in one launch (a weight gradient's partial products and the bias column
+// sums its kernel produced on the side): the first blocks own set 0, the rest set 1; identical order of additions.
+const char* kSplitSumPairTemplate = R"(
+// split-K partial sums of {{LABEL}} and of its column sums, one launch
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* ws0, float* dst0, const float* ws1, float* dst1, const unsigned* dsc_step) {
+    constexpr unsigned COUNT0 = {{COUNT0}}u, COUNT1 = {{COUNT1}}u, S = {{S}}u, BLOCKS0 = (COUNT0 + 31u) / 32u;
+    __shared__ float red[8][32];
+    const bool second = blockIdx.x >= BLOCKS0;
+    const float* ws = second ? ws1 : ws0;
+    float* out0 = second ? dst1 : dst0;
+    const unsigned COUNT = second ? COUNT1 : COUNT0;
+    const unsigned tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;
+    const unsigned i = (second ? blockIdx.x - BLOCKS0 : blockIdx.x) * 32u + tx;
+    float part = 0.f;
+    if (i < COUNT) {
+        #pragma unroll 4
+        for (unsigned s = ty; s < S; s += 8u) part += ws[s * COUNT + i];
+    }
+    red[ty][tx] = part;
+    __syncthreads();
+    if (ty != 0 || i >= COUNT) return;
+    float acc = red[0][tx];
+    #pragma unroll
+    for (unsigned g = 1; g < 8u; ++g) acc += red[g][tx];
+    out0[i] = acc;
+}
+)";
+
+// launches that add the S partials of a product (scratch offset 0 -> product_node) and, when the kernel also produced
+// column-sum partials (scratch colsum_offset -> colsum_node), both in one kernel
+void emit_split_sums(ClusterCode* out, const std::string& name, int ci, const std::string& label, int64_t S, int64_t out_count, int product_node,
+                     bool colsum, int64_t colsum_count, int64_t colsum_offset, int colsum_node) {
+    KernelLaunch s;
+    s.cluster = ci;
+    if (colsum) {
+        s.entry = name + "_splitsums";
+        out->source += subst(kSplitSumPairTemplate, {{"LABEL", label}, {"NAME", s.entry}, {"COUNT0", num(out_count)}, {"COUNT1", num(colsum_count)}, {"S", num(S)}});
+        s.grid_x = (uint32_t)(div_round_up(out_count, 32) + div_round_up(colsum_count, 32));
+        s.label = "SplitSum (+ column sums) " + label;
+        s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, product_node, 0}, {KernelArg::Scratch, -1, colsum_offset}, {KernelArg::NodeBuffer, colsum_node, 0}};
+    } else {
+        s.entry = name + "_splitsum";
+        out->source += subst(kSplitSumTemplate, {{"LABEL", label}, {"NAME", s.entry}, {"COUNT", num(out_count)}, {"S", num(S)}});
+        s.grid_x = (uint32_t)div_round_up(out_count, 32);
+        s.label = "SplitSum " + label;
+        s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, product_node, 0}};
+    }
+    out->launches.push_back(s);
+}
+
 struct GemmTile { int bm, bn, bk, tm, tn, nt; };
 
 GemmTile choose_gemm_tile(int64_t M, int64_t N) {
@@ -1400,28 +1450,11 @@ bool gen_conv_weight_gradient(const Graph& g, const Cluster& c, int ci, const Co
     l.flops = 2.0 * (double)G * (double)KW * (double)NCO * (double)MPIX;
     out->launches.push_back(l);
     out->scratch_bytes = S * out_count * 4;
-    const std::string sname = name + "_splitsum";
-    out->source += subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
-    KernelLaunch s;
-    s.entry = sname;
-    s.grid_x = (uint32_t)div_round_up(out_count, 32);
-    s.label = "SplitSum " + c.label;
-    s.cluster = ci;
-    s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
-    out->launches.push_back(s);
     if (colsum) {
         out->column_sum_done = true;
         out->scratch_bytes = colsum_offset + S * G * NCO * 4;
-        const std::string cname = name + "_colsum";
-        out->source += subst(kSplitSumTemplate, {{"LABEL", "column sums of " + c.label}, {"NAME", cname}, {"COUNT", num(G * NCO)}, {"S", num(S)}});
-        KernelLaunch cs;
-        cs.entry = cname;
-        cs.grid_x = (uint32_t)div_round_up(G * NCO, 32);
-        cs.label = "SplitSum column sums " + c.label;
-        cs.cluster = ci;
-        cs.args = {{KernelArg::Scratch, -1, colsum_offset}, {KernelArg::NodeBuffer, c.outputs[1], 0}};
-        out->launches.push_back(cs);
     }
+    emit_split_sums(out, name, ci, c.label, S, out_count, c.outputs[0], colsum, G * NCO, colsum_offset, colsum ? c.outputs[1] : -1);
     return true;
 }
 
@@ -1558,27 +1591,8 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
             bind_operand_loads(l, out, nullptr, &lb);
             out->launches.push_back(l);
             out->scratch_bytes = S * out_count * 4;
-            if (colsum) {
-                out->scratch_bytes = colsum_offset + S * BC * N * 4;
-                const std::string cname = name + "_colsum";
-                out->source += subst(kSplitSumTemplate, {{"LABEL", "column sums of " + c.label}, {"NAME", cname}, {"COUNT", num(BC * N)}, {"S", num(S)}});
-                KernelLaunch cs;
-                cs.entry = cname;
-                cs.grid_x = (uint32_t)div_round_up(BC * N, 32);
-                cs.label = "SplitSum column sums " + c.label;
-                cs.cluster = ci;
-                cs.args = {{KernelArg::Scratch, -1, colsum_offset}, {KernelArg::NodeBuffer, c.outputs[1], 0}};
-                out->launches.push_back(cs);
-            }
-            const std::string sname = name + "_splitsum";
-            out->source += subst(kSplitSumTemplate, {{"LABEL", c.label}, {"NAME", sname}, {"COUNT", num(out_count)}, {"S", num(S)}});
-            KernelLaunch s;
-            s.entry = sname;
-            s.grid_x = (uint32_t)div_round_up(out_count, 32);
-            s.label = "SplitSum " + c.label;
-            s.cluster = ci;
-            s.args = {{KernelArg::Scratch, -1, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
-            out->launches.push_back(s);
+            if (colsum) out->scratch_bytes = colsum_offset + S * BC * N * 4;
+            emit_split_sums(out, name, ci, c.label, S, out_count, c.outputs[0], colsum, BC * N, colsum_offset, colsum ? c.outputs[1] : -1);
         } else {
             l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
             l.args.push_back(colsum_arg);
@@ -1726,7 +1740,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
         const int64_t target = (int64_t)opt.sm_count * (tc ? 4 : std::max(2, std::min(8, 1024 / t.nt)));
         const int64_t in_elems = a.chain.addressed_count() + b.chain.addressed_count();
         S = 1;
-        if (tiles * 2 <= target && K >= 8 * t.bk) {
+        if (tiles * 2 <= target && K >= std::max<int64_t>(8 * t.bk, 512)) {  // a split costs a second launch and a workspace round trip: not for short reductions
             S = std::min<int64_t>(div_round_up(target, tiles), K / (4 * t.bk));
             S = std::min<int64_t>(S, std::max<int64_t>(1, in_elems / (4 * out_count)));
         }

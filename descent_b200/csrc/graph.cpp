@@ -1177,6 +1177,9 @@ void Graph::build_clusters() {
         for (auto [dst, k] : cons[id])
             if (ops_.nodes[dst].alive) lv = std::min(lv, level[dst] - edge_cost(dst, ops_.nodes[dst].in[k]));
         if (lv == INT32_MAX || node.op.kind == OpKind::AllReduce || node.op.kind == OpKind::Input) lv = asap[id];
+        // scalars (the step counter, Adam's bias-corrected step size) cost nothing to keep alive: computed as early as
+        // possible they share one kernel instead of one per level
+        if (node.op.is_per_element() && node.shape.element_count() == 1) lv = asap[id];
         DSC_CHECK(lv >= asap[id], "level inversion");
         level[id] = lv;
     }

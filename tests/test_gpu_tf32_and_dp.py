@@ -19,11 +19,12 @@ from oracle import run_graph
 pytestmark = pytest.mark.gpu
 TF32_LOSS_TOL = 2e-3  # measured 3.2e-4
 TF32_PARAM_TOL = 1.5e-1  # measured 1.4e-2 .. 5.3e-2 (Adam steps of near-zero gradients flip sign)
-# conv-net, 100 Adam steps at m = 256 (calibration run, B200): loss 2.4e-4, accuracy sum 1.3 %, parameters 0.0055 .. 0.38 of
-# max|theta| in the maximum norm (the dense layers; see the test's docstring for why Adam makes that norm meaningless)
-CONV_NET_TF32_PARAM_TOL = 6e-1
-CONV_NET_TF32_PARAM_RMS_TOL = 3e-1
-CONV_NET_TF32_ACCURACY_TOL = 3e-2
+# conv-net, 100 Adam steps at m = 256 (calibration run on a B200, scripts/debug/calibrate_tf32_contract.py; the test's docstring
+# explains the yardstick): strict path rms drift 0.001 .. 0.19 per tensor, TF32 path 0.0027 .. 0.32, ratios 1.05 .. 5.3
+CONV_NET_TF32_DRIFT_FACTOR = 4.0
+CONV_NET_TF32_DRIFT_FLOOR = 1e-2
+CONV_NET_TF32_PARAM_RMS_CAP = 6e-1
+CONV_NET_TF32_ACCURACY_TOL = 5e-2
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -122,43 +123,59 @@ def test_tf32_view_chain_gemms_match_tf32_oracle(env, network, m, tol):
     assert abs(env.read_parameter_scalar(ex.loss_sum) - float(want[ex.loss_sum.id][0])) <= 1e-5 * abs(float(want[ex.loss_sum.id][0]))
 
 
-def test_tf32_conv_net_100_steps_within_stated_tolerance(env):
+def test_tf32_conv_net_100_steps_within_stated_tolerance(env, built_library):
     """BASELINE.json: "within a stated TF32 tolerance on loss and parameters after N steps for tensor-core GEMMs", stated on
     the headline network.  N = 100 Adam steps of conv-net at m = 256 (fresh synthetic batch and dropout seed every step)
-    on the tensor-core path, against the STRICT oracle (oracle.cpu_ref: float32 sums like the reference's kernels) fed the
-    same batches and seeds.  Tolerances (measured values are printed):
-      * accumulated loss over the 100 steps: 2e-3 relative (SURVEY.md section 8d proposal);
-      * every parameter tensor: CONV_NET_TF32_PARAM_TOL * max|theta|.  Adam normalises each step to ~lr whatever the
-        gradient's size, so an entry whose gradient is a cancellation residue moves by +-lr per step in either
-        implementation: after 100 steps of lr = 0.005 the two trajectories may differ by a sizeable fraction of 100 * lr on
-        such entries while the loss agrees to 1e-3 -- which is why the bound is stated relative to max|theta| and is not 5e-3."""
+    on the GPU twice -- strict FP32 kernels and TF32 tensor-core operands -- and in the STRICT oracle (oracle.cpu_ref: float32
+    sums like the reference's kernels), all fed the same batches and seeds.  The contract:
+      * accumulated loss over the 100 steps: strict path 1e-4 relative (measured 4e-6), TF32 path 2e-3 (measured 2.4e-4;
+        SURVEY.md section 8d proposal);
+      * accumulated accuracy count: 5e-2 relative, both paths (measured 0.6 % / 2.0 %);
+      * parameters: Adam normalises each step to ~lr whatever the gradient's size, so an entry whose gradient is a
+        cancellation residue moves by +-lr per step in either implementation, and after 100 steps two FP32 implementations
+        that differ only in summation order already disagree by up to 0.19 of a tensor's norm (the last layer's 10 biases;
+        0.001-0.04 elsewhere) while their losses agree to 4e-6.  A bound on TF32 relative to the oracle alone would
+        therefore measure Adam, not TF32: the yardstick is the strict GPU path's own drift on the same run.  Per tensor,
+        |theta_tf32 - theta_oracle|_2 / |theta_oracle|_2 <= CONV_NET_TF32_DRIFT_FACTOR * (the strict path's figure) +
+        CONV_NET_TF32_DRIFT_FLOOR (measured ratios 1.05 .. 5.3, the largest on a tensor whose strict drift is 0.001), and
+        never above CONV_NET_TF32_PARAM_RMS_CAP."""
     from oracle import cpu_ref
-    env.set_tf32(True)
     m, steps = 256, 100
-    ex = env.example("conv-net", m)
+    runs = {}
+    for mode in ("strict", "tf32"):
+        e = built_library.Environment(0) if mode == "tf32" else env
+        e.set_tf32(mode == "tf32")
+        runs[mode] = (e, e.example("conv-net", m))
+    ex = runs["strict"][1]
     rng = np.random.default_rng(77)
     params = init_example_params(ex, rng)
-    upload(env, params)
+    for e, _ in runs.values():
+        upload(e, params)
     program = cpu_ref.Program(ex.train_graph_json)
     state = {pid: np.ascontiguousarray(v, np.float32) for pid, v in params.items()}
     for step in range(steps):
         x, y = synthetic_batch(ex, rng)
         seed = int(rng.integers(0, 2 ** 32))
-        env.write(ex.x, x)
-        env.write(ex.y, y)
-        env.run(ex.train_graph, seed)
+        for e, exm in runs.values():
+            e.write(exm.x, x)
+            e.write(exm.y, y)
+            e.run(exm.train_graph, seed)
         state[ex.x.id], state[ex.y.id] = x, y
         out, _ = program.run(state, seed)
         state.update({pid: v.copy() for pid, v in out.items()})
     program.close()
-    got, want = env.read_parameter_scalar(ex.loss_sum), float(state[ex.loss_sum.id].reshape(-1)[0])
-    drift = {p.name() + "#%d" % p.id: max_rel_err(env.read(p), state[p.id]) for p in ex.parameters}
-    rms = {p.name() + "#%d" % p.id: float(np.linalg.norm(env.read(p).astype(np.float64) - state[p.id]) / np.linalg.norm(state[p.id].astype(np.float64))) for p in ex.parameters}
-    acc_got, acc_want = env.read_parameter_scalar(ex.accuracy_sum), float(state[ex.accuracy_sum.id].reshape(-1)[0])
-    print("conv-net tf32 vs strict oracle after %d steps: loss %.6g vs %.6g (rel %.3g), accuracy sum %g vs %g, parameter drift max / max|theta| %s, "
-          "|d theta|_2 / |theta|_2 %s" % (steps, got, want, abs(got - want) / abs(want), acc_got, acc_want, {k: "%.3g" % v for k, v in drift.items()},
-                                         {k: "%.3g" % v for k, v in rms.items()}))
-    assert abs(got - want) <= TF32_LOSS_TOL * abs(want), (got, want)
-    assert abs(acc_got - acc_want) <= CONV_NET_TF32_ACCURACY_TOL * acc_want, (acc_got, acc_want)
-    assert max(rms.values()) <= CONV_NET_TF32_PARAM_RMS_TOL, rms
-    assert max(drift.values()) <= CONV_NET_TF32_PARAM_TOL, drift
+    want, acc_want = float(state[ex.loss_sum.id].reshape(-1)[0]), float(state[ex.accuracy_sum.id].reshape(-1)[0])
+    rms, loss_err, acc_err = {}, {}, {}
+    for mode, (e, exm) in runs.items():
+        loss_err[mode] = abs(e.read_parameter_scalar(exm.loss_sum) - want) / abs(want)
+        acc_err[mode] = abs(e.read_parameter_scalar(exm.accuracy_sum) - acc_want) / acc_want
+        rms[mode] = {p.name() + "#%d" % p.id: float(np.linalg.norm(e.read(p).astype(np.float64) - state[p.id]) / np.linalg.norm(state[p.id].astype(np.float64)))
+                     for p in exm.parameters}
+        print("conv-net %s vs strict oracle after %d steps: loss rel %.3g, accuracy rel %.3g, |d theta|_2 / |theta|_2 %s" %
+              (mode, steps, loss_err[mode], acc_err[mode], {k: "%.3g" % v for k, v in rms[mode].items()}))
+    assert loss_err["strict"] <= 1e-4 and loss_err["tf32"] <= TF32_LOSS_TOL, loss_err
+    assert max(acc_err.values()) <= CONV_NET_TF32_ACCURACY_TOL, acc_err
+    for name, v in rms["tf32"].items():
+        assert v <= CONV_NET_TF32_DRIFT_FACTOR * rms["strict"][name] + CONV_NET_TF32_DRIFT_FLOOR, (name, v, rms["strict"][name])
+        assert v <= CONV_NET_TF32_PARAM_RMS_CAP, (name, v)
+    runs["tf32"][0].close()
