@@ -173,7 +173,12 @@ int dsc_env_profile(dsc_env* env, dsc_graphdef* graph, uint32_t rand_seed, int i
         os << "[";
         for (size_t i = 0; i < timings.size(); ++i) {
             const auto& t = timings[i];
-            os << (i ? "," : "") << "{\"label\":\"" << t.label << "\",\"entry\":\"" << t.entry << "\",\"cluster\":" << t.cluster << ",\"ms\":" << t.ms
+            os << (i ? "," : "") << "{\"label\":\"" << t.label << "\",\"entry\":\"" << t.entry << "\",\"cluster\":" << t.cluster << ",\"clusters\":[" << [&] {
+                      std::string list;
+                      if (t.covers.empty()) list = std::to_string(t.cluster);
+                      for (size_t k = 0; k < t.covers.size(); ++k) list += (k ? "," : "") + std::to_string(t.covers[k]);
+                      return list;
+                  }() << "],\"ms\":" << t.ms
                << ",\"bytes\":" << t.algorithmic_bytes << ",\"flops\":" << t.flops << ",\"grid\":[" << t.grid[0] << "," << t.grid[1] << "," << t.grid[2]
                << "],\"block\":" << t.block << ",\"smem\":" << t.smem << "}";
         }

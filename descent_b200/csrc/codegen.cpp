@@ -265,6 +265,10 @@ std::string op_expression(const PerElementOp& op, const std::function<std::strin
 // The straight-line program of a per-element cluster for element `e` (statements `const float t<i> = ...;`).
 // Inputs flagged in `vector_load` were fetched as `vin<i>[v]`; input `register_input` (if >= 0) is not in memory
 // at all: its value for this element is `acc[v]` (a GEMM epilogue evaluating the cluster on its accumulator).
+// `g_load_override`, when set, may name the value of an input that is not in memory at all (dense chains: the accumulator
+// element, the activation held in shared memory); an empty answer means "load it as usual".
+std::function<std::string(int)>* g_load_override = nullptr;
+
 void emit_per_element_ops(std::ostringstream& os, const Cluster& c, const CodegenOptions& opt, int& uniq, const std::vector<bool>& vector_load,
                           int register_input) {
     for (size_t oi = 0; oi < c.ops.size(); ++oi) {
@@ -274,7 +278,10 @@ void emit_per_element_ops(std::ostringstream& os, const Cluster& c, const Codege
         switch (op.kind) {
             case PerElementOp::Load: {
                 const auto& in = c.inputs[op.input_index];
-                if (op.input_index == register_input) {
+                const std::string named = g_load_override ? (*g_load_override)(op.input_index) : std::string();
+                if (!named.empty()) {
+                    os << "    const float " << t << " = " << named << ";\n";
+                } else if (op.input_index == register_input) {
                     os << "    const float " << t << " = acc[v];\n";
                 } else if (vector_load[op.input_index]) {
                     os << "    const float " << t << " = vin" << op.input_index << "[v];\n";
@@ -2397,6 +2404,520 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
     return code;
 }
 
+// ---- dense chains (graph.hpp DenseChain): a whole MLP training step per 128-row tile in ONE kernel -----------------
+// SURVEY.md section 8f-1 (examples/image_fit/main.rs:50-118,259-275; module.rs:70-90).  One persistent CTA per SM walks
+// 128-row tiles of the batch.  Per tile, in order: the forward layers (tcgen05 TF32 MMAs, accumulator in TMEM, the
+// layer's bias + activation program evaluated on the accumulator, the activation written back to SHARED memory in the
+// two layouts the next MMAs read: K-major for the next layer's A operand, MN-major for the weight gradient), the loss
+// program, then for every layer from the last to the first the weight-gradient MMAs x_l^T dz_l (accumulated in TMEM
+// across all tiles of the CTA) and the backward product dz_l W_l^T with the activation-backward program as its epilogue
+// (dz_{l-1} overwrites x_l's MN-major copy in place, after reading it for the activation's sign).  Activations and their
+// gradients never reach HBM: the kernel reads x_0 and the loss target, and writes the gradient with respect to x_0, one
+// partial weight gradient / bias gradient / loss sum per CTA (added by a fixed-order split-sum launch).
+// Weights live in shared memory for the whole kernel in both orientations (W_l^T as the forward B operand, W_l as the
+// backward one), K-major without swizzle; MN-major operands use SWIZZLE_128B_BASE32B, the one MN-major layout tf32
+// accepts (gemm_tc_template.inc).  All MMAs are M = 128: the weight gradients put the wider of (x_l, dz_l) on the
+// accumulator lanes.  Bias gradients are exact FP32 column sums (warp transpose-reduction of the epilogue registers),
+// not tensor-core products.
+const char* kDenseChainHelpers = R"(
+#ifndef DSC_DENSE_CHAIN_HELPERS
+#define DSC_DENSE_CHAIN_HELPERS
+// K-major operand without swizzle: 8-row x 16-byte core matrices, k-chunk (4 floats) stride lbo, 8-row group stride 128
+__device__ __forceinline__ unsigned dc_km(unsigned lbo, int r, int c) {
+    return (unsigned)(c >> 2) * lbo + (unsigned)(r >> 3) * 128u + (unsigned)(r & 7) * 16u + (unsigned)(c & 3) * 4u;
+}
+// MN-major operand, SWIZZLE_128B_BASE32B, 128 k (the tile's rows): 128-byte rows of 32 mn, 4 k per 512-byte atom,
+// 32-byte chunks XOR-ed with (k mod 4), 32-mn block stride 16384
+__device__ __forceinline__ unsigned dc_mn(int mn, int k) {
+    return (unsigned)(mn >> 5) * 16384u + (unsigned)(k >> 2) * 512u + (unsigned)(k & 3) * 128u + (((((unsigned)mn & 31u) >> 3) ^ ((unsigned)k & 3u)) << 5) +
+           (unsigned)(mn & 7) * 4u;
+}
+__device__ __forceinline__ unsigned long long dc_desc(unsigned addr, unsigned lbo, unsigned sbo, unsigned mn_major) {
+    return (unsigned long long)((addr >> 4) & 0x3fffu) | ((unsigned long long)((lbo >> 4) & 0x3fffu) << 16) | ((unsigned long long)((sbo >> 4) & 0x3fffu) << 32) |
+           (1ull << 46) | ((unsigned long long)mn_major << 61);
+}
+__device__ __forceinline__ void dc_mma(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void dc_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void dc_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DC_DONE;\n"
+        "bra DC_WAIT;\n"
+        "DC_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void dc_ld16(unsigned taddr, float (&v)[16]) {
+    unsigned u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]),
+          "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
+}
+// Every lane holds 16 values (one row, 16 columns).  Returns in every lane the sum over the warp's 32 rows of column
+// dc_colsum16_column(lane): a fixed tree of additions (lanes 16 apart first, then 8, 4, 2, 1).
+__device__ __forceinline__ float dc_colsum16(const float (&o)[16], int lane) {
+    float a[8], b[4], c[2];
+    bool hi = (lane & 16) != 0;
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (hi ? o[i + 8] : o[i]) + __shfl_xor_sync(0xffffffffu, hi ? o[i] : o[i + 8], 16);
+    hi = (lane & 8) != 0;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = (hi ? a[i + 4] : a[i]) + __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[i + 4], 8);
+    hi = (lane & 4) != 0;
+    #pragma unroll
+    for (int i = 0; i < 2; ++i) c[i] = (hi ? b[i + 2] : b[i]) + __shfl_xor_sync(0xffffffffu, hi ? b[i] : b[i + 2], 4);
+    hi = (lane & 2) != 0;
+    float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, hi ? c[0] : c[1], 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+__device__ __forceinline__ int dc_colsum16_column(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+#endif
+)";
+
+}  // namespace
+
+bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const CodegenOptions& opt, ClusterCode* out) {
+    if (!opt.use_tf32) return false;
+    const auto& clusters = g.clusters();
+    const int L = (int)ch.forward.size();
+    const int64_t M = ch.rows;
+    auto up = [](int64_t v, int64_t a) { return (v + a - 1) / a * a; };
+    std::vector<int64_t> W = ch.widths;  // W[l] = input width of layer l, W[l + 1] = its output width
+    for (int l = 1; l < L; ++l)
+        if (W[l] % 16 != 0 || W[l] > 128) return false;   // hidden activations are MMA K and N dimensions and 16-column epilogue chunks
+    if (W[0] > 128 || W[L] > 128 || M >= ((int64_t)1 << 31) / 128) return false;
+    const bool has_dx = ch.backward[0] >= 0;
+    const int ci = ch.last_cluster();
+    const std::string name = "k" + num(ci);
+
+    // ---- shared memory plan -------------------------------------------------------------------------------------------
+    // MN-major buffers first (an A operand narrower than 128 lets the MMA read up to 48 KB past its buffer: harmless
+    // values on accumulator lanes nobody reads, but the addresses must exist), then the two K-major slots, the weights
+    int64_t off = 0;
+    std::vector<int64_t> mn_act(L), km_lbo_w_f(L), km_lbo_w_b(L), wf(L), wb(L, -1);
+    for (int l = 0; l < L; ++l) { mn_act[l] = off; off += up(W[l], 32) / 32 * 16384; }
+    const int64_t mn_dy = off;
+    off += up(W[L], 32) / 32 * 16384;
+    const int64_t mn_end = off;
+    int64_t km_chunks = 0;
+    for (int l = 0; l < L; ++l) km_chunks = std::max(km_chunks, up(W[l], 8) / 4);       // x_l as the forward A operand
+    for (int l = 0; l < L; ++l) km_chunks = std::max(km_chunks, up(W[l + 1], 8) / 4);   // dz_l as the backward A operand
+    constexpr int64_t kActLbo = 16 * 128 + 16;
+    const int64_t km_slot_bytes = up(km_chunks * kActLbo, 1024);
+    const int64_t km_slot[2] = {off, off + km_slot_bytes};
+    off += 2 * km_slot_bytes;
+    for (int l = 0; l < L; ++l) {
+        const int64_t n16 = up(W[l + 1], 16), kp = up(W[l], 8);
+        km_lbo_w_f[l] = n16 / 8 * 128 + 16;
+        wf[l] = off;
+        off += up(kp / 4 * km_lbo_w_f[l], 128);
+        if (l > 0 || has_dx) {
+            const int64_t k16 = up(W[l], 16), np = up(W[l + 1], 8);
+            km_lbo_w_b[l] = k16 / 8 * 128 + 16;
+            wb[l] = off;
+            off += up(np / 4 * km_lbo_w_b[l], 128);
+        }
+    }
+    const int64_t bar_off = off;
+    off += 64;  // mbarrier, TMEM slot
+    const int64_t red_off = off;
+    off += 64;  // 8 warp partials of a loss sum
+    const int64_t smem_bytes = off + 1024;  // + alignment slack
+    if (smem_bytes > 227 * 1024) return false;
+    for (int l = 0; l < L; ++l)  // the widest read an M = 128 MN-major A operand can make from buffer l
+        if (mn_act[l] + 4 * 16384 > off) return false;
+    if (mn_dy + 4 * 16384 > off) return false;
+    (void)mn_end;
+
+    // ---- tensor memory plan: the working accumulator, then one weight-gradient accumulator per layer ---------------------
+    int64_t work_cols = 16;
+    for (int l = 0; l < L; ++l) work_cols = std::max(work_cols, up(W[l + 1], 16));
+    for (int l = 0; l < L; ++l)
+        if (l > 0 || has_dx) work_cols = std::max(work_cols, up(W[l], 16));
+    std::vector<int64_t> dw_col(L), dw_cols(L);
+    std::vector<char> dw_a_is_dz(L);
+    int64_t cols = work_cols;
+    for (int l = 0; l < L; ++l) {
+        dw_a_is_dz[l] = W[l + 1] >= W[l];  // the wider operand goes on the lanes
+        dw_cols[l] = up(dw_a_is_dz[l] ? W[l] : W[l + 1], 16);
+        dw_col[l] = cols;
+        cols += dw_cols[l];
+    }
+    int64_t tmem_cols = 32;
+    while (tmem_cols < cols) tmem_cols *= 2;
+    if (tmem_cols > 512) return false;
+
+    // ---- kernel parameters ------------------------------------------------------------------------------------------------
+    std::vector<KernelArg> args;
+    std::ostringstream params;
+    std::map<int, std::string> param_of_node;  // external node -> parameter name
+    std::vector<int> reads;
+    double bytes = 0;
+    auto param_for = [&](int node, bool is_output) {
+        auto it = param_of_node.find(node);
+        if (it != param_of_node.end()) return it->second;
+        const std::string p = "p" + num((int64_t)args.size());
+        params << (is_output ? "float* " : "const float* ") << p << ", ";
+        args.push_back({KernelArg::NodeBuffer, node, 0});
+        param_of_node[node] = p;
+        if (!is_output) reads.push_back(node);
+        bytes += 4.0 * (double)g.ops().nodes[node].shape.element_count();
+        return p;
+    };
+    const Cluster& f0 = clusters[ch.forward[0]];
+    const std::string px = param_for(f0.inputs[0].node_id, false);
+    std::vector<std::string> pw(L);
+    for (int l = 0; l < L; ++l) pw[l] = param_for(clusters[ch.forward[l]].inputs[1].node_id, false);
+    const std::string pdx = has_dx ? param_for(clusters[ch.backward[0]].outputs[0], true) : "";
+
+    // one per-element program evaluated on 16 accumulator columns of this thread's row: `product` is the input fed from
+    // the accumulator, `internal` (if >= 0) the input fed from hv[j] (the activation's MN-major copy)
+    auto emit_program = [&](std::ostringstream& os, const Cluster& p, int product, int internal, int64_t N, const std::string& indent) {
+        os << indent << "{\n";
+        for (size_t i = 0; i < p.inputs.size(); ++i) {
+            if ((int)i == product || (int)i == internal) continue;
+            os << indent << "    const float* in" << i << " = " << param_for(p.inputs[i].node_id, false) << ";\n";
+        }
+        os << indent << "    #pragma unroll\n" << indent << "    for (int j = 0; j < 16; ++j) {\n";
+        os << indent << "        const int c = c0 + j;\n";
+        os << indent << "        if (c < " << N << " && row_ok) {\n";
+        os << indent << "        const unsigned e = (unsigned)gm * " << unum(N) << " + (unsigned)c; (void)e;\n";
+        std::function<std::string(int)> override_fn = [&](int input) -> std::string {
+            if (input == product) return "acc[j]";
+            if (input == internal) return "hv[j]";
+            return "";
+        };
+        g_load_override = &override_fn;
+        int uniq = 0;
+        std::vector<bool> no_vector(p.inputs.size(), false);
+        std::ostringstream body;
+        emit_per_element_ops(body, p, opt, uniq, no_vector, -1);
+        g_load_override = nullptr;
+        os << body.str();
+    };
+
+    std::ostringstream os;
+    os << kDenseChainHelpers;
+    os << "// dense chain: " << L << " layers, widths";
+    for (int64_t w : W) os << " " << w;
+    os << ", " << M << " rows  [tcgen05 tf32, one persistent CTA per SM, activations in shared memory]\n";
+    std::ostringstream body;  // the kernel body; the parameter list is complete only after every program was emitted
+    const int64_t tiles = div_round_up(M, 128);
+    const int64_t grid = std::min<int64_t>(tiles, opt.sm_count);
+    // scratch layout (floats): per layer dW partials [grid][K*N], column-sum partials [grid*4][N]; loss sums [grid]
+    std::vector<int64_t> ws_dw(L), ws_cs(L, -1);
+    std::vector<int64_t> ws_sum(ch.sums.size());
+    int64_t ws = 0;
+    for (int l = 0; l < L; ++l) { ws_dw[l] = ws; ws += grid * W[l] * W[l + 1]; }
+    for (int l = 0; l < L; ++l)
+        if (!clusters[ch.weight_gradient[l]].column_sum.empty()) { ws_cs[l] = ws; ws += grid * 4 * W[l + 1]; }
+    for (size_t s = 0; s < ch.sums.size(); ++s) { ws_sum[s] = ws; ws += grid; }
+
+    body << "    constexpr int M = " << M << ", TILES = " << tiles << ";\n";
+    body << "    extern __shared__ unsigned char dsc_smem_raw[];\n";
+    body << "    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<unsigned long long>(dsc_smem_raw) + 1023ull) & ~1023ull);\n";
+    body << "    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);\n";
+    body << "    const unsigned bar = sbase + " << bar_off << "u;\n";
+    body << "    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + " << bar_off + 16 << ");\n";
+    body << "    float* red = reinterpret_cast<float*>(smem + " << red_off << ");\n";
+    body << "    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;\n";
+    body << "    const int r = quad * 32 + lane;  // this thread's row of the tile = its TMEM lane\n";
+    body << "    if (tid == 0) {\n        asm volatile(\"mbarrier.init.shared::cta.b64 [%0], 1;\" ::\"r\"(bar));\n"
+            "        asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n    }\n";
+    body << "    if (warp == 0) {\n        asm volatile(\"tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\" ::\"r\"((unsigned)__cvta_generic_to_shared(tmem_slot)), \"n\"("
+         << tmem_cols << ") : \"memory\");\n        asm volatile(\"tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\" ::: \"memory\");\n    }\n";
+    // weights
+    for (int l = 0; l < L; ++l) {
+        const int64_t K = W[l], N = W[l + 1], n16 = up(N, 16), kp = up(K, 8);
+        body << "    for (int i = tid; i < " << n16 * kp << "; i += 256) {  // W_" << l << "^T: forward B operand [n][k]\n";
+        body << "        const int n = i % " << n16 << ", k = i / " << n16 << ";\n";
+        body << "        *reinterpret_cast<float*>(smem + " << wf[l] << " + dc_km(" << km_lbo_w_f[l] << "u, n, k)) = (n < " << N << " && k < " << K << ") ? " << pw[l] << "[k * " << N
+             << " + n] : 0.f;\n    }\n";
+        if (wb[l] >= 0) {
+            const int64_t k16 = up(K, 16), np = up(N, 8);
+            body << "    for (int i = tid; i < " << k16 * np << "; i += 256) {  // W_" << l << ": backward B operand [k][n]\n";
+            body << "        const int n = i % " << np << ", k = i / " << np << ";\n";
+            body << "        *reinterpret_cast<float*>(smem + " << wb[l] << " + dc_km(" << km_lbo_w_b[l] << "u, k, n)) = (n < " << N << " && k < " << K << ") ? " << pw[l] << "[k * " << N
+                 << " + n] : 0.f;\n    }\n";
+        }
+    }
+    body << "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n";
+    body << "    asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n    __syncthreads();\n    asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
+    body << "    const unsigned tmem = *tmem_slot;\n";
+    body << "    const unsigned tlane = tmem + ((unsigned)(quad * 32) << 16);\n";
+    body << "    unsigned phase = 0;\n    bool first_tile = true;\n";
+    // per-thread partial sums carried across tiles
+    for (int l = 0; l < L; ++l)
+        if (ws_cs[l] >= 0)
+            for (int64_t i = 0; i < div_round_up(up(W[l + 1], 16) / 16, 2); ++i) body << "    float cs" << l << "_" << i << " = 0.f;\n";
+    for (size_t s = 0; s < ch.sums.size(); ++s) body << "    float lsum" << s << " = 0.f;\n";
+
+    auto idesc = [&](bool a_mn, bool b_mn, int64_t n) {
+        return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((unsigned)(n >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+    };
+    auto sync_then_issue = [&](std::ostringstream& o) {
+        o << "        asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n";
+        o << "        asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n        __syncthreads();\n";
+        o << "        if (tid == 0) {\n            asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
+    };
+    auto commit_and_wait = [&](std::ostringstream& o) {
+        o << "            dc_commit(bar);\n        }\n";
+        o << "        dc_wait(bar, phase); phase ^= 1u;\n        asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
+    };
+    auto store_km = [&](std::ostringstream& o, int64_t slot, int64_t kdim) {  // o[16] -> K-major A operand, columns below kdim
+        o << "            #pragma unroll\n            for (int q = 0; q < 4; ++q)\n                if (c0 + 4 * q < " << kdim << ")\n";
+        o << "                    *reinterpret_cast<float4*>(smem + " << slot << " + dc_km(" << kActLbo << "u, r, c0 + 4 * q)) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);\n";
+    };
+    auto store_mn = [&](std::ostringstream& o, int64_t buf) {
+        o << "            #pragma unroll\n            for (int q = 0; q < 4; ++q)\n";
+        o << "                *reinterpret_cast<float4*>(smem + " << buf << " + dc_mn(c0 + 4 * q, r)) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);\n";
+    };
+    auto column_sums = [&](std::ostringstream& o, int l) {  // of the o[16] just produced, into layer l's accumulators
+        if (ws_cs[l] < 0) return;
+        const int64_t per_warp = div_round_up(up(W[l + 1], 16) / 16, 2);
+        o << "            {\n                const float s = dc_colsum16(o, lane);\n";
+        for (int64_t i = 0; i < per_warp; ++i) o << "                if ((ch >> 1) == " << i << ") cs" << l << "_" << i << " += s;\n";
+        o << "            }\n";
+    };
+
+    int km_next = 0;  // K-major slots alternate: a tensor is written while the MMAs read the other slot
+    body << "    for (int tile = blockIdx.x; tile < TILES; tile += gridDim.x) {\n";
+    body << "        const int gm = tile * 128 + r;\n        const bool row_ok = gm < M;\n";
+    {   // x_0
+        const int64_t K = W[0], kp = up(K, 8);
+        const int64_t slot = km_slot[km_next];
+        if (K % 4 == 0) {
+            body << "        for (int u = tid; u < " << 128 * (K / 4) << "; u += 256) {  // x_0 -> both operand layouts\n";
+            body << "            const int xr = u / " << K / 4 << ", xc = (u % " << K / 4 << ") * 4;\n";
+            body << "            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);\n";
+            body << "            if (tile * 128 + xr < M) x = *reinterpret_cast<const float4*>(" << px << " + (size_t)(tile * 128 + xr) * " << K << " + xc);\n";
+            body << "            *reinterpret_cast<float4*>(smem + " << slot << " + dc_km(" << kActLbo << "u, xr, xc)) = x;\n";
+            body << "            *reinterpret_cast<float4*>(smem + " << mn_act[0] << " + dc_mn(xc, xr)) = x;\n        }\n";
+        } else {
+            body << "        for (int u = tid; u < " << 128 * K << "; u += 256) {  // x_0 -> both operand layouts\n";
+            body << "            const int xr = u / " << K << ", xc = u % " << K << ";\n";
+            body << "            const float x = tile * 128 + xr < M ? " << px << "[(size_t)(tile * 128 + xr) * " << K << " + xc] : 0.f;\n";
+            body << "            *reinterpret_cast<float*>(smem + " << slot << " + dc_km(" << kActLbo << "u, xr, xc)) = x;\n";
+            body << "            *reinterpret_cast<float*>(smem + " << mn_act[0] << " + dc_mn(xc, xr)) = x;\n        }\n";
+        }
+        if (kp != K) {
+            body << "        for (int u = tid; u < " << 128 * (kp - K) << "; u += 256)  // zero the k padding of x_0\n";
+            body << "            *reinterpret_cast<float*>(smem + " << slot << " + dc_km(" << kActLbo << "u, u / " << (kp - K) << ", " << K << " + u % " << (kp - K) << ")) = 0.f;\n";
+        }
+    }
+    // ---- forward layers ------------------------------------------------------------------------------------------------
+    for (int l = 0; l < L; ++l) {
+        const Cluster& fc = clusters[ch.forward[l]];
+        const int64_t K = W[l], N = W[l + 1], kp = up(K, 8), n16 = up(N, 16);
+        const int64_t a_slot = km_slot[km_next];
+        km_next ^= 1;
+        body << "        // forward layer " << l << ": [128, " << K << "] x W_" << l << " -> [128, " << N << "]\n";
+        sync_then_issue(body);
+        body << "            #pragma unroll\n            for (int kk = 0; kk < " << kp / 8 << "; ++kk)\n";
+        body << "                dc_mma(tmem, dc_desc(sbase + " << a_slot << "u + kk * " << 2 * kActLbo << "u, " << kActLbo << "u, 128u, 0u), dc_desc(sbase + " << wf[l] << "u + kk * "
+             << 2 * km_lbo_w_f[l] << "u, " << km_lbo_w_f[l] << "u, 128u, 0u), " << idesc(false, false, n16) << "u, kk != 0 ? 1u : 0u);\n";
+        commit_and_wait(body);
+        if (l < L - 1) {
+            const int64_t out_slot = km_slot[km_next];
+            body << "        for (int ch = half; ch < " << n16 / 16 << "; ch += 2) {  // bias + activation on the accumulator -> x_" << l + 1 << " in shared memory\n";
+            body << "            const int c0 = ch * 16;\n            float acc[16], o[16];\n            dc_ld16(tlane + (unsigned)c0, acc);\n";
+            if (fc.epilogue.empty()) {
+                body << "            #pragma unroll\n            for (int j = 0; j < 16; ++j) o[j] = acc[j];\n";
+            } else {
+                const Cluster& p = fc.epilogue[0];
+                emit_program(body, p, fc.epilogue_product_input, -1, N, "            ");
+                body << "                o[j] = t" << p.output_ops[0] << ";\n";
+                body << "                } else o[j] = 0.f;\n                }\n            }\n";
+            }
+            store_km(body, out_slot, up(N, 8));
+            store_mn(body, mn_act[l + 1]);
+            body << "        }\n";
+        } else {
+            // the loss program on the last product: dz_{L-1} and the values that are summed over the batch
+            const Cluster& p = clusters[ch.loss];
+            int product = -1;
+            for (size_t i = 0; i < p.inputs.size(); ++i)
+                if (p.inputs[i].node_id == fc.outputs[0]) product = (int)i;
+            const int64_t out_slot = km_slot[km_next];
+            body << "        for (int ch = half; ch < " << n16 / 16 << "; ch += 2) {  // loss program on the last product -> dz_" << l << "\n";
+            body << "            const int c0 = ch * 16;\n            float acc[16], o[16];\n            dc_ld16(tlane + (unsigned)c0, acc);\n";
+            if (!fc.epilogue.empty()) return false;  // (a bias absorbed into the last layer would need two programs here)
+            emit_program(body, p, product, -1, N, "            ");
+            body << "                o[j] = t" << p.output_ops[ch.loss_gradient_output] << ";\n";
+            for (size_t s = 0; s < ch.sums.size(); ++s) body << "                lsum" << s << " += t" << p.output_ops[ch.sums[s].output] << ";\n";
+            body << "                } else o[j] = 0.f;\n                }\n            }\n";
+            store_km(body, out_slot, up(N, 8));
+            store_mn(body, mn_dy);
+            column_sums(body, l);
+            body << "        }\n";
+        }
+    }
+    // ---- backward: weight gradient and backward product per layer, last first ---------------------------------------------
+    for (int l = L - 1; l >= 0; --l) {
+        const int64_t K = W[l], N = W[l + 1], np = up(N, 8), k16 = up(K, 16);
+        const int64_t dz_slot = km_slot[km_next];
+        km_next ^= 1;
+        const int64_t dz_mn = l == L - 1 ? mn_dy : mn_act[l + 1];  // dz_l lives where x_{l+1} was
+        const bool has_b = l > 0 || has_dx;
+        body << "        // layer " << l << ": dW_" << l << " += x_" << l << "^T dz_" << l << (has_b ? "; dz W^T -> activation backward\n" : "\n");
+        sync_then_issue(body);
+        {
+            const int64_t a_buf = dw_a_is_dz[l] ? dz_mn : mn_act[l], b_buf = dw_a_is_dz[l] ? mn_act[l] : dz_mn;
+            body << "            #pragma unroll\n            for (int kk = 0; kk < 16; ++kk)\n";
+            body << "                dc_mma(tmem + " << dw_col[l] << "u, dc_desc(sbase + " << a_buf << "u + kk * 1024u, 16384u, 512u, 1u), dc_desc(sbase + " << b_buf
+                 << "u + kk * 1024u, 16384u, 512u, 1u), " << idesc(true, true, dw_cols[l]) << "u, (!first_tile || kk != 0) ? 1u : 0u);\n";
+        }
+        if (has_b) {
+            body << "            #pragma unroll\n            for (int kk = 0; kk < " << np / 8 << "; ++kk)\n";
+            body << "                dc_mma(tmem, dc_desc(sbase + " << dz_slot << "u + kk * " << 2 * kActLbo << "u, " << kActLbo << "u, 128u, 0u), dc_desc(sbase + " << wb[l] << "u + kk * "
+                 << 2 * km_lbo_w_b[l] << "u, " << km_lbo_w_b[l] << "u, 128u, 0u), " << idesc(false, false, k16) << "u, kk != 0 ? 1u : 0u);\n";
+        }
+        commit_and_wait(body);
+        if (l > 0) {
+            const Cluster& bc = clusters[ch.backward[l]];
+            const Cluster& p = bc.epilogue[0];
+            int internal = -1;
+            for (size_t i = 0; i < p.inputs.size(); ++i)
+                if ((int)i != bc.epilogue_product_input && g.ops().nodes[p.inputs[i].node_id].op.kind != OpKind::Input) internal = (int)i;
+            const int64_t out_slot = km_slot[km_next];
+            body << "        for (int ch = half; ch < " << k16 / 16 << "; ch += 2) {  // activation backward -> dz_" << l - 1 << " (over x_" << l << "'s MN-major copy)\n";
+            body << "            const int c0 = ch * 16;\n            float acc[16], o[16], hv[16];\n            dc_ld16(tlane + (unsigned)c0, acc);\n";
+            body << "            #pragma unroll\n            for (int q = 0; q < 4; ++q) {\n";
+            body << "                const float4 h = *reinterpret_cast<const float4*>(smem + " << mn_act[l] << " + dc_mn(c0 + 4 * q, r));\n";
+            body << "                hv[4 * q] = h.x; hv[4 * q + 1] = h.y; hv[4 * q + 2] = h.z; hv[4 * q + 3] = h.w;\n            }\n";
+            emit_program(body, p, bc.epilogue_product_input, internal, K, "            ");
+            body << "                o[j] = t" << p.output_ops[0] << ";\n";
+            body << "                } else o[j] = 0.f;\n                }\n            }\n";
+            store_km(body, out_slot, up(K, 8));
+            store_mn(body, mn_act[l]);
+            column_sums(body, l - 1);
+            body << "        }\n";
+        } else if (has_dx) {
+            body << "        for (int ch = half; ch < " << k16 / 16 << "; ch += 2) {  // gradient with respect to x_0 -> global memory\n";
+            body << "            const int c0 = ch * 16;\n            float acc[16];\n            dc_ld16(tlane + (unsigned)c0, acc);\n";
+            body << "            if (row_ok) {\n";
+            if (K % 4 == 0) {
+                body << "                #pragma unroll\n                for (int q = 0; q < 4; ++q)\n                    if (c0 + 4 * q < " << K << ")\n";
+                body << "                        *reinterpret_cast<float4*>(" << pdx << " + (size_t)gm * " << K << " + c0 + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);\n";
+            } else {
+                body << "                #pragma unroll\n                for (int j = 0; j < 16; ++j)\n                    if (c0 + j < " << K << ") " << pdx << "[(size_t)gm * " << K << " + c0 + j] = acc[j];\n";
+            }
+            body << "            }\n        }\n";
+        }
+    }
+    body << "        first_tile = false;\n";
+    body << "        asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n        __syncthreads();  // the next tile's x_0 overwrites operands of this tile's last MMAs (waited for above)\n";
+    body << "    }\n";
+    // ---- per-CTA partial results -> scratch ---------------------------------------------------------------------------------
+    body << "    asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
+    for (int l = 0; l < L; ++l) {
+        const int64_t K = W[l], N = W[l + 1];
+        body << "    for (int ch = half; ch < " << dw_cols[l] / 16 << "; ch += 2) {  // this CTA's partial dW_" << l << "\n";
+        body << "        const int c0 = ch * 16;\n        float acc[16];\n        dc_ld16(tlane + " << dw_col[l] << "u + (unsigned)c0, acc);\n";
+        body << "        float* dst = ws + " << ws_dw[l] << " + (size_t)blockIdx.x * " << K * N << ";\n";
+        body << "        #pragma unroll\n        for (int j = 0; j < 16; ++j) {\n";
+        if (dw_a_is_dz[l]) body << "            if (r < " << N << " && c0 + j < " << K << ") dst[(c0 + j) * " << N << " + r] = acc[j];  // lanes = n, columns = k\n";
+        else body << "            if (r < " << K << " && c0 + j < " << N << ") dst[r * " << N << " + c0 + j] = acc[j];  // lanes = k, columns = n\n";
+        body << "        }\n    }\n";
+        if (ws_cs[l] >= 0) {
+            const int64_t per_warp = div_round_up(up(N, 16) / 16, 2);
+            for (int64_t i = 0; i < per_warp; ++i) {
+                body << "    {\n        const int c = (" << 2 * i << " + half) * 16 + dc_colsum16_column(lane);\n";
+                body << "        if ((lane & 1) == 0 && c < " << N << ") ws[" << ws_cs[l] << " + (size_t)(blockIdx.x * 4 + quad) * " << N << " + c] = cs" << l << "_" << i << ";\n    }\n";
+            }
+        }
+    }
+    for (size_t s = 0; s < ch.sums.size(); ++s) {
+        body << "    {\n        float v = lsum" << s << ";\n        #pragma unroll\n        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);\n";
+        body << "        __syncthreads();\n        if (lane == 0) red[warp] = v;\n        __syncthreads();\n";
+        body << "        if (tid == 0) {\n            float t = red[0];\n            #pragma unroll\n            for (int w = 1; w < 8; ++w) t += red[w];\n";
+        body << "            ws[" << ws_sum[s] << " + blockIdx.x] = t;\n        }\n    }\n";
+    }
+    body << "    asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n    __syncthreads();\n";
+    body << "    if (warp == 0) {\n        asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
+    body << "        asm volatile(\"tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\" ::\"r\"(tmem), \"n\"(" << tmem_cols << ") : \"memory\");\n    }\n";
+
+    os << "extern \"C\" __global__ void __launch_bounds__(256, 1) " << name << "(" << params.str() << "float* ws, const unsigned* dsc_step) {\n";
+    os << "    (void)dsc_step;\n" << body.str() << "}\n";
+
+    // ---- split sums: every per-CTA partial set -> its node, one launch -------------------------------------------------------
+    struct Set { int64_t offset, count, splits; int node; };
+    std::vector<Set> sets;
+    for (int l = 0; l < L; ++l) {
+        const Cluster& gc = clusters[ch.weight_gradient[l]];
+        sets.push_back({ws_dw[l], W[l] * W[l + 1], grid, gc.outputs[0]});
+        if (ws_cs[l] >= 0) sets.push_back({ws_cs[l], W[l + 1], grid * 4, gc.outputs[1]});
+    }
+    for (size_t s = 0; s < ch.sums.size(); ++s) sets.push_back({ws_sum[s], 1, grid, clusters[ch.sums[s].batch_reduce].outputs[0]});
+    const std::string sname = name + "_sums";
+    os << "// per-CTA partial weight gradients, bias gradients and loss sums of the dense chain -> their arrays: 32 outputs x 8 split\n"
+          "// lanes per CTA, lane g adds partials g, g + 8, ... in ascending order, then the eight lane sums in lane order\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(256) " << sname << "(const float* ws";
+    for (size_t i = 0; i < sets.size(); ++i) os << ", float* out" << i;
+    os << ", const unsigned* dsc_step) {\n    (void)dsc_step;\n    __shared__ float red[8][32];\n    const unsigned tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;\n";
+    os << "    const float* src; float* dst; unsigned count, splits, block;\n";
+    int64_t blocks = 0;
+    for (size_t i = 0; i < sets.size(); ++i) {
+        const int64_t b = div_round_up(sets[i].count, 32);
+        os << "    " << (i ? "else " : "") << "if (blockIdx.x < " << blocks + b << "u) { src = ws + " << sets[i].offset << "; dst = out" << i << "; count = " << sets[i].count
+           << "u; splits = " << sets[i].splits << "u; block = blockIdx.x - " << blocks << "u; }\n";
+        blocks += b;
+    }
+    os << "    else return;\n    const unsigned i = block * 32u + tx;\n    float part = 0.f;\n    if (i < count) {\n        #pragma unroll 4\n"
+          "        for (unsigned s = ty; s < splits; s += 8u) part += src[(size_t)s * count + i];\n    }\n    red[ty][tx] = part;\n    __syncthreads();\n"
+          "    if (ty != 0 || i >= count) return;\n    float acc = red[0][tx];\n    #pragma unroll\n    for (unsigned g2 = 1; g2 < 8u; ++g2) acc += red[g2][tx];\n    dst[i] = acc;\n}\n\n";
+
+    out->source = os.str();
+    out->scratch_bytes = ws * 4;
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)grid;
+    l.block = 256;
+    l.smem = (uint32_t)smem_bytes;
+    std::ostringstream label;
+    label << "DenseChain (" << L << " layers:";
+    for (int64_t w : W) label << " " << w;
+    label << ") [" << M << "] forward + loss + backward";
+    l.label = "TensorCore" + label.str();
+    l.cluster = ci;
+    l.covers = ch.all_clusters();
+    l.args = args;
+    l.args.push_back({KernelArg::Scratch, -1, 0});
+    l.algorithmic_bytes = bytes;
+    for (int k = 0; k < L; ++k) l.flops += 6.0 * (double)M * (double)W[k] * (double)W[k + 1];
+    out->launches.push_back(l);
+    KernelLaunch s;
+    s.entry = sname;
+    s.grid_x = (uint32_t)blocks;
+    s.label = "SplitSum dense chain (" + num((int64_t)sets.size()) + " arrays)";
+    s.cluster = ci;
+    s.args.push_back({KernelArg::Scratch, -1, 0});
+    for (const auto& set : sets) s.args.push_back({KernelArg::NodeBuffer, set.node, 0});
+    out->launches.push_back(s);
+    out->extra_reads = reads;
+    for (const auto& set : sets) out->extra_writes.push_back(set.node);
+    if (has_dx) out->extra_writes.push_back(clusters[ch.backward[0]].outputs[0]);
+    return true;
+}
+
+namespace {
 }  // namespace
 
 int64_t eval_chain(const ViewChain& chain, int64_t e) {

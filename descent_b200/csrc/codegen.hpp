@@ -25,6 +25,7 @@ struct KernelLaunch {
     int gemm_splits = 1;  // TensorGemm: k slices, each writing a partial product [M, N] into args[2] (then a scratch workspace)
     std::string label;
     int cluster = -1;
+    std::vector<int> covers;       // clusters whose work this launch does besides its own (a fused dense chain)
     double algorithmic_bytes = 0;  // 4*(sum of min(source, addressed) input elements + outputs)
     double flops = 0;              // 2*b*m*n*k for GEMMs
 };
@@ -38,6 +39,9 @@ struct ClusterCode {
     // operand prologues (graph.hpp OperandPrologue): nodes this cluster's kernels read although no graph edge says so
     // (the inputs of a producer evaluated inside the operand loader): the planner keeps them alive until this cluster
     std::vector<int> extra_reads;
+    // results of OTHER clusters this cluster's kernels write (a fused dense chain runs at its last cluster's slot): the
+    // planner gives them storage here
+    std::vector<int> extra_writes;
     bool skipped = false;  // a producer every consumer evaluates on the fly: no kernel, its output is never materialised
 };
 
@@ -57,6 +61,10 @@ struct CodegenOptions {
 
 std::string kernel_prelude();
 ClusterCode generate_cluster_code(const Graph& graph, int cluster_index, const CodegenOptions& options, PrologueRequest* prologue = nullptr);
+
+// One kernel for a whole dense chain (graph.hpp DenseChain), to run at the chain's last cluster; false if these options or
+// widths rule it out (the clusters then run one by one as usual).
+bool generate_dense_chain_code(const Graph& graph, const DenseChain& chain, const CodegenOptions& options, ClusterCode* out);
 
 // host-side evaluation of a chain (tests, layout heuristics): consumer element -> producer element
 int64_t eval_chain(const ViewChain& chain, int64_t e);

@@ -51,8 +51,24 @@ std::string generate_graph_source(const Graph& graph, const CodegenOptions& opti
     // kernel and its output is never written.  Otherwise nothing changes for that producer.
     std::vector<PrologueRequest> accepted(nc);
     std::vector<ClusterCode> pregenerated(nc);
-    std::vector<char> has_pregenerated(nc, 0), skipped(nc, 0);
+    std::vector<char> has_pregenerated(nc, 0), skipped(nc, 0), in_dense_chain(nc, 0);
+    // Dense chains (graph.hpp DenseChain): one kernel at the chain's last cluster does the work of all of them when the
+    // options and widths allow; the other clusters of the chain then run nothing and their intermediates never exist.
+    for (const DenseChain& chain : graph.dense_chains()) {
+        ClusterCode code;
+        if (!generate_dense_chain_code(graph, chain, options, &code)) continue;
+        const int host = chain.last_cluster();
+        for (int ci : chain.all_clusters()) {
+            in_dense_chain[ci] = 1;
+            if (ci != host) skipped[ci] = 1;
+        }
+        pregenerated[host] = std::move(code);
+        has_pregenerated[host] = 1;
+    }
     for (const OperandPrologue& cand : graph.operand_prologues()) {
+        bool feeds_dense_chain = false;
+        for (const auto& use : cand.uses) feeds_dense_chain |= in_dense_chain[use.cluster] != 0;
+        if (feeds_dense_chain || in_dense_chain[cand.producer]) continue;  // the fused kernel reads its operands from memory
         std::vector<std::pair<int, PrologueRequest>> requests;  // one per consumer cluster (A and B may both name this producer)
         for (const auto& use : cand.uses) {
             auto it = std::find_if(requests.begin(), requests.end(), [&](const auto& r) { return r.first == use.cluster; });
@@ -186,6 +202,7 @@ struct ResolvedLaunch {
     bool async_collective = false, join_collectives = false;  // AllReduce: on the side stream / wait for the side stream first
     std::string label, entry;
     int cluster = -1;
+    std::vector<int> covers;
     double algorithmic_bytes = 0, flops = 0;
     int64_t gemm_m = 0, gemm_n = 0, gemm_k = 0;
     bool gemm_a_is_mk = true, gemm_b_is_kn = true;
@@ -457,17 +474,20 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
         // release what nobody after the previous cluster needs
         if (ci > 0)
             for (int id : dying_at[ci - 1]) arena.release(storage[id].offset, ops.nodes[id].shape.buffer_size());
-        for (int out : clusters[ci].outputs) {
-            if (codes[ci].skipped) continue;  // computed on the fly by its consumers: never in memory
+        auto place = [&](int out) {
             if (alias[out] >= 0) {
                 storage[out] = storage[alias[out]];
-                continue;
+                return;
             }
-            if (storage[out].kind != Storage::None) continue;  // parameter or bucket
+            if (storage[out].kind != Storage::None) return;  // parameter or bucket
             storage[out] = {Storage::Arena, -1, arena.alloc(ops.nodes[out].shape.buffer_size())};
             int d = std::max(death[out], ci);
             if (!lives_to_end[out]) dying_at[d].push_back(out);
-        }
+        };
+        const bool fused_host = !codes[ci].extra_writes.empty();  // a dense chain's kernel: it writes exactly extra_writes
+        if (!codes[ci].skipped && !fused_host)  // (skipped: computed on the fly by its consumers, never in memory)
+            for (int out : clusters[ci].outputs) place(out);
+        for (int out : codes[ci].extra_writes) place(out);
         if (codes[ci].scratch_bytes > 0) {
             scratch_offset[ci] = arena.alloc(codes[ci].scratch_bytes);
             arena.release(scratch_offset[ci], codes[ci].scratch_bytes);  // free again for the next cluster...
@@ -518,6 +538,7 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
             r.label = l.label;
             r.entry = l.entry;
             r.cluster = ci;
+            r.covers = l.covers;
             r.algorithmic_bytes = l.algorithmic_bytes;
             r.flops = l.flops;
             if (l.kind == KernelLaunch::ZeroScratch) {
@@ -639,6 +660,7 @@ std::vector<KernelTiming> Environment::profile(const Graph& graph, uint32_t rand
         out[i].label = exec.launches[i].label;
         out[i].entry = exec.launches[i].entry;
         out[i].cluster = exec.launches[i].cluster;
+        out[i].covers = exec.launches[i].covers;
         out[i].algorithmic_bytes = exec.launches[i].algorithmic_bytes;
         out[i].flops = exec.launches[i].flops;
         out[i].grid[0] = exec.launches[i].gx; out[i].grid[1] = exec.launches[i].gy; out[i].grid[2] = exec.launches[i].gz;

@@ -39,6 +39,7 @@ struct KernelTiming {
     std::string label;
     std::string entry;
     int cluster = -1;
+    std::vector<int> covers;  // a fused launch: every cluster whose work it does
     double ms = 0;  // average per launch
     uint32_t grid[3] = {0, 0, 0}, block = 0, smem = 0;
     double algorithmic_bytes = 0;

@@ -170,7 +170,33 @@ std::string export_ops_json(const OpGraph& ops, const std::vector<ParameterStora
 }
 
 std::string Scope::export_json() const { return export_ops_json(ops_, *parameters_, nullptr); }
-std::string Graph::export_json() const { return export_ops_json(ops_, *parameters_, &clusters_); }
+std::string Graph::export_json() const {
+    std::string json = export_ops_json(ops_, *parameters_, &clusters_);
+    // dense-chain candidates (graph.hpp DenseChain), appended as one more key of the top-level object
+    std::ostringstream os;
+    os << ",\"dense_chains\":[";
+    for (size_t i = 0; i < dense_chains_.size(); ++i) {
+        const DenseChain& ch = dense_chains_[i];
+        auto list = [&](const char* key, const std::vector<int>& v) {
+            os << "\"" << key << "\":[";
+            for (size_t j = 0; j < v.size(); ++j) os << (j ? "," : "") << v[j];
+            os << "]";
+        };
+        os << (i ? "," : "") << "{\"rows\":" << ch.rows << ",\"widths\":[";
+        for (size_t j = 0; j < ch.widths.size(); ++j) os << (j ? "," : "") << ch.widths[j];
+        os << "],";
+        list("forward", ch.forward); os << ",";
+        list("weight_gradient", ch.weight_gradient); os << ",";
+        list("backward", ch.backward); os << ",";
+        list("clusters", ch.all_clusters());
+        os << ",\"loss\":" << ch.loss << "}";
+    }
+    os << "]";
+    const size_t end = json.rfind('}');
+    DSC_CHECK(end != std::string::npos, "malformed graph json");
+    json.insert(end, os.str());
+    return json;
+}
 
 // ---- Graph ------------------------------------------------------------------------------------
 
@@ -1354,6 +1380,7 @@ void Graph::build_clusters() {
     absorb_column_sums(clusters);
     absorb_max_pools(clusters);
     fuse_rows(clusters);
+    schedule_after_dense_chains(clusters);
     sink_parameter_updates(clusters);
     group_small_per_element(clusters);
 
@@ -1372,6 +1399,269 @@ void Graph::build_clusters() {
     for (auto& node : ops_.nodes)
         if (node.alive && node.cluster_id >= 0) node.cluster_id = new_index[node.cluster_id];
     find_operand_prologues();
+    // the final list: a candidate stands only if every reader of its results runs after its last cluster
+    dense_chains_.clear();
+    {
+        auto cons = ops_.consumers();
+        for (const auto& ch : detect_dense_chains(clusters_)) {
+            const auto all = ch.all_clusters();
+            std::set<int> members(all.begin(), all.end());
+            bool ok = true;
+            for (int c : all)
+                for (int out : clusters_[c].outputs)
+                    for (auto [dst, k] : cons[out]) {
+                        (void)k;
+                        const int dc = ops_.nodes[dst].cluster_id;
+                        if (ops_.nodes[dst].alive && dc >= 0 && !members.count(dc) && dc <= all.back()) ok = false;
+                    }
+            if (ok) dense_chains_.push_back(ch);
+        }
+    }
+}
+
+std::vector<int> DenseChain::all_clusters() const {
+    std::vector<int> all;
+    for (int c : forward) all.push_back(c);
+    for (int c : weight_gradient) all.push_back(c);
+    for (int c : backward) if (c >= 0) all.push_back(c);
+    all.push_back(loss);
+    for (const auto& s : sums) { all.push_back(s.row_reduce); all.push_back(s.batch_reduce); }
+    std::sort(all.begin(), all.end());
+    return all;
+}
+
+int DenseChain::last_cluster() const { return all_clusters().back(); }
+
+// See DenseChain (graph.hpp).  A purely structural match on the clusters the other passes produced; anything that does
+// not fit exactly is left alone.  `clusters` may be the working list of build_clusters (emptied clusters are skipped) or
+// the final one: node.cluster_id indexes it either way.
+std::vector<DenseChain> Graph::detect_dense_chains(const std::vector<Cluster>& clusters) const {
+    std::vector<DenseChain> found;
+    auto cons = ops_.consumers();
+    const int nc = (int)clusters.size();
+    auto cluster_of = [&](int node) { return ops_.nodes[node].cluster_id; };
+    // element (i, j) of a [1, rows, cols] operand reads element (j, i) of a [cols, rows]-shaped source
+    auto is_transposed = [&](const ClusterInput& in, int64_t rows, int64_t cols) {
+        if (in.arg_shape.len() != 3 || in.arg_shape[0] != 1 || in.arg_shape[1] != rows || in.arg_shape[2] != cols) return false;
+        if (in.chain.input_count != rows * cols || in.chain.output_count != rows * cols) return false;
+        for (int64_t i : {(int64_t)0, (int64_t)1, rows / 2, rows - 1})
+            for (int64_t j : {(int64_t)0, (int64_t)1, cols / 3, cols - 1})
+                if (i < rows && j < cols && eval_chain(in.chain, i * cols + j) != j * rows + i) return false;
+        return true;
+    };
+    auto is_plain = [&](const ClusterInput& in, int64_t rows, int64_t cols) {
+        return in.chain.is_identity() && in.arg_shape.element_count() == rows * cols && in.arg_shape.at(-1) == cols &&
+               ops_.nodes[in.node_id].shape.element_count() == rows * cols;
+    };
+    auto plain_matmul = [&](const Cluster& c) {
+        return c.kind == ClusterKind::MatMul && !c.members.empty() && !c.conv_backward_input.enabled && !c.pool.enabled && c.inputs.size() >= 2;
+    };
+    auto is_parameter = [&](int node) { return ops_.nodes[node].op.kind == OpKind::Input; };
+    // forward layer candidates: [M, K] activation (plain) x [K, N] parameter (plain)
+    struct Forward { int64_t m, k, n; int a, w, out; };
+    std::map<int, Forward> forward;  // cluster -> shape
+    for (int ci = 0; ci < nc; ++ci) {
+        const Cluster& c = clusters[ci];
+        if (!plain_matmul(c) || c.matmul_absorbs_reduce || !c.column_sum.empty() || c.outputs.size() != 1) continue;
+        const OpNode& mm = ops_.nodes[c.node_id];
+        if (mm.op.kind != OpKind::MatMul || mm.shape.len() != 4 || mm.shape[0] != 1 || mm.shape[1] != 1) continue;
+        const int64_t M = mm.shape[2], N = mm.shape[3], K = c.inputs[0].arg_shape.at(-1);
+        if (!is_plain(c.inputs[0], M, K) || !is_plain(c.inputs[1], K, N) || !is_parameter(c.inputs[1].node_id) || M < 1024) continue;
+        bool ok = true;
+        if (!c.epilogue.empty()) {
+            const Cluster& p = c.epilogue[0];
+            ok = p.outputs.size() == 1 && p.element_count == M * N;
+            for (size_t i = 0; i < p.inputs.size(); ++i)
+                if ((int)i != c.epilogue_product_input) ok = ok && is_parameter(p.inputs[i].node_id);
+            for (const auto& op : p.ops) ok = ok && op.kind != PerElementOp::Gather && op.kind != PerElementOp::BuiltIn;
+        }
+        if (ok) forward[ci] = {M, K, N, c.inputs[0].node_id, c.inputs[1].node_id, c.outputs[0]};
+    }
+    std::map<int, int> forward_reading;  // activation node -> forward cluster that takes it as A
+    for (auto& [ci, f] : forward) {
+        if (forward_reading.count(f.a)) forward_reading[f.a] = -1;  // two readers: not a chain
+        else forward_reading[f.a] = ci;
+    }
+    std::set<int> produced_by_forward;
+    for (auto& [ci, f] : forward) produced_by_forward.insert(f.out);
+    for (auto& [start, f0] : forward) {
+        if (produced_by_forward.count(f0.a) && forward_reading.count(f0.a) && forward_reading[f0.a] >= 0) {
+            // not the first layer of its chain
+            bool has_pred = false;
+            for (auto& [cj, fj] : forward) has_pred |= fj.out == f0.a;
+            if (has_pred) continue;
+        }
+        DenseChain ch;
+        ch.rows = f0.m;
+        ch.widths.push_back(f0.k);
+        for (int ci = start;;) {
+            const Forward& f = forward[ci];
+            if (f.m != ch.rows || f.k != ch.widths.back()) break;
+            ch.forward.push_back(ci);
+            ch.widths.push_back(f.n);
+            auto it = forward_reading.find(f.out);
+            if (it == forward_reading.end() || it->second < 0 || !forward.count(it->second)) break;
+            ci = it->second;
+        }
+        const int L = (int)ch.forward.size();
+        if (L < 2) continue;
+        const int64_t M = ch.rows;
+        bool ok = true;
+        std::vector<int> act(L + 1, -1), dz(L, -1);  // act[l] = input of layer l (act[L] = last product), dz[l] = gradient at layer l's output
+        act[0] = forward[ch.forward[0]].a;
+        for (int l = 0; l < L; ++l) act[l + 1] = forward[ch.forward[l]].out;
+        // the loss cluster: the only reader of the last product
+        {
+            std::set<int> readers;
+            for (auto [dst, k] : cons[act[L]]) {
+                (void)k;
+                if (!ops_.nodes[dst].alive) continue;
+                if (ops_.nodes[dst].op.kind == OpKind::Output || cluster_of(dst) < 0) ok = false;
+                else readers.insert(cluster_of(dst));
+            }
+            if (!ok || readers.size() != 1) continue;
+            ch.loss = *readers.begin();
+        }
+        const Cluster& lc = clusters[ch.loss];
+        if (lc.kind != ClusterKind::PerElement || !lc.group.empty() || lc.element_count != M * ch.widths[L]) continue;
+        int product_inputs = 0;
+        for (const auto& in : lc.inputs) {
+            if (in.node_id == act[L]) { product_inputs += 1; ok = ok && in.chain.is_identity(); }
+            else ok = ok && is_parameter(in.node_id);
+        }
+        for (const auto& op : lc.ops) ok = ok && op.kind != PerElementOp::Gather && op.kind != PerElementOp::BuiltIn;
+        if (!ok || product_inputs != 1) continue;
+        // weight gradients and backward products, last layer first
+        ch.weight_gradient.assign(L, -1);
+        ch.backward.assign(L, -1);
+        for (int l = L - 1; l >= 0 && ok; --l) {
+            const int64_t K = ch.widths[l], N = ch.widths[l + 1];
+            const int w = forward[ch.forward[l]].w;
+            int g = -1;
+            for (auto [dst, k] : cons[act[l]]) {
+                (void)k;
+                const int ci = cluster_of(dst);
+                if (ci < 0 || !plain_matmul(clusters[ci]) || !clusters[ci].matmul_absorbs_reduce || !clusters[ci].epilogue.empty()) continue;
+                if (clusters[ci].inputs[0].node_id == act[l] && is_transposed(clusters[ci].inputs[0], K, M) && is_plain(clusters[ci].inputs[1], M, N)) g = ci;
+            }
+            if (g < 0) { ok = false; break; }
+            const Cluster& gc = clusters[g];
+            ch.weight_gradient[l] = g;
+            const int d = gc.inputs[1].node_id;
+            if (l == L - 1) {
+                dz[l] = d;
+                ch.loss_gradient_output = -1;
+                for (size_t i = 0; i < lc.outputs.size(); ++i)
+                    if (lc.outputs[i] == d) ch.loss_gradient_output = (int)i;
+                if (ch.loss_gradient_output < 0) { ok = false; break; }
+            } else if (dz[l] != d) { ok = false; break; }
+            if (ops_.nodes[gc.outputs[0]].shape.element_count() != K * N || gc.column_sum.size() > 1 || gc.outputs.size() != 1 + gc.column_sum.size()) { ok = false; break; }
+            if (!gc.column_sum.empty()) {
+                const Cluster& rc = gc.column_sum[0];
+                ok = ok && rc.inputs.size() == 1 && rc.inputs[0].node_id == d && rc.inputs[0].chain.is_identity() &&
+                     ops_.nodes[rc.node_id].op.reduce == ReduceOp::Sum && ops_.nodes[gc.outputs[1]].shape.element_count() == N;
+            }
+            // backward product dz_l W_l^T
+            int b = -1;
+            for (auto [dst, k] : cons[d]) {
+                (void)k;
+                const int ci = cluster_of(dst);
+                if (ci < 0 || ci == g || !plain_matmul(clusters[ci]) || clusters[ci].matmul_absorbs_reduce || !clusters[ci].column_sum.empty()) continue;
+                if (clusters[ci].inputs[0].node_id == d && is_plain(clusters[ci].inputs[0], M, N) && clusters[ci].inputs[1].node_id == w &&
+                    is_transposed(clusters[ci].inputs[1], N, K) && clusters[ci].outputs.size() == 1)
+                    b = ci;
+            }
+            ch.backward[l] = b;
+            if (l > 0) {
+                if (b < 0 || clusters[b].epilogue.empty()) { ok = false; break; }
+                const Cluster& p = clusters[b].epilogue[0];
+                ok = ok && p.outputs.size() == 1 && p.element_count == M * K;
+                for (size_t i = 0; i < p.inputs.size(); ++i) {
+                    if ((int)i == clusters[b].epilogue_product_input) continue;
+                    if (p.inputs[i].node_id == act[l]) ok = ok && p.inputs[i].chain.is_identity();
+                    else ok = ok && is_parameter(p.inputs[i].node_id);
+                }
+                for (const auto& op : p.ops) ok = ok && op.kind != PerElementOp::Gather && op.kind != PerElementOp::BuiltIn;
+                dz[l - 1] = clusters[b].outputs[0];
+            } else if (b >= 0 && !clusters[b].epilogue.empty()) {
+                ok = false;
+            }
+        }
+        if (!ok) continue;
+        // sums of the loss cluster's other outputs: Reduce along the row, then over the batch
+        for (size_t i = 0; i < lc.outputs.size() && ok; ++i) {
+            if ((int)i == ch.loss_gradient_output) continue;
+            auto single_reduce = [&](int node, int axis, int64_t count_out) {
+                int r = -1, readers = 0;
+                for (auto [dst, k] : cons[node]) {
+                    if (!ops_.nodes[dst].alive) continue;
+                    readers += 1;
+                    const OpNode& d = ops_.nodes[dst];
+                    const int ci = cluster_of(dst);
+                    if (d.op.kind == OpKind::Reduce && d.op.reduce == ReduceOp::Sum && d.op.axis == axis && d.in[k].chain.is_identity() && ci >= 0 &&
+                        clusters[ci].kind == ClusterKind::Reduce && clusters[ci].members.size() == 1 && d.shape.element_count() == count_out)
+                        r = ci;
+                }
+                return readers == 1 ? r : -1;
+            };
+            const int rr = single_reduce(lc.outputs[i], 1, M);
+            if (rr < 0 || ops_.nodes[lc.outputs[i]].shape.len() != 2) { ok = false; break; }
+            const int br = single_reduce(clusters[rr].outputs[0], 0, 1);
+            if (br < 0) { ok = false; break; }
+            ch.sums.push_back({(int)i, rr, br});
+        }
+        if (!ok) continue;
+        // every intermediate is read by the chain only, and no chain cluster belongs to two chains
+        std::set<int> members;
+        for (int c : ch.all_clusters()) members.insert(c);
+        if ((int)members.size() != (int)ch.all_clusters().size()) continue;
+        std::vector<int> internal;
+        for (int l = 1; l <= L; ++l) internal.push_back(act[l]);
+        for (int l = 0; l < L; ++l) internal.push_back(dz[l]);
+        for (const auto& s : ch.sums) { internal.push_back(lc.outputs[s.output]); internal.push_back(clusters[s.row_reduce].outputs[0]); }
+        for (int node : internal)
+            for (auto [dst, k] : cons[node]) {
+                (void)k;
+                if (!ops_.nodes[dst].alive) continue;
+                if (ops_.nodes[dst].op.kind == OpKind::Output || !members.count(cluster_of(dst))) ok = false;
+            }
+        for (const auto& other : found)
+            for (int c : other.all_clusters()) ok = ok && !members.count(c);
+        if (ok) found.push_back(ch);
+    }
+    return found;
+}
+
+// Readers of a dense chain's results must come after the chain's last cluster, where the fused kernel runs.
+void Graph::schedule_after_dense_chains(std::vector<Cluster>& clusters) {
+    auto chains = detect_dense_chains(clusters);
+    if (chains.empty()) return;
+    auto cons = ops_.consumers();
+    for (const auto& ch : chains) {
+        std::set<int> members;
+        int last_level = 0;
+        for (int c : ch.all_clusters()) { members.insert(c); last_level = std::max(last_level, clusters[c].level); }
+        for (int c : members)
+            for (int out : clusters[c].outputs)
+                for (auto [dst, k] : cons[out]) {
+                    (void)k;
+                    const int dc = ops_.nodes[dst].cluster_id;
+                    if (ops_.nodes[dst].alive && dc >= 0 && !members.count(dc) && clusters[dc].level <= last_level) clusters[dc].level = last_level + 1;
+                }
+    }
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        for (const auto& node : ops_.nodes) {
+            if (!node.alive || node.cluster_id < 0) continue;
+            Cluster& dc = clusters[node.cluster_id];
+            for (const auto& e : node.in) {
+                const OpNode& src = ops_.nodes[e.src];
+                if (!src.alive || src.cluster_id < 0 || src.cluster_id == node.cluster_id) continue;
+                if (dc.level <= clusters[src.cluster_id].level) { dc.level = clusters[src.cluster_id].level + 1; changed = true; }
+            }
+        }
+    }
 }
 
 // See OperandPrologue (graph.hpp).  Candidates: ungrouped per-element clusters with one output X, a straight-line

@@ -113,6 +113,27 @@ struct OperandPrologue {
     std::vector<Use> uses;
 };
 
+// A multi-layer perceptron's whole training step over the batch rows (the image_fit heads,
+// examples/image_fit/main.rs:50-118,259-275; module.rs:70-90 Dense): forward layers x_{l+1} = act(x_l W_l + b_l), a
+// per-element loss on the last product, and for every layer the weight gradient x_l^T dz_l (+ bias column sums) and the
+// backward product dz_l W_l^T (+ activation backward).  Every one of these is row-local except the sums over the batch,
+// so a 128-row tile can go through all of them without its activations ever leaving the SM.  The graph only records the
+// candidate (cluster indices in execution order); the code generator decides (tensor-core path, widths that fit shared
+// memory): it then emits ONE kernel at the position of the last cluster and the other clusters run nothing.
+struct DenseChain {
+    int64_t rows = 0;                  // batch rows M
+    std::vector<int64_t> widths;       // widths[0] = width of the input x_0, widths[l + 1] = output width of layer l
+    std::vector<int> forward;          // per layer: MatMul cluster x_l W_l (+ per-element epilogue: bias, activation)
+    std::vector<int> weight_gradient;  // per layer: MatMul cluster x_l^T dz_l (+ column sums of dz_l)
+    std::vector<int> backward;         // per layer: MatMul cluster dz_l W_l^T (+ epilogue: activation backward of layer l-1); backward[0] = -1 if x_0 needs no gradient
+    int loss = -1;                     // per-element cluster: last product (+ bias, target) -> dz_{L-1} and values that are summed
+    int loss_gradient_output = 0;      // which output of the loss cluster is dz_{L-1}
+    struct Sum { int output; int row_reduce; int batch_reduce; };  // loss output -> Reduce along the row -> Reduce over the batch
+    std::vector<Sum> sums;
+    std::vector<int> all_clusters() const;
+    int last_cluster() const;
+};
+
 class Graph {
 public:
     Graph(SharedParameters parameters, const OpGraph& ops, DataParallel dp);
@@ -120,6 +141,7 @@ public:
     const OpGraph& ops() const { return ops_; }
     const std::vector<Cluster>& clusters() const { return clusters_; }  // already in execution order
     const std::vector<OperandPrologue>& operand_prologues() const { return operand_prologues_; }
+    const std::vector<DenseChain>& dense_chains() const { return dense_chains_; }
     const SharedParameters& parameters() const { return parameters_; }
     const DataParallel& dp() const { return dp_; }
     std::vector<int> input_nodes() const;
@@ -151,12 +173,15 @@ private:
     void build_clusters();
     void build_per_element_program(Cluster& c);
     void find_operand_prologues();
+    std::vector<DenseChain> detect_dense_chains(const std::vector<Cluster>& clusters) const;
+    void schedule_after_dense_chains(std::vector<Cluster>& clusters);
 
     SharedParameters parameters_;
     OpGraph ops_;
     DataParallel dp_;
     std::vector<Cluster> clusters_;
     std::vector<OperandPrologue> operand_prologues_;
+    std::vector<DenseChain> dense_chains_;
 };
 
 std::string export_ops_json(const OpGraph& ops, const std::vector<ParameterStorage>& parameters, const std::vector<Cluster>* clusters);

@@ -165,7 +165,8 @@ def test_ragged_batch_sizes(env, network, m, precision):
         clusters = ex.train_graph.export_json()["clusters"]
         for t in env.profile(ex.train_graph, 0, 1):
             if t["label"].startswith("TensorCore"):
-                tensor_core.update(clusters[t["cluster"]]["members"])
+                for ci in t["clusters"]:
+                    tensor_core.update(clusters[ci]["members"])
         upload(env, params)  # the profiling pass ran the step once
     env.run(ex.train_graph, seed)
     want = run_graph(ex.train_graph_json, params, seed, tf32=("trunc", tensor_core) if tensor_core else None)

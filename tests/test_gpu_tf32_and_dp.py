@@ -34,7 +34,8 @@ def tensor_core_nodes(env, ex):
     nodes = set()
     for t in env.profile(ex.train_graph, 0, 1):
         if t["label"].startswith("TensorCore"):
-            nodes.update(clusters[t["cluster"]]["members"])
+            for ci in t["clusters"]:
+                nodes.update(clusters[ci]["members"])
     return nodes
 
 
