@@ -2432,6 +2432,17 @@ __device__ __forceinline__ unsigned dc_mn(int mn, int k) {
     return (unsigned)(mn >> 5) * 16384u + (unsigned)(k >> 2) * 512u + (unsigned)(k & 3) * 128u + (((((unsigned)mn & 31u) >> 3) ^ ((unsigned)k & 3u)) << 5) +
            (unsigned)(mn & 7) * 4u;
 }
+// shared memory through 32-bit shared-space addresses (the aligned base is computed from an integer, so the compiler would
+// otherwise fall back to generic loads and stores)
+__device__ __forceinline__ void dc_sts4(unsigned addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void dc_sts1(unsigned addr, float a) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
+__device__ __forceinline__ float4 dc_lds4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long dc_desc(unsigned addr, unsigned lbo, unsigned sbo, unsigned mn_major) {
     return (unsigned long long)((addr >> 4) & 0x3fffu) | ((unsigned long long)((lbo >> 4) & 0x3fffu) << 16) | ((unsigned long long)((sbo >> 4) & 0x3fffu) << 32) |
            (1ull << 46) | ((unsigned long long)mn_major << 61);
@@ -2443,6 +2454,18 @@ __device__ __forceinline__ void dc_mma(unsigned d_tmem, unsigned long long adesc
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// one lane of a converged warp (the MMA-issuing thread): with elect.sync the compiler knows exactly one thread runs the
+// branch and issues each tcgen05.mma once, instead of looping over the lanes it must assume active
+__device__ __forceinline__ bool dc_elect() {
+    unsigned pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void dc_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -2538,7 +2561,7 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
     const int64_t bar_off = off;
     off += 64;  // mbarrier, TMEM slot
     const int64_t red_off = off;
-    off += 64;  // 8 warp partials of a loss sum
+    off += 64;  // 16 warp partials of a loss sum
     const int64_t smem_bytes = off + 1024;  // + alignment slack
     if (smem_bytes > 227 * 1024) return false;
     for (int l = 0; l < L; ++l)  // the widest read an M = 128 MN-major A operand can make from buffer l
@@ -2574,7 +2597,7 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
         auto it = param_of_node.find(node);
         if (it != param_of_node.end()) return it->second;
         const std::string p = "p" + num((int64_t)args.size());
-        params << (is_output ? "float* " : "const float* ") << p << ", ";
+        params << (is_output ? "float* __restrict__ " : "const float* __restrict__ ") << p << ", ";
         args.push_back({KernelArg::NodeBuffer, node, 0});
         param_of_node[node] = p;
         if (!is_output) reads.push_back(node);
@@ -2589,7 +2612,7 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
 
     // one per-element program evaluated on 16 accumulator columns of this thread's row: `product` is the input fed from
     // the accumulator, `internal` (if >= 0) the input fed from hv[j] (the activation's MN-major copy)
-    auto emit_program = [&](std::ostringstream& os, const Cluster& p, int product, int internal, int64_t N, const std::string& indent) {
+    auto emit_program = [&](std::ostringstream& os, const Cluster& p, int product, int internal, int64_t N, const std::string& indent, bool guarded) {
         os << indent << "{\n";
         for (size_t i = 0; i < p.inputs.size(); ++i) {
             if ((int)i == product || (int)i == internal) continue;
@@ -2597,7 +2620,10 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
         }
         os << indent << "    #pragma unroll\n" << indent << "    for (int j = 0; j < 16; ++j) {\n";
         os << indent << "        const int c = c0 + j;\n";
-        os << indent << "        if (c < " << N << " && row_ok) {\n";
+        // rows past the batch and padding columns: only where a program loads per-row data or feeds a sum (the loss); the hidden
+        // layers' widths are whole chunks, and what they compute on the zero rows of a ragged last tile is never used (the loss
+        // program zeroes dz on those rows, and every later product of zeros is zero)
+        os << indent << "        if (" << (guarded ? "c < " + num(N) + " && row_ok" : "true") << ") {\n";
         os << indent << "        const unsigned e = (unsigned)gm * " << unum(N) << " + (unsigned)c; (void)e;\n";
         std::function<std::string(int)> override_fn = [&](int input) -> std::string {
             if (input == product) return "acc[j]";
@@ -2637,36 +2663,40 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
     body << "    const unsigned bar = sbase + " << bar_off << "u;\n";
     body << "    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + " << bar_off + 16 << ");\n";
     body << "    float* red = reinterpret_cast<float*>(smem + " << red_off << ");\n";
-    body << "    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;\n";
+    body << "    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31, quad = warp & 3, grp = warp >> 2;  // 16 warps: TMEM lane quadrant x column group\n";
     body << "    const int r = quad * 32 + lane;  // this thread's row of the tile = its TMEM lane\n";
-    body << "    if (tid == 0) {\n        asm volatile(\"mbarrier.init.shared::cta.b64 [%0], 1;\" ::\"r\"(bar));\n"
+    body << "    const unsigned bar2 = bar + 8u;  // completion of the weight-gradient MMAs, which run under the backward epilogues\n";
+    body << "    if (tid == 0) {\n        asm volatile(\"mbarrier.init.shared::cta.b64 [%0], 1;\" ::\"r\"(bar));\n        asm volatile(\"mbarrier.init.shared::cta.b64 [%0], 1;\" ::\"r\"(bar2));\n"
             "        asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n    }\n";
     body << "    if (warp == 0) {\n        asm volatile(\"tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\" ::\"r\"((unsigned)__cvta_generic_to_shared(tmem_slot)), \"n\"("
          << tmem_cols << ") : \"memory\");\n        asm volatile(\"tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\" ::: \"memory\");\n    }\n";
     // weights
     for (int l = 0; l < L; ++l) {
         const int64_t K = W[l], N = W[l + 1], n16 = up(N, 16), kp = up(K, 8);
-        body << "    for (int i = tid; i < " << n16 * kp << "; i += 256) {  // W_" << l << "^T: forward B operand [n][k]\n";
+        body << "    for (int i = tid; i < " << n16 * kp << "; i += 512) {  // W_" << l << "^T: forward B operand [n][k]\n";
         body << "        const int n = i % " << n16 << ", k = i / " << n16 << ";\n";
-        body << "        *reinterpret_cast<float*>(smem + " << wf[l] << " + dc_km(" << km_lbo_w_f[l] << "u, n, k)) = (n < " << N << " && k < " << K << ") ? " << pw[l] << "[k * " << N
-             << " + n] : 0.f;\n    }\n";
+        body << "        dc_sts1(sbase + " << wf[l] << "u + dc_km(" << km_lbo_w_f[l] << "u, n, k), (n < " << N << " && k < " << K << ") ? " << pw[l] << "[k * " << N
+             << " + n] : 0.f);\n    }\n";
         if (wb[l] >= 0) {
             const int64_t k16 = up(K, 16), np = up(N, 8);
-            body << "    for (int i = tid; i < " << k16 * np << "; i += 256) {  // W_" << l << ": backward B operand [k][n]\n";
+            body << "    for (int i = tid; i < " << k16 * np << "; i += 512) {  // W_" << l << ": backward B operand [k][n]\n";
             body << "        const int n = i % " << np << ", k = i / " << np << ";\n";
-            body << "        *reinterpret_cast<float*>(smem + " << wb[l] << " + dc_km(" << km_lbo_w_b[l] << "u, k, n)) = (n < " << N << " && k < " << K << ") ? " << pw[l] << "[k * " << N
-                 << " + n] : 0.f;\n    }\n";
+            body << "        dc_sts1(sbase + " << wb[l] << "u + dc_km(" << km_lbo_w_b[l] << "u, k, n), (n < " << N << " && k < " << K << ") ? " << pw[l] << "[k * " << N
+                 << " + n] : 0.f);\n    }\n";
         }
     }
     body << "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n";
     body << "    asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n    __syncthreads();\n    asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
-    body << "    const unsigned tmem = *tmem_slot;\n";
+    // (broadcast through a shuffle so that the compiler knows the address is warp-uniform: tcgen05.mma takes uniform registers,
+    // and a value it cannot prove uniform costs an elect / broadcast loop per MMA on the one issuing thread)
+    body << "    const unsigned tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);\n";
     body << "    const unsigned tlane = tmem + ((unsigned)(quad * 32) << 16);\n";
-    body << "    unsigned phase = 0;\n    bool first_tile = true;\n";
+    body << "    unsigned phase = 0, phase2 = 0;\n    bool first_tile = true;\n";
     // per-thread partial sums carried across tiles
     for (int l = 0; l < L; ++l)
         if (ws_cs[l] >= 0)
-            for (int64_t i = 0; i < div_round_up(up(W[l + 1], 16) / 16, 2); ++i) body << "    float cs" << l << "_" << i << " = 0.f;\n";
+            for (int64_t i = 0; i < div_round_up(up(W[l + 1], 16) / 16, 4); ++i)
+                body << "    float cs" << l << "_" << i << "[16];\n    #pragma unroll\n    for (int j = 0; j < 16; ++j) cs" << l << "_" << i << "[j] = 0.f;\n";
     for (size_t s = 0; s < ch.sums.size(); ++s) body << "    float lsum" << s << " = 0.f;\n";
 
     auto idesc = [&](bool a_mn, bool b_mn, int64_t n) {
@@ -2675,7 +2705,7 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
     auto sync_then_issue = [&](std::ostringstream& o) {
         o << "        asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n";
         o << "        asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n        __syncthreads();\n";
-        o << "        if (tid == 0) {\n            asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
+        o << "        if (warp == 0 && dc_elect()) {\n            asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
     };
     auto commit_and_wait = [&](std::ostringstream& o) {
         o << "            dc_commit(bar);\n        }\n";
@@ -2683,18 +2713,20 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
     };
     auto store_km = [&](std::ostringstream& o, int64_t slot, int64_t kdim) {  // o[16] -> K-major A operand, columns below kdim
         o << "            #pragma unroll\n            for (int q = 0; q < 4; ++q)\n                if (c0 + 4 * q < " << kdim << ")\n";
-        o << "                    *reinterpret_cast<float4*>(smem + " << slot << " + dc_km(" << kActLbo << "u, r, c0 + 4 * q)) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);\n";
+        o << "                    dc_sts4(sbase + " << slot << "u + dc_km(" << kActLbo << "u, r, c0 + 4 * q), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);\n";
     };
     auto store_mn = [&](std::ostringstream& o, int64_t buf) {
         o << "            #pragma unroll\n            for (int q = 0; q < 4; ++q)\n";
-        o << "                *reinterpret_cast<float4*>(smem + " << buf << " + dc_mn(c0 + 4 * q, r)) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);\n";
+        o << "                dc_sts4(sbase + " << buf << "u + dc_mn(c0 + 4 * q, r), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);\n";
     };
     auto column_sums = [&](std::ostringstream& o, int l) {  // of the o[16] just produced, into layer l's accumulators
         if (ws_cs[l] < 0) return;
-        const int64_t per_warp = div_round_up(up(W[l + 1], 16) / 16, 2);
-        o << "            {\n                const float s = dc_colsum16(o, lane);\n";
-        for (int64_t i = 0; i < per_warp; ++i) o << "                if ((ch >> 1) == " << i << ") cs" << l << "_" << i << " += s;\n";
-        o << "            }\n";
+        const int64_t per_warp = div_round_up(up(W[l + 1], 16) / 16, 4);
+        // bias gradient: this thread's rows first (one register per column, across all tiles), the 128 rows of the tile slot
+        // at the end of the kernel
+        for (int64_t i = 0; i < per_warp; ++i) {
+            o << "            if ((ch >> 2) == " << i << ") {\n                #pragma unroll\n                for (int j = 0; j < 16; ++j) cs" << l << "_" << i << "[j] += o[j];\n            }\n";
+        }
     };
 
     int km_next = 0;  // K-major slots alternate: a tensor is written while the MMAs read the other slot
@@ -2704,22 +2736,22 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
         const int64_t K = W[0], kp = up(K, 8);
         const int64_t slot = km_slot[km_next];
         if (K % 4 == 0) {
-            body << "        for (int u = tid; u < " << 128 * (K / 4) << "; u += 256) {  // x_0 -> both operand layouts\n";
+            body << "        for (int u = tid; u < " << 128 * (K / 4) << "; u += 512) {  // x_0 -> both operand layouts\n";
             body << "            const int xr = u / " << K / 4 << ", xc = (u % " << K / 4 << ") * 4;\n";
             body << "            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);\n";
             body << "            if (tile * 128 + xr < M) x = *reinterpret_cast<const float4*>(" << px << " + (size_t)(tile * 128 + xr) * " << K << " + xc);\n";
-            body << "            *reinterpret_cast<float4*>(smem + " << slot << " + dc_km(" << kActLbo << "u, xr, xc)) = x;\n";
-            body << "            *reinterpret_cast<float4*>(smem + " << mn_act[0] << " + dc_mn(xc, xr)) = x;\n        }\n";
+            body << "            dc_sts4(sbase + " << slot << "u + dc_km(" << kActLbo << "u, xr, xc), x.x, x.y, x.z, x.w);\n";
+            body << "            dc_sts4(sbase + " << mn_act[0] << "u + dc_mn(xc, xr), x.x, x.y, x.z, x.w);\n        }\n";
         } else {
-            body << "        for (int u = tid; u < " << 128 * K << "; u += 256) {  // x_0 -> both operand layouts\n";
+            body << "        for (int u = tid; u < " << 128 * K << "; u += 512) {  // x_0 -> both operand layouts\n";
             body << "            const int xr = u / " << K << ", xc = u % " << K << ";\n";
             body << "            const float x = tile * 128 + xr < M ? " << px << "[(size_t)(tile * 128 + xr) * " << K << " + xc] : 0.f;\n";
-            body << "            *reinterpret_cast<float*>(smem + " << slot << " + dc_km(" << kActLbo << "u, xr, xc)) = x;\n";
-            body << "            *reinterpret_cast<float*>(smem + " << mn_act[0] << " + dc_mn(xc, xr)) = x;\n        }\n";
+            body << "            dc_sts1(sbase + " << slot << "u + dc_km(" << kActLbo << "u, xr, xc), x);\n";
+            body << "            dc_sts1(sbase + " << mn_act[0] << "u + dc_mn(xc, xr), x);\n        }\n";
         }
         if (kp != K) {
-            body << "        for (int u = tid; u < " << 128 * (kp - K) << "; u += 256)  // zero the k padding of x_0\n";
-            body << "            *reinterpret_cast<float*>(smem + " << slot << " + dc_km(" << kActLbo << "u, u / " << (kp - K) << ", " << K << " + u % " << (kp - K) << ")) = 0.f;\n";
+            body << "        for (int u = tid; u < " << 128 * (kp - K) << "; u += 512)  // zero the k padding of x_0\n";
+            body << "            dc_sts1(sbase + " << slot << "u + dc_km(" << kActLbo << "u, u / " << (kp - K) << ", " << K << " + u % " << (kp - K) << "), 0.f);\n";
         }
     }
     // ---- forward layers ------------------------------------------------------------------------------------------------
@@ -2736,13 +2768,13 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
         commit_and_wait(body);
         if (l < L - 1) {
             const int64_t out_slot = km_slot[km_next];
-            body << "        for (int ch = half; ch < " << n16 / 16 << "; ch += 2) {  // bias + activation on the accumulator -> x_" << l + 1 << " in shared memory\n";
+            body << "        for (int ch = grp; ch < " << n16 / 16 << "; ch += 4) {  // bias + activation on the accumulator -> x_" << l + 1 << " in shared memory\n";
             body << "            const int c0 = ch * 16;\n            float acc[16], o[16];\n            dc_ld16(tlane + (unsigned)c0, acc);\n";
             if (fc.epilogue.empty()) {
                 body << "            #pragma unroll\n            for (int j = 0; j < 16; ++j) o[j] = acc[j];\n";
             } else {
                 const Cluster& p = fc.epilogue[0];
-                emit_program(body, p, fc.epilogue_product_input, -1, N, "            ");
+                emit_program(body, p, fc.epilogue_product_input, -1, N, "            ", N % 16 != 0);
                 body << "                o[j] = t" << p.output_ops[0] << ";\n";
                 body << "                } else o[j] = 0.f;\n                }\n            }\n";
             }
@@ -2756,10 +2788,10 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
             for (size_t i = 0; i < p.inputs.size(); ++i)
                 if (p.inputs[i].node_id == fc.outputs[0]) product = (int)i;
             const int64_t out_slot = km_slot[km_next];
-            body << "        for (int ch = half; ch < " << n16 / 16 << "; ch += 2) {  // loss program on the last product -> dz_" << l << "\n";
+            body << "        for (int ch = grp; ch < " << n16 / 16 << "; ch += 4) {  // loss program on the last product -> dz_" << l << "\n";
             body << "            const int c0 = ch * 16;\n            float acc[16], o[16];\n            dc_ld16(tlane + (unsigned)c0, acc);\n";
             if (!fc.epilogue.empty()) return false;  // (a bias absorbed into the last layer would need two programs here)
-            emit_program(body, p, product, -1, N, "            ");
+            emit_program(body, p, product, -1, N, "            ", true);
             body << "                o[j] = t" << p.output_ops[ch.loss_gradient_output] << ";\n";
             for (size_t s = 0; s < ch.sums.size(); ++s) body << "                lsum" << s << " += t" << p.output_ops[ch.sums[s].output] << ";\n";
             body << "                } else o[j] = 0.f;\n                }\n            }\n";
@@ -2777,19 +2809,24 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
         const int64_t dz_mn = l == L - 1 ? mn_dy : mn_act[l + 1];  // dz_l lives where x_{l+1} was
         const bool has_b = l > 0 || has_dx;
         body << "        // layer " << l << ": dW_" << l << " += x_" << l << "^T dz_" << l << (has_b ? "; dz W^T -> activation backward\n" : "\n");
+        // the backward product first (its epilogue is the critical path), then the weight-gradient MMAs, which the tensor core
+        // works through while the epilogue warps read the accumulator and evaluate the activation backward; the epilogue's
+        // stores (dz_{l-1} over x_l's MN-major copy, an operand of those MMAs) wait for their completion on bar2
         sync_then_issue(body);
+        if (has_b) {
+            body << "            #pragma unroll\n            for (int kk = 0; kk < " << np / 8 << "; ++kk)\n";
+            body << "                dc_mma(tmem, dc_desc(sbase + " << dz_slot << "u + kk * " << 2 * kActLbo << "u, " << kActLbo << "u, 128u, 0u), dc_desc(sbase + " << wb[l] << "u + kk * "
+                 << 2 * km_lbo_w_b[l] << "u, " << km_lbo_w_b[l] << "u, 128u, 0u), " << idesc(false, false, k16) << "u, kk != 0 ? 1u : 0u);\n";
+            body << "            dc_commit(bar);\n";
+        }
         {
             const int64_t a_buf = dw_a_is_dz[l] ? dz_mn : mn_act[l], b_buf = dw_a_is_dz[l] ? mn_act[l] : dz_mn;
             body << "            #pragma unroll\n            for (int kk = 0; kk < 16; ++kk)\n";
             body << "                dc_mma(tmem + " << dw_col[l] << "u, dc_desc(sbase + " << a_buf << "u + kk * 1024u, 16384u, 512u, 1u), dc_desc(sbase + " << b_buf
                  << "u + kk * 1024u, 16384u, 512u, 1u), " << idesc(true, true, dw_cols[l]) << "u, (!first_tile || kk != 0) ? 1u : 0u);\n";
+            body << "            dc_commit(bar2);\n        }\n";
         }
-        if (has_b) {
-            body << "            #pragma unroll\n            for (int kk = 0; kk < " << np / 8 << "; ++kk)\n";
-            body << "                dc_mma(tmem, dc_desc(sbase + " << dz_slot << "u + kk * " << 2 * kActLbo << "u, " << kActLbo << "u, 128u, 0u), dc_desc(sbase + " << wb[l] << "u + kk * "
-                 << 2 * km_lbo_w_b[l] << "u, " << km_lbo_w_b[l] << "u, 128u, 0u), " << idesc(false, false, k16) << "u, kk != 0 ? 1u : 0u);\n";
-        }
-        commit_and_wait(body);
+        if (has_b) body << "        dc_wait(bar, phase); phase ^= 1u;\n        asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
         if (l > 0) {
             const Cluster& bc = clusters[ch.backward[l]];
             const Cluster& p = bc.epilogue[0];
@@ -2797,20 +2834,21 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
             for (size_t i = 0; i < p.inputs.size(); ++i)
                 if ((int)i != bc.epilogue_product_input && g.ops().nodes[p.inputs[i].node_id].op.kind != OpKind::Input) internal = (int)i;
             const int64_t out_slot = km_slot[km_next];
-            body << "        for (int ch = half; ch < " << k16 / 16 << "; ch += 2) {  // activation backward -> dz_" << l - 1 << " (over x_" << l << "'s MN-major copy)\n";
+            body << "        for (int ch = grp; ch < " << k16 / 16 << "; ch += 4) {  // activation backward -> dz_" << l - 1 << " (over x_" << l << "'s MN-major copy)\n";
             body << "            const int c0 = ch * 16;\n            float acc[16], o[16], hv[16];\n            dc_ld16(tlane + (unsigned)c0, acc);\n";
             body << "            #pragma unroll\n            for (int q = 0; q < 4; ++q) {\n";
-            body << "                const float4 h = *reinterpret_cast<const float4*>(smem + " << mn_act[l] << " + dc_mn(c0 + 4 * q, r));\n";
+            body << "                const float4 h = dc_lds4(sbase + " << mn_act[l] << "u + dc_mn(c0 + 4 * q, r));\n";
             body << "                hv[4 * q] = h.x; hv[4 * q + 1] = h.y; hv[4 * q + 2] = h.z; hv[4 * q + 3] = h.w;\n            }\n";
-            emit_program(body, p, bc.epilogue_product_input, internal, K, "            ");
+            emit_program(body, p, bc.epilogue_product_input, internal, K, "            ", K % 16 != 0);
             body << "                o[j] = t" << p.output_ops[0] << ";\n";
             body << "                } else o[j] = 0.f;\n                }\n            }\n";
+            body << "            dc_wait(bar2, phase2);  // x_" << l << "'s MN-major copy is free (a completed phase answers at once on later chunks)\n";
             store_km(body, out_slot, up(K, 8));
             store_mn(body, mn_act[l]);
             column_sums(body, l - 1);
-            body << "        }\n";
+            body << "        }\n        phase2 ^= 1u;\n";
         } else if (has_dx) {
-            body << "        for (int ch = half; ch < " << k16 / 16 << "; ch += 2) {  // gradient with respect to x_0 -> global memory\n";
+            body << "        for (int ch = grp; ch < " << k16 / 16 << "; ch += 4) {  // gradient with respect to x_0 -> global memory\n";
             body << "            const int c0 = ch * 16;\n            float acc[16];\n            dc_ld16(tlane + (unsigned)c0, acc);\n";
             body << "            if (row_ok) {\n";
             if (K % 4 == 0) {
@@ -2821,6 +2859,7 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
             }
             body << "            }\n        }\n";
         }
+        if (l == 0) body << "        dc_wait(bar2, phase2); phase2 ^= 1u;  // the next tile's x_0 overwrites operands of the last weight-gradient MMAs\n";
     }
     body << "        first_tile = false;\n";
     body << "        asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n        __syncthreads();  // the next tile's x_0 overwrites operands of this tile's last MMAs (waited for above)\n";
@@ -2829,7 +2868,7 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
     body << "    asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
     for (int l = 0; l < L; ++l) {
         const int64_t K = W[l], N = W[l + 1];
-        body << "    for (int ch = half; ch < " << dw_cols[l] / 16 << "; ch += 2) {  // this CTA's partial dW_" << l << "\n";
+        body << "    for (int ch = grp; ch < " << dw_cols[l] / 16 << "; ch += 4) {  // this CTA's partial dW_" << l << "\n";
         body << "        const int c0 = ch * 16;\n        float acc[16];\n        dc_ld16(tlane + " << dw_col[l] << "u + (unsigned)c0, acc);\n";
         body << "        float* dst = ws + " << ws_dw[l] << " + (size_t)blockIdx.x * " << K * N << ";\n";
         body << "        #pragma unroll\n        for (int j = 0; j < 16; ++j) {\n";
@@ -2837,24 +2876,24 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
         else body << "            if (r < " << K << " && c0 + j < " << N << ") dst[r * " << N << " + c0 + j] = acc[j];  // lanes = k, columns = n\n";
         body << "        }\n    }\n";
         if (ws_cs[l] >= 0) {
-            const int64_t per_warp = div_round_up(up(N, 16) / 16, 2);
+            const int64_t per_warp = div_round_up(up(N, 16) / 16, 4);
             for (int64_t i = 0; i < per_warp; ++i) {
-                body << "    {\n        const int c = (" << 2 * i << " + half) * 16 + dc_colsum16_column(lane);\n";
-                body << "        if ((lane & 1) == 0 && c < " << N << ") ws[" << ws_cs[l] << " + (size_t)(blockIdx.x * 4 + quad) * " << N << " + c] = cs" << l << "_" << i << ";\n    }\n";
+                body << "    {\n        const float s = dc_colsum16(cs" << l << "_" << i << ", lane);\n        const int c = (" << 4 * i << " + grp) * 16 + dc_colsum16_column(lane);\n";
+                body << "        if ((lane & 1) == 0 && c < " << N << ") ws[" << ws_cs[l] << " + (size_t)(blockIdx.x * 4 + quad) * " << N << " + c] = s;\n    }\n";
             }
         }
     }
     for (size_t s = 0; s < ch.sums.size(); ++s) {
         body << "    {\n        float v = lsum" << s << ";\n        #pragma unroll\n        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);\n";
         body << "        __syncthreads();\n        if (lane == 0) red[warp] = v;\n        __syncthreads();\n";
-        body << "        if (tid == 0) {\n            float t = red[0];\n            #pragma unroll\n            for (int w = 1; w < 8; ++w) t += red[w];\n";
+        body << "        if (tid == 0) {\n            float t = red[0];\n            #pragma unroll\n            for (int w = 1; w < 16; ++w) t += red[w];\n";
         body << "            ws[" << ws_sum[s] << " + blockIdx.x] = t;\n        }\n    }\n";
     }
     body << "    asm volatile(\"tcgen05.fence::before_thread_sync;\" ::: \"memory\");\n    __syncthreads();\n";
     body << "    if (warp == 0) {\n        asm volatile(\"tcgen05.fence::after_thread_sync;\" ::: \"memory\");\n";
     body << "        asm volatile(\"tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\" ::\"r\"(tmem), \"n\"(" << tmem_cols << ") : \"memory\");\n    }\n";
 
-    os << "extern \"C\" __global__ void __launch_bounds__(256, 1) " << name << "(" << params.str() << "float* ws, const unsigned* dsc_step) {\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(512, 1) " << name << "(" << params.str() << "float* __restrict__ ws, const unsigned* dsc_step) {\n";
     os << "    (void)dsc_step;\n" << body.str() << "}\n";
 
     // ---- split sums: every per-CTA partial set -> its node, one launch -------------------------------------------------------
@@ -2889,7 +2928,7 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
     KernelLaunch l;
     l.entry = name;
     l.grid_x = (uint32_t)grid;
-    l.block = 256;
+    l.block = 512;
     l.smem = (uint32_t)smem_bytes;
     std::ostringstream label;
     label << "DenseChain (" << L << " layers:";
