@@ -210,6 +210,7 @@ Graph::Graph(SharedParameters parameters, const OpGraph& ops, DataParallel dp)
     eliminate_dead_code();
     hoist_all_reduce_views();
     sink_permutations_into_per_element();
+    sink_views_into_selects();
     build_clusters();
 }
 
@@ -464,6 +465,50 @@ void Graph::sink_permutations_into_per_element() {
             }
             node.shape = shape;
             for (auto [dst, k] : cons[id]) ops_.nodes[dst].in[k].chain = ViewChain::identity(shape.element_count());
+            changed = true;
+            break;  // consumer lists are stale
+        }
+    }
+}
+
+static bool edge_is_fusable(const OpGraph& ops, int dst, const OpEdge& e);
+
+// Concatenation chains.  `a.concat(b, axis)` (array.rs: two pads and a CompareAndSelect on the axis coordinate) reads both
+// operands through clamping pad views, and a chain of k concats -- the ten per-level feature pairs of a hash grid joined
+// into one [m, 20] MLP input, examples/image_fit/main.rs:201-215 -- re-reads and re-writes the growing prefix k times
+// (nine kernels and 226 MB for [262144, 20]).  A select whose only reader is another select reading it through a view
+// is evaluated in that reader's index space instead: the view is appended to the select's own operand chains (loads of
+// arrays that exist in memory anyway, literals, coordinates), the edge becomes an identity and the two fuse; repeated
+// along the chain, all k selects become ONE kernel that reads each piece once and writes the result once.  Values are
+// selected, never recomputed differently: bit-exact.
+void Graph::sink_views_into_selects() {
+    for (bool changed = true; changed;) {
+        changed = false;
+        auto cons = ops_.consumers();
+        for (int id = (int)ops_.nodes.size() - 1; id >= 0; --id) {
+            OpNode& node = ops_.nodes[id];
+            if (!node.alive || node.op.kind != OpKind::CompareAndSelect || cons[id].size() != 1) continue;
+            const auto [dst, k] = cons[id][0];
+            OpNode& reader = ops_.nodes[dst];
+            OpEdge& edge = reader.in[k];
+            if (!reader.alive || reader.op.kind != OpKind::CompareAndSelect || edge.chain.is_identity() ||
+                reader.shape.element_count() != edge.chain.output_count || edge.chain.output_count > 4 * edge.chain.input_count)
+                continue;
+            // operands computed in registers for this select would have to be spilled to memory: then nothing moves
+            bool ok = true;
+            for (const OpEdge& e : node.in) {
+                const OpNode& src = ops_.nodes[e.src];
+                if (!src.op.is_inline_source() && src.op.kind != OpKind::Input && edge_is_fusable(ops_, id, e)) ok = false;
+            }
+            if (!ok) continue;
+            const ViewChain view = edge.chain;
+            const Shape shape = edge.arg_shape;
+            for (OpEdge& e : node.in) {
+                e.chain.append(view);
+                e.arg_shape = shape;
+            }
+            node.shape = shape;
+            edge.chain = ViewChain::identity(shape.element_count());
             changed = true;
             break;  // consumer lists are stale
         }

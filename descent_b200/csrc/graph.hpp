@@ -162,6 +162,7 @@ private:
     void reuse_activation_sign();
     void hoist_all_reduce_views();
     void sink_permutations_into_per_element();
+    void sink_views_into_selects();
     void absorb_per_element_epilogues(std::vector<Cluster>& clusters);
     void absorb_column_sums(std::vector<Cluster>& clusters);
     void absorb_max_pools(std::vector<Cluster>& clusters);
