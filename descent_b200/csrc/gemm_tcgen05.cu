@@ -97,6 +97,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn_major,
            ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 template <int BN, int STAGES>
 struct SharedStorage {
     alignas(1024) float a[STAGES][BM * BK];
@@ -118,7 +129,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     using Storage = SharedStorage<BN, STAGES>;
     Storage& s = *reinterpret_cast<Storage*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    // (shuffles: warp-uniform values the compiler can keep in uniform registers, which TMA and tcgen05.mma operands need)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;
     const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN, num_tiles = tiles_m * tiles_n, k_blocks = (k + BK - 1) / BK;  // TMA zero-fills out-of-range boxes
     // split K: work item = (split, tile); split s accumulates k-blocks [s * kbs, (s + 1) * kbs) into c + s * m * n
     const int kbs = (k_blocks + splits - 1) / splits, num_items = num_tiles * splits;
@@ -147,9 +159,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = s.tmem_base;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, s.tmem_base, 0);
 
-    if (warp == 0 && lane == 0) {
+    // the single producer / issuer threads are chosen with elect.sync: under `lane == 0` the compiler must assume any subset
+    // of lanes and wraps every TMA / MMA in an elect-and-broadcast loop (BRA.U.ANY per instruction in SASS)
+    if (warp == 0) { if (elect_one()) {
         // ===== TMA producer =====
         uint32_t stage = 0, phase = 0;
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -172,7 +186,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } } else if (warp == 1) { if (elect_one()) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
         // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused; step 32 B per UMMA_K inside the 128 B row.
@@ -204,7 +218,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tcgen05_commit(&s.tmem_full[acc_stage]);  // accumulator complete
             if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
         }
-    } else if (warp >= 4) {
+    } } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> global =====
         const int quad = warp % 4;  // TMEM lanes [32*quad, 32*quad+32)
         uint32_t acc_stage = 0, acc_phase = 0;
