@@ -2404,6 +2404,102 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
     return code;
 }
 
+}  // namespace
+
+// ---- scatter_add groups ---------------------------------------------------------------------------------------------------
+// The ten hash-grid levels of image_fit (examples/image_fit/main.rs:190-199) each scatter into their own small table at
+// the same point of the backward pass: ten partial kernels of a few hundred CTAs and ten ordered-sum kernels of 1-256
+// CTAs, launched one after the other, each ending in a partial wave.  Independent scatter_adds of one dependency level
+// whose tables live in shared memory are launched together: ONE partial kernel and ONE sum kernel whose block ranges
+// select the member (its code is the member's own kernel, turned into a device function).  Every member keeps its own
+// partials and its own fixed order of additions, so results are bit-identical to the ungrouped launches.
+bool generate_scatter_group_code(const Graph& g, const std::vector<int>& members, const CodegenOptions& opt, ClusterCode* out) {
+    if (members.size() < 2) return false;
+    const int host = members.back();
+    const std::string name = "k" + num(host);
+    std::ostringstream src, part_params, sum_params, part_body, sum_body;
+    KernelLaunch part, sum;
+    int64_t scratch = 0, part_blocks = 0, sum_blocks = 0, max_table = 0;
+    double bytes = 0;
+    auto replace_once = [](std::string& text, const std::string& from, const std::string& to) {
+        const size_t at = text.find(from);
+        if (at == std::string::npos) return false;
+        text.replace(at, from.size(), to);
+        return true;
+    };
+    for (size_t m = 0; m < members.size(); ++m) {
+        const int ci = members[m];
+        const Cluster& c = g.clusters()[ci];
+        if (c.kind != ClusterKind::ScatterAdd) return false;
+        ClusterCode code = gen_scatter_add(g, c, ci, opt);
+        if (code.launches.size() != 2 || code.launches[0].grid_y != 1 || code.source.find("per-warp sorted partial sums") == std::string::npos) return false;
+        const std::string k = "k" + num(ci);
+        std::string text = code.source;
+        if (!replace_once(text, "extern \"C\" __global__ void __launch_bounds__(256) " + k + "_part(", "__device__ __forceinline__ void " + k + "_part_body(const unsigned dsc_bx, float* table, ") ||
+            !replace_once(text, "    __shared__ float table[ROWS * INNER];\n", "") ||
+            !replace_once(text, "extern \"C\" __global__ void __launch_bounds__(1024) " + k + "_sum(", "__device__ __forceinline__ void " + k + "_sum_body(const unsigned dsc_bx, float (*red)[33], ") ||
+            !replace_once(text, "    __shared__ float red[32][33];\n", ""))
+            return false;
+        text = replace_all(replace_all(text, "blockIdx.x", "dsc_bx"), "blockIdx.y", "0u");
+        src << text;
+        const OpNode& node = g.ops().nodes[c.node_id];
+        max_table = std::max<int64_t>(max_table, node.shape.element_count());
+        const KernelLaunch& p = code.launches[0];
+        const KernelLaunch& sm = code.launches[1];
+        const int64_t base = scratch;
+        scratch += div_round_up(code.scratch_bytes, 256) * 256;
+        part_body << "    " << (m ? "else " : "") << "if (blockIdx.x < " << unum(part_blocks + p.grid_x) << ") " << k << "_part_body(blockIdx.x - " << unum(part_blocks) << ", table, ";
+        for (size_t a = 0; a < p.args.size(); ++a) {
+            const bool is_scratch = p.args[a].kind == KernelArg::Scratch;
+            part_params << (is_scratch ? "float* " : "const float* ") << "a" << m << "_" << a << ", ";
+            part_body << "a" << m << "_" << a << ", ";
+            KernelArg arg = p.args[a];
+            if (is_scratch) arg.scratch_offset += base;
+            part.args.push_back(arg);
+        }
+        part_body << "dsc_step);\n";
+        sum_body << "    " << (m ? "else " : "") << "if (blockIdx.x < " << unum(sum_blocks + sm.grid_x) << ") " << k << "_sum_body(blockIdx.x - " << unum(sum_blocks) << ", red, ";
+        for (size_t a = 0; a < sm.args.size(); ++a) {
+            const bool is_out = a + 1 == sm.args.size();
+            sum_params << (is_out ? "float* " : "const float* ") << "b" << m << "_" << a << ", ";
+            sum_body << "b" << m << "_" << a << ", ";
+            KernelArg arg = sm.args[a];
+            if (arg.kind == KernelArg::Scratch) arg.scratch_offset += base;
+            sum.args.push_back(arg);
+        }
+        sum_body << "dsc_step);\n";
+        part_blocks += p.grid_x;
+        sum_blocks += sm.grid_x;
+        bytes += p.algorithmic_bytes;
+        for (const auto& in : c.inputs) out->extra_reads.push_back(in.node_id);
+        out->extra_writes.push_back(c.outputs[0]);
+    }
+    src << "// " << members.size() << " scatter_add partial kernels of one level, one launch: block ranges select the table\n";
+    src << "extern \"C\" __global__ void __launch_bounds__(256) " << name << "_parts(" << part_params.str() << "const unsigned* dsc_step) {\n";
+    src << "    __shared__ float table[" << max_table << "];\n" << part_body.str() << "}\n";
+    src << "// ... and their ordered sums\n";
+    src << "extern \"C\" __global__ void __launch_bounds__(1024) " << name << "_sums(" << sum_params.str() << "const unsigned* dsc_step) {\n";
+    src << "    __shared__ float red[32][33];\n" << sum_body.str() << "}\n\n";
+    out->source = src.str();
+    out->scratch_bytes = scratch;
+    part.entry = name + "_parts";
+    part.grid_x = (uint32_t)part_blocks;
+    part.label = "ScatterAdd group (" + num((int64_t)members.size()) + " tables)";
+    part.cluster = host;
+    part.covers = members;
+    part.algorithmic_bytes = bytes;
+    sum.entry = name + "_sums";
+    sum.grid_x = (uint32_t)sum_blocks;
+    sum.block = 1024;
+    sum.label = "ScatterSum group (" + num((int64_t)members.size()) + " tables)";
+    sum.cluster = host;
+    out->launches.push_back(part);
+    out->launches.push_back(sum);
+    return true;
+}
+
+namespace {
+
 // ---- dense chains (graph.hpp DenseChain): a whole MLP training step per 128-row tile in ONE kernel -----------------
 // SURVEY.md section 8f-1 (examples/image_fit/main.rs:50-118,259-275; module.rs:70-90).  One persistent CTA per SM walks
 // 128-row tiles of the batch.  Per tile, in order: the forward layers (tcgen05 TF32 MMAs, accumulator in TMEM, the

@@ -66,6 +66,10 @@ ClusterCode generate_cluster_code(const Graph& graph, int cluster_index, const C
 // widths rule it out (the clusters then run one by one as usual).
 bool generate_dense_chain_code(const Graph& graph, const DenseChain& chain, const CodegenOptions& options, ClusterCode* out);
 
+// One partial launch + one sum launch for several independent shared-memory-table scatter_adds of one level (cluster
+// indices in execution order; the code runs at the last one's slot); false if a member does not qualify.
+bool generate_scatter_group_code(const Graph& graph, const std::vector<int>& members, const CodegenOptions& options, ClusterCode* out);
+
 // host-side evaluation of a chain (tests, layout heuristics): consumer element -> producer element
 int64_t eval_chain(const ViewChain& chain, int64_t e);
 

@@ -65,6 +65,23 @@ std::string generate_graph_source(const Graph& graph, const CodegenOptions& opti
         pregenerated[host] = std::move(code);
         has_pregenerated[host] = 1;
     }
+    // scatter_add groups: maximal runs of ScatterAdd clusters of one level (clusters are in level order)
+    for (int ci = 0; ci < nc;) {
+        int cj = ci;
+        if (graph.clusters()[ci].kind == ClusterKind::ScatterAdd)
+            while (cj + 1 < nc && graph.clusters()[cj + 1].kind == ClusterKind::ScatterAdd && graph.clusters()[cj + 1].level == graph.clusters()[ci].level) cj += 1;
+        if (cj > ci) {
+            std::vector<int> members;
+            for (int k = ci; k <= cj; ++k) members.push_back(k);
+            ClusterCode code;
+            if (generate_scatter_group_code(graph, members, options, &code)) {
+                for (int k = ci; k < cj; ++k) skipped[k] = 1;
+                pregenerated[cj] = std::move(code);
+                has_pregenerated[cj] = 1;
+            }
+        }
+        ci = cj + 1;
+    }
     for (const OperandPrologue& cand : graph.operand_prologues()) {
         bool feeds_dense_chain = false;
         for (const auto& use : cand.uses) feeds_dense_chain |= in_dense_chain[use.cluster] != 0;
