@@ -779,3 +779,124 @@ class Example:
         out = ctypes.c_void_p()
         _check(lib.dsc_example_graph_json(self.env._h, which, ctypes.byref(out)))
         return json.loads(_take_string(out))
+
+
+# ---- host random numbers and data front ends of the reference's examples ---------------
+c_u8_p = ctypes.POINTER(ctypes.c_uint8)
+c_u64_p = ctypes.POINTER(ctypes.c_uint64)
+
+
+class ChaCha20Rng:
+    """`rand_chacha::ChaCha20Rng::seed_from_u64(seed)` with the rand 0.8 sampling rules the examples use
+    (descent_b200/csrc/host_rng.hpp): next_u32 (the per-step rand_seed), Open01 floats, gen_range, shuffle."""
+
+    def __init__(self, seed):
+        self._h = ctypes.c_void_p()
+        _check(lib.dsc_rng_create(ctypes.c_uint64(seed), ctypes.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            lib.dsc_rng_destroy(self._h)
+            self._h = None
+
+    def next_u32(self):
+        out = ctypes.c_uint32()
+        _check(lib.dsc_rng_next_u32(self._h, ctypes.byref(out)))
+        return out.value
+
+    def next_u64(self):
+        out = ctypes.c_uint64()
+        _check(lib.dsc_rng_next_u64(self._h, ctypes.byref(out)))
+        return out.value
+
+    def open01(self, count):
+        out = np.empty(count, dtype=np.float32)
+        _check(lib.dsc_rng_open01_f32(self._h, out.ctypes.data_as(c_f32_p), ctypes.c_size_t(count)))
+        return out
+
+    def gen_range(self, low, high, u32=False):
+        """rng.gen_range(low..high): `u32=True` for u32 bounds, otherwise usize (64-bit draws) as in image_fit/main.rs:377."""
+        out = ctypes.c_uint64()
+        _check(lib.dsc_rng_gen_range(self._h, ctypes.c_uint64(low), ctypes.c_uint64(high), int(u32), ctypes.byref(out)))
+        return out.value
+
+    def shuffle(self, indices):
+        """indices.shuffle(&mut rng) (fashion_mnist/main.rs:382): returns the shuffled copy as uint64."""
+        arr = np.ascontiguousarray(indices, dtype=np.uint64).copy()
+        _check(lib.dsc_rng_shuffle(self._h, arr.ctypes.data_as(c_u64_p), ctypes.c_size_t(arr.size)))
+        return arr
+
+
+def _reset_parameter_rng(self, param, rng):
+    """Environment::reset_parameter(param, &mut rng) with the reference's generator (environment.rs:190-202)."""
+    _check(lib.dsc_env_reset_parameter_rng(self._h, param.id, rng._h))
+
+
+Environment.reset_parameter_rng = _reset_parameter_rng
+
+
+def _take_bytes(ptr, size):
+    data = ctypes.string_at(ptr, size)
+    lib.dsc_free_bytes(ptr)
+    return data
+
+
+def load_gz_bytes(path):
+    """examples/fashion_mnist/main.rs:13-19."""
+    ptr, size = c_u8_p(), ctypes.c_size_t()
+    _check(lib.dsc_load_gz_bytes(os.fsencode(path), ctypes.byref(ptr), ctypes.byref(size)))
+    return _take_bytes(ptr, size.value)
+
+
+def gunzip(data):
+    ptr, size = c_u8_p(), ctypes.c_size_t()
+    _check(lib.dsc_gunzip(data, ctypes.c_size_t(len(data)), ctypes.byref(ptr), ctypes.byref(size)))
+    return _take_bytes(ptr, size.value)
+
+
+def read_images_info(data):
+    """(images, rows, cols) of an IDX image file (fashion_mnist/main.rs:26-33)."""
+    n, r, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    _check(lib.dsc_idx_images_info(data, ctypes.c_size_t(len(data)), ctypes.byref(n), ctypes.byref(r), ctypes.byref(c)))
+    return n.value, r.value, c.value
+
+
+def read_labels_info(data):
+    n = ctypes.c_uint32()
+    _check(lib.dsc_idx_labels_info(data, ctypes.c_size_t(len(data)), ctypes.byref(n)))
+    return n.value
+
+
+def unpack_images(data, indices):
+    """[len(indices), rows * cols] float32 = byte / 255 (fashion_mnist/main.rs:42-60)."""
+    _, rows, cols = read_images_info(data)
+    idx = np.ascontiguousarray(indices, dtype=np.uint64)
+    out = np.empty((idx.size, rows * cols), dtype=np.float32)
+    _check(lib.dsc_idx_unpack_images(data, ctypes.c_size_t(len(data)), idx.ctypes.data_as(c_u64_p), ctypes.c_size_t(idx.size), out.ctypes.data_as(c_f32_p)))
+    return out
+
+
+def unpack_labels(data, indices):
+    idx = np.ascontiguousarray(indices, dtype=np.uint64)
+    out = np.empty(idx.size, dtype=np.float32)
+    _check(lib.dsc_idx_unpack_labels(data, ctypes.c_size_t(len(data)), idx.ctypes.data_as(c_u64_p), ctypes.c_size_t(idx.size), out.ctypes.data_as(c_f32_p)))
+    return out
+
+
+def decode_jpeg_rgb(data):
+    """[height, width, 3] uint8 of a baseline JPEG file (image_fit/main.rs:278-282)."""
+    w, h, ptr = ctypes.c_int(), ctypes.c_int(), c_u8_p()
+    _check(lib.dsc_jpeg_decode_rgb(data, ctypes.c_size_t(len(data)), ctypes.byref(w), ctypes.byref(h), ctypes.byref(ptr)))
+    raw = _take_bytes(ptr, w.value * h.value * 3)
+    return np.frombuffer(raw, dtype=np.uint8).reshape(h.value, w.value, 3).copy()
+
+
+def write_ppm(path, rgb):
+    """A predicted image [height, width, 3] in [0, 1] as a binary PPM (byte = x * 255 + 0.5 clamped, image_fit/main.rs:423-426)."""
+    arr = np.ascontiguousarray(rgb, dtype=np.float32)
+    _check(lib.dsc_write_ppm(os.fsencode(path), arr.ctypes.data_as(c_f32_p), arr.shape[1], arr.shape[0]))
+
+
+def write_csv_row(stream, values):
+    """One row of the examples' statistics files (fashion_mnist/main.rs:398-412, image_fit/main.rs:408-416): `"label", v, v, ...`."""
+    stream.write(", ".join('"%s"' % v if isinstance(v, str) else repr(float(v)) if isinstance(v, float) else str(v) for v in values) + "\n")

@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
                 if verbose and warn:
                     sys.stderr.write(warn)
     if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-L", CUDA_LIB, "-lnvrtc", "-ldl", "-Xlinker", "-rpath," + CUDA_LIB, "-cudart", "static"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-L", CUDA_LIB, "-lnvrtc", "-ldl", "-lz", "-Xlinker", "-rpath," + CUDA_LIB, "-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))

@@ -4,6 +4,8 @@
 
 #include "../../include/descent_api.h"
 #include "examples.hpp"
+#include "host_io.hpp"
+#include "host_rng.hpp"
 
 using namespace descent;
 
@@ -71,6 +73,8 @@ Array arr(dsc_scope* s, int node) {
 DualArray dual(dsc_scope* s, int v, int g) { return DualArray(arr(s, v), arr(s, g)); }
 
 }  // namespace
+
+struct dsc_rng { descent::ChaCha20Rng rng; };
 
 extern "C" {
 
@@ -459,5 +463,59 @@ int dsc_example_graph_json(dsc_env* env, int which, char** json_out) {
         *json_out = dup_string(which == 0 ? ex.train_graph_json : ex.test_graph_json);
     });
 }
+
+// ---- host random numbers and data front ends ----------------------------------------------
+static void bytes_out(std::vector<uint8_t>&& v, uint8_t** out, size_t* size) {
+    *out = static_cast<uint8_t*>(std::malloc(std::max<size_t>(v.size(), 1)));
+    if (!*out) throw std::bad_alloc();
+    std::memcpy(*out, v.data(), v.size());
+    if (size) *size = v.size();
+}
+int dsc_rng_create(uint64_t seed, dsc_rng** out) {
+    *out = nullptr;
+    return guarded([&] { *out = new dsc_rng{descent::ChaCha20Rng::seed_from_u64(seed)}; });
+}
+int dsc_rng_destroy(dsc_rng* rng) { delete rng; return DSC_OK; }
+int dsc_rng_next_u32(dsc_rng* rng, uint32_t* out) { return guarded([&] { *out = rng->rng.next_u32(); }); }
+int dsc_rng_next_u64(dsc_rng* rng, uint64_t* out) { return guarded([&] { *out = rng->rng.next_u64(); }); }
+int dsc_rng_open01_f32(dsc_rng* rng, float* out, size_t count) {
+    return guarded([&] { for (size_t i = 0; i < count; ++i) out[i] = rng->rng.open01(); });
+}
+int dsc_rng_gen_range(dsc_rng* rng, uint64_t low, uint64_t high, int as_u32, uint64_t* out) {
+    return guarded([&] {
+        DSC_CHECK(low < high && (!as_u32 || high <= 0xffffffffull), "gen_range needs low < high (and 32-bit bounds for u32 draws)");
+        *out = as_u32 ? (uint64_t)rng->rng.gen_range_u32((uint32_t)low, (uint32_t)high) : rng->rng.gen_range_u64(low, high);
+    });
+}
+int dsc_rng_shuffle(dsc_rng* rng, uint64_t* indices, size_t count) { return guarded([&] { rng->rng.shuffle(indices, count); }); }
+int dsc_env_reset_parameter_rng(dsc_env* env, int param, dsc_rng* rng) {
+    return guarded([&] { env->env->reset_parameter(env->param(param), rng->rng); });
+}
+int dsc_load_gz_bytes(const char* path, uint8_t** out, size_t* size) { *out = nullptr; return guarded([&] { bytes_out(descent::load_gz_bytes(path), out, size); }); }
+int dsc_gunzip(const uint8_t* data, size_t n, uint8_t** out, size_t* size) { *out = nullptr; return guarded([&] { bytes_out(descent::gunzip(data, n), out, size); }); }
+int dsc_free_bytes(uint8_t* bytes) { std::free(bytes); return DSC_OK; }
+int dsc_idx_images_info(const uint8_t* bytes, size_t size, uint32_t* images, uint32_t* rows, uint32_t* cols) {
+    return guarded([&] { auto i = descent::read_images_info(bytes, size); *images = i.images; *rows = i.rows; *cols = i.cols; });
+}
+int dsc_idx_labels_info(const uint8_t* bytes, size_t size, uint32_t* items) {
+    return guarded([&] { *items = descent::read_labels_info(bytes, size).items; });
+}
+int dsc_idx_unpack_images(const uint8_t* bytes, size_t size, const uint64_t* indices, size_t count, float* out) {
+    return guarded([&] { descent::unpack_images(bytes, size, indices, count, out); });
+}
+int dsc_idx_unpack_labels(const uint8_t* bytes, size_t size, const uint64_t* indices, size_t count, float* out) {
+    return guarded([&] { descent::unpack_labels(bytes, size, indices, count, out); });
+}
+int dsc_jpeg_decode_rgb(const uint8_t* data, size_t size, int* width, int* height, uint8_t** rgb_out) {
+    *rgb_out = nullptr;
+    return guarded([&] {
+        auto image = descent::decode_jpeg_rgb(data, size);
+        *width = image.width;
+        *height = image.height;
+        bytes_out(std::move(image.rgb), rgb_out, nullptr);
+    });
+}
+int dsc_write_ppm(const char* path, const float* rgb, int width, int height) { return guarded([&] { descent::write_ppm(path, rgb, width, height); }); }
+
 
 }  // extern "C"

@@ -338,21 +338,38 @@ float Environment::read_parameter_scalar(const Parameter& p) {
     read_parameter(p, &v, 1);
     return v;
 }
-void Environment::reset_parameter(const Parameter& p, HostRng& rng) {
-    DSC_CHECK(p.is_trainable(), "reset_parameter on a static parameter");
-    const Initializer init = *p.reset_to();
-    const size_t n = (size_t)p.shape().element_count();
-    if (init.kind == InitKind::Zero) return zero_fill(p);
+template <class Rng>
+static std::vector<float> initial_values(const Initializer& init, size_t n, Rng& rng) {
     std::vector<float> data(n);
     const float pi = 3.14159265358979323846f;
     for (size_t i = 0; i < n; ++i) {
         if (init.kind == InitKind::RandNormal) {  // Box-Muller, environment.rs:16-27
             float u1 = rng.open01(), u2 = rng.open01();
             data[i] = init.scale * (std::sqrt(-2.0f * std::log(u1)) * std::cos(2.0f * pi * u2));
-        } else {
+        } else {  // environment.rs:29-40
             data[i] = init.scale * (rng.open01() * 2.0f - 1.0f);
         }
     }
+    return data;
+}
+
+void Environment::reset_parameter(const Parameter& p, HostRng& rng) {
+    DSC_CHECK(p.is_trainable(), "reset_parameter on a static parameter");
+    const Initializer init = *p.reset_to();
+    const size_t n = (size_t)p.shape().element_count();
+    if (init.kind == InitKind::Zero) return zero_fill(p);
+    const auto data = initial_values(init, n, rng);
+    write_parameter(p, data.data(), n);
+}
+
+// The reference's own generator (examples seed rand_chacha::ChaCha20Rng::seed_from_u64 and hand it to reset_parameter,
+// environment.rs:190-202): same draws in the same order (host_rng.hpp).
+void Environment::reset_parameter(const Parameter& p, ChaCha20Rng& rng) {
+    DSC_CHECK(p.is_trainable(), "reset_parameter on a static parameter");
+    const Initializer init = *p.reset_to();
+    const size_t n = (size_t)p.shape().element_count();
+    if (init.kind == InitKind::Zero) return zero_fill(p);
+    const auto data = initial_values(init, n, rng);
     write_parameter(p, data.data(), n);
 }
 

@@ -13,12 +13,15 @@
 
 #include "../../include/descent_cuda.h"
 #include "codegen.hpp"
+#include "host_rng.hpp"
 
 namespace descent {
 
 // Host generator for Environment::reset_parameter.  The reference draws from rand_chacha's
 // ChaCha20Rng (environment.rs:16-40), which is not vendored and is not pinned by any reference test
 // (SURVEY.md §8c): the distributions are restated (Open01, Box-Muller), the bit stream is not.
+// (Round 2: host_rng.hpp restates the generator itself -- ChaCha20Rng, seed_from_u64, Open01, gen_range, shuffle -- and
+// reset_parameter has an overload for it; this splitmix generator stays for callers that only need reproducible values.)
 class HostRng {
 public:
     explicit HostRng(uint64_t seed) : state_(seed) {}
@@ -78,6 +81,7 @@ public:
     std::vector<float> read_parameter_to_vec(const Parameter& p);
     float read_parameter_scalar(const Parameter& p);
     void reset_parameter(const Parameter& p, HostRng& rng);
+    void reset_parameter(const Parameter& p, ChaCha20Rng& rng);  // the reference examples' generator
 
     std::unique_ptr<Scope> scope() const { return std::make_unique<Scope>(parameters_, dp_); }
     std::unique_ptr<Graph> build_graph(const std::function<void(Scope&)>& f) const;

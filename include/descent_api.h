@@ -144,6 +144,31 @@ int dsc_example_create(dsc_env* env, const char* network, int64_t mini_batch_siz
                        int64_t image_width, int64_t image_height, dsc_example* out);
 int dsc_example_graph_json(dsc_env* env, int which /*0 train, 1 test*/, char** json_out); /* raw graph of the last example created */
 
+/* ---- Host random numbers of the reference's examples -----------------------------------------
+ * rand_chacha::ChaCha20Rng::seed_from_u64 and the rand 0.8 sampling rules the examples use (descent_b200/csrc/host_rng.hpp):
+ * examples/fashion_mnist/main.rs:362-386, examples/image_fit/main.rs:352-395, examples/sentiment/main.rs:164. */
+typedef struct dsc_rng dsc_rng;
+int dsc_rng_create(uint64_t seed, dsc_rng** out);                       /* ChaCha20Rng::seed_from_u64 */
+int dsc_rng_destroy(dsc_rng* rng);
+int dsc_rng_next_u32(dsc_rng* rng, uint32_t* out);                      /* RngCore::next_u32: the per-step rand_seed */
+int dsc_rng_next_u64(dsc_rng* rng, uint64_t* out);
+int dsc_rng_open01_f32(dsc_rng* rng, float* out, size_t count);        /* rng.sample(Open01), environment.rs:22,35 */
+int dsc_rng_gen_range(dsc_rng* rng, uint64_t low, uint64_t high, int as_u32, uint64_t* out);  /* gen_range(low..high): u32 or usize draws */
+int dsc_rng_shuffle(dsc_rng* rng, uint64_t* indices, size_t count);    /* SliceRandom::shuffle, main.rs:382 */
+int dsc_env_reset_parameter_rng(dsc_env* env, int param, dsc_rng* rng); /* Environment::reset_parameter(param, &mut rng), environment.rs:190-202 */
+
+/* ---- Data front ends of the examples (descent_b200/csrc/host_io.cpp) --------------------------
+ * Byte buffers returned through `bytes_out` are released with dsc_free_bytes. */
+int dsc_load_gz_bytes(const char* path, uint8_t** bytes_out, size_t* size_out);                 /* fashion_mnist/main.rs:13-19 */
+int dsc_gunzip(const uint8_t* data, size_t size, uint8_t** bytes_out, size_t* size_out);
+int dsc_free_bytes(uint8_t* bytes);
+int dsc_idx_images_info(const uint8_t* bytes, size_t size, uint32_t* images, uint32_t* rows, uint32_t* cols); /* read_images_info :26 */
+int dsc_idx_labels_info(const uint8_t* bytes, size_t size, uint32_t* items);                                   /* read_labels_info :35 */
+int dsc_idx_unpack_images(const uint8_t* bytes, size_t size, const uint64_t* indices, size_t count, float* out); /* unpack_images :42 */
+int dsc_idx_unpack_labels(const uint8_t* bytes, size_t size, const uint64_t* indices, size_t count, float* out); /* unpack_labels :62 */
+int dsc_jpeg_decode_rgb(const uint8_t* data, size_t size, int* width, int* height, uint8_t** rgb_out);          /* image_fit/main.rs:278-282 */
+int dsc_write_ppm(const char* path, const float* rgb, int width, int height);                                  /* image_fit/main.rs:421-435 (as PPM) */
+
 #ifdef __cplusplus
 }
 #endif
