@@ -3083,7 +3083,7 @@ __device__ __forceinline__ unsigned dsc_pcg(unsigned v) {
     return (word >> 22u) ^ word;
 }
 // float(hash)/float(0xffffffffu): the divisor rounds to 2^32, so this is an exact scale of the RNE conversion
-// One lane of a converged warp.  The thread that issues tcgen05.mma is chosen with elect.sync under a warp-uniform
+// One lane of a converged warp.  The thread that issues the tensor-core MMAs is chosen with elect.sync under a warp-uniform
 // condition: the compiler then knows exactly one thread runs the branch and emits each MMA once; under `tid == 0` it must
 // assume any subset of lanes and wraps every MMA in an elect / broadcast loop (measured in SASS: BRA.U.ANY per MMA).
 __device__ __forceinline__ bool dsc_elect_one() {
