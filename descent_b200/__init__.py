@@ -900,3 +900,68 @@ def write_ppm(path, rgb):
 def write_csv_row(stream, values):
     """One row of the examples' statistics files (fashion_mnist/main.rs:398-412, image_fit/main.rs:408-416): `"label", v, v, ...`."""
     stream.write(", ".join('"%s"' % v if isinstance(v, str) else repr(float(v)) if isinstance(v, float) else str(v) for v in values) + "\n")
+
+
+# ---- op-level entry points (include/descent_api.h "Op-level entry points", csrc/ops_api.cpp) -------------------------------
+class Op:
+    """One fused op planned for a shape (dsc_op_*): owns its operand / result buffers on the device."""
+
+    def __init__(self, env, handle):
+        self.env, self._h = env, handle
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            lib.dsc_op_destroy(self._h)
+            self._h = None
+
+    def parameter(self, name):
+        pid = ctypes.c_int()
+        _check(lib.dsc_op_parameter(self._h, name.encode(), ctypes.byref(pid)))
+        return self.env.parameter(pid.value)
+
+    def device_buffer(self, name):
+        """(device address, bytes) of a buffer: what a caller's own kernels would read / write in place."""
+        ptr, size = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(lib.dsc_op_buffer(self._h, name.encode(), ctypes.byref(ptr), ctypes.byref(size)))
+        return ptr.value, size.value
+
+    def write(self, name, data):
+        self.env.write(self.parameter(name), data)
+
+    def read(self, name):
+        return self.env.read(self.parameter(name))
+
+    def run(self, rand_seed=0):
+        _check(lib.dsc_op_run(self._h, ctypes.c_uint32(rand_seed)))
+
+
+def _op_conv2d(self, images, height, width, in_channels, out_channels, filter_h, filter_w, pad=0, stride=(1, 1), groups=1, backward=False):
+    h = ctypes.c_void_p()
+    _check(lib.dsc_op_conv2d(self._h, *(ctypes.c_int64(v) for v in (images, height, width, in_channels, out_channels, filter_h, filter_w, pad, stride[0], stride[1], groups)),
+                             int(backward), ctypes.byref(h)))
+    return Op(self, h)
+
+
+def _op_scatter_add(self, rows, inner, count):
+    h = ctypes.c_void_p()
+    _check(lib.dsc_op_scatter_add(self._h, ctypes.c_int64(rows), ctypes.c_int64(inner), ctypes.c_int64(count), ctypes.byref(h)))
+    return Op(self, h)
+
+
+def _op_softmax_cross_entropy(self, rows, classes):
+    h = ctypes.c_void_p()
+    _check(lib.dsc_op_softmax_cross_entropy(self._h, ctypes.c_int64(rows), ctypes.c_int64(classes), ctypes.byref(h)))
+    return Op(self, h)
+
+
+def _op_adam_step(self, counts, learning_rate, beta1=0.9, beta2=0.999, epsilon=1.0e-8):
+    arr, n = _i64(counts)
+    h = ctypes.c_void_p()
+    _check(lib.dsc_op_adam_step(self._h, arr, n, ctypes.c_float(learning_rate), ctypes.c_float(beta1), ctypes.c_float(beta2), ctypes.c_float(epsilon), ctypes.byref(h)))
+    return Op(self, h)
+
+
+Environment.op_conv2d = _op_conv2d
+Environment.op_scatter_add = _op_scatter_add
+Environment.op_softmax_cross_entropy = _op_softmax_cross_entropy
+Environment.op_adam_step = _op_adam_step

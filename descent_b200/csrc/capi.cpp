@@ -26,6 +26,8 @@ struct dsc_scope {
     std::unique_ptr<Scope> scope;
     Parameter param(int id) const { return env->param(id); }
 };
+Environment& dsc_env_environment(dsc_env* env) { return *env->env; }  // ops_api.cpp
+
 struct dsc_graphdef {
     std::unique_ptr<Graph> owned;
     Graph* graph = nullptr;  // either owned or borrowed from an Example

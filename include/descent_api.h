@@ -169,6 +169,31 @@ int dsc_idx_unpack_labels(const uint8_t* bytes, size_t size, const uint64_t* ind
 int dsc_jpeg_decode_rgb(const uint8_t* data, size_t size, int* width, int* height, uint8_t** rgb_out);          /* image_fit/main.rs:278-282 */
 int dsc_write_ppm(const char* path, const float* rgb, int width, int height);                                  /* image_fit/main.rs:421-435 (as PPM) */
 
+/* ---- Op-level entry points (the fused kernels without the graph builder; ops_api.cpp) ------------
+ * A Rust kernel.rs that keeps the reference's graph passes can hand one cluster to these.  An op is planned once for its
+ * shape and OWNS its operand / result buffers on the device: dsc_op_buffer returns their addresses (the caller's kernels
+ * read and write them in place), dsc_op_parameter the parameter id (for dsc_env_write_parameter / dsc_env_read_parameter),
+ * dsc_op_run launches the planned kernels on the environment's stream.  Precision follows dsc_env_set_tf32. */
+typedef struct dsc_op dsc_op;
+/* NHWC conv2d with replicate padding, stride and groups (Array::conv2d, array.rs:989-1031; kernel.rs:385-557,712-810).
+ * backward = 0: buffers "x" [images, h, w, ic], "filter" [groups, oc / groups, fh, fw, ic / groups] -> "y".
+ * backward = 1: buffers "x", "filter", "dy" -> "dx", "dfilter" (the backward-input and weight-gradient kernels). */
+int dsc_op_conv2d(dsc_env* env, int64_t images, int64_t height, int64_t width, int64_t in_channels, int64_t out_channels, int64_t filter_h, int64_t filter_w,
+                  int64_t pad, int64_t stride_w, int64_t stride_h, int64_t groups, int backward, dsc_op** out);
+/* Deterministic sort-and-segmented-reduce scatter_add (kernel.rs:812-874 uses float atomics): "table" [rows, inner] +=
+ * "values" [count, inner] at rows "indices" [count] (uint32 row numbers). */
+int dsc_op_scatter_add(dsc_env* env, int64_t rows, int64_t inner, int64_t count, dsc_op** out);
+/* loss.rs:4-34 as one row kernel: "z" [rows, classes], "y" [rows, 1] (labels as f32) -> "loss" [rows, 1], "accuracy" [rows, 1],
+ * "dz" [rows, classes] (gradient of the summed loss). */
+int dsc_op_softmax_cross_entropy(dsc_env* env, int64_t rows, int64_t classes, dsc_op** out);
+/* optimizer.rs:62-112 for `tensors` parameter tensors in ONE launch: buffers "theta<i>", "grad<i>" [counts[i]], and the
+ * optimiser state "state<j>" (zeroed at creation: the step counter, then m and v per tensor). */
+int dsc_op_adam_step(dsc_env* env, const int64_t* counts, int tensors, float learning_rate, float beta1, float beta2, float epsilon, dsc_op** out);
+int dsc_op_buffer(dsc_op* op, const char* name, void** device_ptr, size_t* bytes);
+int dsc_op_parameter(dsc_op* op, const char* name, int* param);
+int dsc_op_run(dsc_op* op, uint32_t rand_seed);
+int dsc_op_destroy(dsc_op* op);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,3 +151,19 @@ def test_ppm_and_csv_output(built_library, tmp_path):
     out = io.StringIO()
     d.write_csv_row(out, ["conv-net", 3, 0.25])
     assert out.getvalue() == '"conv-net", 3, 0.25\n'
+
+
+def test_op_level_entry_points_plan_without_a_device(host_env):
+    """dsc_op_* (include/descent_api.h): every op builds its graph and names its buffers on a host-only environment."""
+    ops = {
+        "conv fwd": (host_env.op_conv2d(64, 14, 14, 16, 32, 3, 3, pad=1, groups=2), {"x": (64, 14, 14, 16), "filter": (2, 16, 3, 3, 8), "y": (64, 14, 14, 32)}),
+        "conv bwd": (host_env.op_conv2d(64, 14, 14, 16, 32, 3, 3, pad=1, groups=2, backward=True), {"dy": (64, 14, 14, 32), "dx": (64, 14, 14, 16), "dfilter": (2, 16, 3, 3, 8)}),
+        "scatter": (host_env.op_scatter_add(577, 2, 1000), {"table": (577, 2), "values": (1000, 2), "indices": (1000,)}),
+        "xent": (host_env.op_softmax_cross_entropy(100, 10), {"z": (100, 10), "y": (100, 1), "loss": (100, 1), "accuracy": (100, 1), "dz": (100, 10)}),
+        "adam": (host_env.op_adam_step([10, 20], 0.01), {"theta0": (10,), "grad1": (20,), "state0": (1,)}),
+    }
+    for name, (op, buffers) in ops.items():
+        for buffer, shape in buffers.items():
+            assert tuple(op.parameter(buffer).shape()) == shape, (name, buffer)
+    with pytest.raises(Exception):
+        ops["xent"][0].parameter("nope")
