@@ -23,8 +23,18 @@ std::string replace_all(std::string s, const std::string& from, const std::strin
     }
     return s;
 }
+// measurement hook: the halo conv kernels' MMA-issuing thread chosen by `tid == 0` (default) or by elect.sync under a
+// warp-uniform condition (DSC_HALO_ELECT=1; see dsc_elect_one in the prelude)
+bool halo_elect() {
+    static const bool v = [] { const char* e = std::getenv("DSC_HALO_ELECT"); return e && std::atoi(e) != 0; }();
+    return v;
+}
+
 std::string subst(std::string s, const std::vector<std::pair<std::string, std::string>>& kv) {
     for (const auto& p : kv) s = replace_all(s, "{{" + p.first + "}}", p.second);
+    s = replace_all(s, "{{WARP_EXPR}}", halo_elect() ? "__shfl_sync(0xffffffffu, tid >> 5, 0)" : "tid >> 5");
+    s = replace_all(s, "{{TMEM_EXPR}}", halo_elect() ? "__shfl_sync(0xffffffffu, *tmem_slot, 0)" : "*tmem_slot");
+    s = replace_all(s, "{{ISSUE_COND}}", halo_elect() ? "warp == 0 && dsc_elect_one()" : "tid == 0");
     DSC_CHECK(s.find("{{") == std::string::npos, "unsubstituted placeholder in kernel template: " << s.substr(s.find("{{"), 24));
     return s;
 }

@@ -1221,18 +1221,29 @@ void Graph::build_clusters() {
         for (int id : order)
             if (ops_.nodes[id].op.kind == OpKind::AllReduce) ar_nodes.push_back(id);
         if (!ar_nodes.empty()) {
+            // Two buckets.  The split is the level at which the LARGEST gradient tensor is ready (conv-net: the dense layers'
+            // weights, computed first in the backward pass and 98 % of the bytes): everything ready by then is reduced on the
+            // side stream under the rest of the backward pass.  When the largest tensor is itself among the last to be ready
+            // (multi-hash: a hash table, behind the scatter_adds) that rule leaves one exposed bucket; then every gradient
+            // that is ready before the last level goes early instead (the MLP's, reduced under the table scatter).
             int late_level = 0, largest = ar_nodes[0];
             for (int id : ar_nodes) {
                 late_level = std::max(late_level, asap[id]);
                 if (ops_.nodes[id].shape.element_count() > ops_.nodes[largest].shape.element_count()) largest = id;
             }
+            int split = asap[largest];
+            if (split == late_level) {
+                split = -1;
+                for (int id : ar_nodes)
+                    if (asap[id] < late_level) split = std::max(split, asap[id]);
+            }
             int early_level = 0;
             bool any_late = false;
             for (int id : ar_nodes) {
-                if (asap[id] <= asap[largest]) early_level = std::max(early_level, asap[id]);
+                if (asap[id] <= split) early_level = std::max(early_level, asap[id]);
                 else any_late = true;
             }
-            const int split = asap[largest];
+            any_late = any_late && split >= 0;
             for (int id : ar_nodes) ar_target[id] = (any_late && asap[id] <= split) ? early_level : late_level;
             ar_consumer_level = late_level + 1;
             forward();

@@ -106,7 +106,7 @@ int dsc_op_softmax_cross_entropy(dsc_env* env_handle, int64_t rows, int64_t clas
         for (auto& [name, p] : std::map<std::string, Parameter>{{"z", z}, {"y", y}, {"loss", loss}, {"accuracy", accuracy}, {"dz", dz}}) op->buffers.emplace(name, p);
         auto scope = env.scope();
         DualArray logits = scope->parameter(z);
-        Array l = softmax_cross_entropy_loss(logits, y).set_loss();  // loss.rs:4-23; set_loss seeds d loss = 1 per row
+        Array l = softmax_cross_entropy_loss(logits, y).set_loss();  // loss.rs:4-23; set_loss seeds d loss = 1 / rows (batch mean)
         scope->write_parameter_value(loss, l);
         scope->write_parameter_value(accuracy, softmax_cross_entropy_accuracy(logits, y));  // loss.rs:25-34
         scope->write_parameter_value(dz, scope->parameter(z).loss_grad());

@@ -184,7 +184,7 @@ int dsc_op_conv2d(dsc_env* env, int64_t images, int64_t height, int64_t width, i
  * "values" [count, inner] at rows "indices" [count] (uint32 row numbers). */
 int dsc_op_scatter_add(dsc_env* env, int64_t rows, int64_t inner, int64_t count, dsc_op** out);
 /* loss.rs:4-34 as one row kernel: "z" [rows, classes], "y" [rows, 1] (labels as f32) -> "loss" [rows, 1], "accuracy" [rows, 1],
- * "dz" [rows, classes] (gradient of the summed loss). */
+ * "dz" [rows, classes] = (softmax - onehot) / rows, the gradient of the batch-mean loss (DualArray::set_loss). */
 int dsc_op_softmax_cross_entropy(dsc_env* env, int64_t rows, int64_t classes, dsc_op** out);
 /* optimizer.rs:62-112 for `tensors` parameter tensors in ONE launch: buffers "theta<i>", "grad<i>" [counts[i]], and the
  * optimiser state "state<j>" (zeroed at creation: the step counter, then m and v per tensor). */

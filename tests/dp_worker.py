@@ -14,14 +14,17 @@ def main():
     import torch.distributed as dist
     from helpers import init_example_params, max_rel_err, synthetic_batch
     workload = sys.argv[1]
+    m = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    optimizer = sys.argv[3] if len(sys.argv) > 3 else "adam"
+    tf32 = len(sys.argv) > 4 and sys.argv[4] == "tf32"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import descent_b200 as d
-    m = 16
     # reference run: one GPU, full batch
     ref_env = d.Environment(local)
-    ref = ref_env.example(workload, m)
+    ref_env.set_tf32(tf32)
+    ref = ref_env.example(workload, m, optimizer=optimizer)
     rng = np.random.default_rng(77)
     params = init_example_params(ref, rng)
     batches = [synthetic_batch(ref, rng) for _ in range(3)]
@@ -39,7 +42,8 @@ def main():
     uid = [d.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     env.init_data_parallel(world, rank, uid[0])
-    ex = env.example(workload, m // world)
+    env.set_tf32(tf32)
+    ex = env.example(workload, m // world, optimizer=optimizer)
     for p_ref, p in zip(ref.parameters + ref.optimizer_state + [ref.loss_sum, ref.accuracy_sum, ref.learning_rate_scale],
                         ex.parameters + ex.optimizer_state + [ex.loss_sum, ex.accuracy_sum, ex.learning_rate_scale]):
         env.write(p, params[p_ref.id])
@@ -56,7 +60,9 @@ def main():
     flags = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("worst parameter deviation %.3g, loss %g vs %g" % (worst, float(loss.item()), want_loss))
+        labels = [t["label"] for t in env.profile(ex.train_graph, 0, 1)]
+        print("worst parameter deviation %.3g, loss %g vs %g; %d launches, fused: %s" % (worst, float(loss.item()), want_loss, len(labels),
+              [l[:40] for l in labels if "DenseChain" in l or "group" in l or "AllReduce" in l]))
         print("DP_OK" if flags.item() == 1.0 else "DP_MISMATCH")
     env.close()
     ref_env.close()

@@ -83,8 +83,8 @@ def test_tf32_single_step_gradients(env):
         assert max_rel_err(got, want[m_state.id]) <= 5e-5, p.name()
 
 
-@pytest.mark.parametrize("workload", ["conv-net"])
-def test_two_gpu_data_parallel_matches_single_gpu(workload):
+@pytest.mark.parametrize("workload,m,optimizer,precision", [("conv-net", 16, "adam", "strict"), ("multi-hash", 4096, "descent", "tf32")], ids=["conv-net", "multi-hash-fused"])
+def test_two_gpu_data_parallel_matches_single_gpu(workload, m, optimizer, precision):
     """torchrun, 2 ranks, NCCL bucket all-reduce inside the captured step: parameters after 3 steps equal the
     1-GPU run on the concatenated batch (same tolerance as the CPU data-parallel test)."""
     import torch
@@ -92,9 +92,12 @@ def test_two_gpu_data_parallel_matches_single_gpu(workload):
         pytest.skip("needs 2 GPUs")
     script = os.path.join(ROOT, "tests", "dp_worker.py")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29533", script, workload], capture_output=True, text=True, timeout=600)
+                          "--master-port", "29533", script, workload, str(m), optimizer, precision], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DP_OK" in out.stdout, out.stdout[-3000:]
+    print(out.stdout[-600:])
+    if workload == "multi-hash":  # the fused MLP kernel and the grouped scatter run on every rank, the MLP gradients in the early bucket
+        assert "DenseChain" in out.stdout and "ScatterAdd group" in out.stdout and "early bucket" in out.stdout, out.stdout[-3000:]
 
 
 # SIREN's first layer (x30 init) feeds sin() arguments of magnitude ~50: FP32 accumulation-order noise of the GEMM is
