@@ -18,7 +18,7 @@ def build(d, world, rank, network, m_local):
     return env, env.example(network, m_local)
 
 
-@pytest.mark.parametrize("network", ["single-layer-dropout", "conv-net"])
+@pytest.mark.parametrize("network", ["single-layer-dropout", "conv-net", "multi-hash"])
 def test_two_rank_step_equals_single_rank_step(built_library, network):
     d = built_library
     m = 8
