@@ -1623,6 +1623,104 @@ bool gen_thin_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOpti
 
 extern const char* kUnpadTemplate;
 
+// Strided conv2d backward-input as a gather (graph.hpp ConvBackwardInput::strided): one thread per element of the FINAL
+// image gradient [image, y, x, channel] -- after the Unpads, the adjoint of replicate padding (kernel.rs:644-710: border
+// pixels also collect the pad rows / columns beyond them) -- sums, over the padded positions that fold onto it and the
+// filter taps (fy, fx) for which (position - tap) is a multiple of the stride inside the window grid (the col2im range
+// check), the product dY[window, k] * W[k, (tap, channel)].  Replaces MatMul (k=1) + WindowsToImage + two
+// Unpads of MaxBlurPool2D's blur convolution (conv-blur-net m = 8192: 877 + 741 + 366 + 350 us and 460 + 995 + 197 + 180 us).
+bool gen_conv_backward_gather(const Graph& g, const Cluster& c, int ci, ClusterCode* out) {
+    const auto& cbi = c.conv_backward_input;
+    if (!cbi.enabled || !cbi.strided) return false;
+    const ClusterInput& a = cbi.unfused[0];
+    const ClusterInput& b = cbi.unfused[1];
+    const int64_t G = a.arg_shape[0], M = a.arg_shape[1], K = cbi.matmul_k, N = b.arg_shape[2];
+    const int64_t FH = cbi.filter_h, FW = cbi.filter_w, GC = N / (FH * FW), OH = cbi.out_h, OW = cbi.out_w, IH = cbi.in_h, IW = cbi.in_w;
+    const int64_t images = M / (OH * OW), PY = cbi.unpad_h, PX = cbi.unpad_w, H = IH - 2 * PY, W = IW - 2 * PX, C = G * GC;
+    const OpNode& mm = g.ops().nodes[c.node_id];
+    DSC_CHECK(mm.shape[0] == 1 && H >= 1 && W >= 1 && GC * FH * FW == N, "strided conv backward: unexpected shapes");
+    const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
+    (void)rows_mode;  // the operands are addressed through their own chains, whatever the product's layout was
+    const int64_t out_count = images * H * W * C;
+    const std::string name = "k" + num(ci);
+    std::ostringstream os;
+    os << "// " << c.label << "  [gather: one thread per image-gradient element]\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(256) " << name << "(const float* A, const float* B, float* C, const unsigned* dsc_step) {\n";
+    os << "    (void)dsc_step;\n    const unsigned e = blockIdx.x * 256u + threadIdx.x;\n    if (e >= " << unum(out_count) << ") return;\n";
+    os << "    const int ch = (int)(e % " << unum(C) << "), x = (int)((e / " << unum(C) << ") % " << unum(W) << "), y = (int)((e / " << unum(C * W) << ") % " << unum(H)
+       << "), image = (int)(e / " << unum(C * W * H) << ");\n";
+    os << "    const int batch = ch / " << GC << ", gc = ch % " << GC << ";\n";
+    os << "    // padded positions that fold onto (y, x): the pixel itself, plus the pad rows / columns beyond a border pixel\n";
+    os << "    const int y_lo = y == 0 ? 0 : y + " << PY << ", y_hi = y == " << H - 1 << " ? " << IH - 1 << " : y + " << PY << ";\n";
+    os << "    const int x_lo = x == 0 ? 0 : x + " << PX << ", x_hi = x == " << W - 1 << " ? " << IW - 1 << " : x + " << PX << ";\n";
+    os << "    float acc = 0.f;\n";
+    os << "    for (int yp = y_lo; yp <= y_hi; ++yp)\n    for (int xp = x_lo; xp <= x_hi; ++xp) {\n";
+    os << "        #pragma unroll\n        for (int fy = 0; fy < " << FH << "; ++fy) {\n";
+    os << "            const int ty = yp - fy;\n            if (ty < 0 || ty % " << cbi.stride_h << " != 0 || ty / " << cbi.stride_h << " >= " << OH << ") continue;\n";
+    os << "            #pragma unroll\n            for (int fx = 0; fx < " << FW << "; ++fx) {\n";
+    os << "                const int tx = xp - fx;\n                if (tx < 0 || tx % " << cbi.stride_w << " != 0 || tx / " << cbi.stride_w << " >= " << OW << ") continue;\n";
+    os << "                const int gm = (image * " << OH << " + ty / " << cbi.stride_h << ") * " << OW << " + tx / " << cbi.stride_w << ";\n";
+    os << "                const int gn = (fy * " << FW << " + fx) * " << GC << " + gc;\n";
+    os << "                #pragma unroll\n                for (int gk = 0; gk < " << K << "; ++gk) {\n";
+    int uniq = 0;
+    std::string ia = emit_chain(os, a.chain, {{"batch", M * K, G}, {"gm", K, M}, {"gk", 1, K}}, uniq, "                    ");
+    std::string ib = emit_chain(os, b.chain, {{"batch", K * N, G}, {"gk", N, K}, {"gn", 1, N}}, uniq, "                    ");
+    os << "                    acc = fmaf(A[" << ia << "], B[" << ib << "], acc);\n                }\n            }\n        }\n    }\n    C[e] = acc;\n}\n\n";
+    out->source = os.str();
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)div_round_up(out_count, 256);
+    l.label = c.label;
+    l.cluster = ci;
+    l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)out_count;
+    l.flops = 2.0 * (double)G * (double)M * (double)N * (double)K;
+    out->launches.push_back(l);
+    return true;
+}
+
+// Many tiny products: BC independent [M, K] x [K, N] with K * N a few dozen -- the depthwise 3x3 blur convolution of
+// MaxBlurPool2D (module.rs:139-163, 221-245: groups = channels, one input and one output channel per group, K = 9, N = 1)
+// and its backward outer product (K = 1, N = 9).  One thread per OUTPUT element in the output's own memory order, the whole
+// reduction in registers (ascending k, explicit fmaf like every strict-FP32 GEMM here), operands through their view chains.
+// In rows mode ([pixel, group, n], NHWC) consecutive threads are consecutive channels of one pixel, so every load of the
+// window's nine taps is a contiguous run of channels; the thin-rows kernel this replaces ran one group per grid row and
+// touched 4 bytes per 64-byte line (conv-blur-net m = 8192: 1126 + 977 us for the two forward blur convolutions).
+bool gen_grouped_dot(const Graph& g, const Cluster& c, int ci, ClusterCode* out) {
+    const OpNode& mm = g.ops().nodes[c.node_id];
+    const ClusterInput& a = c.inputs[0];
+    const ClusterInput& b = c.inputs[1];
+    const int64_t BC = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
+    if (c.conv_backward_input.enabled || c.matmul_absorbs_reduce || mm.shape[0] != 1 || !c.column_sum.empty() || !c.epilogue.empty() || c.pool.enabled) return false;
+    if (BC < 4 || K > 32 || N > 16 || K * N > 64 || BC * M * N < (1 << 16)) return false;
+    const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows;
+    const int64_t out_count = BC * M * N;
+    const std::string name = "k" + num(ci);
+    std::ostringstream os;
+    os << "// " << c.label << "  [one thread per output element, " << K << "-term dot product in registers]\n";
+    os << "extern \"C\" __global__ void __launch_bounds__(256) " << name << "(const float* A, const float* B, float* C, const unsigned* dsc_step) {\n";
+    os << "    (void)dsc_step;\n    const unsigned e = blockIdx.x * 256u + threadIdx.x;\n    if (e >= " << unum(out_count) << ") return;\n";
+    os << "    const unsigned gn = e % " << unum(N) << ";\n";
+    if (rows_mode) os << "    const unsigned batch = (e / " << unum(N) << ") % " << unum(BC) << ", gm = e / " << unum(N * BC) << ";\n";
+    else os << "    const unsigned gm = (e / " << unum(N) << ") % " << unum(M) << ", batch = e / " << unum(N * M) << ";\n";
+    os << "    float acc = 0.f;\n    #pragma unroll\n    for (unsigned gk = 0; gk < " << unum(K) << "; ++gk) {\n";
+    int uniq = 0;
+    std::string ia = emit_chain(os, a.chain, {{"batch", M * K, BC}, {"gm", K, M}, {"gk", 1, K}}, uniq, "        ");
+    std::string ib = emit_chain(os, b.chain, {{"batch", K * N, BC}, {"gk", N, K}, {"gn", 1, N}}, uniq, "        ");
+    os << "        acc = fmaf(A[" << ia << "], B[" << ib << "], acc);\n    }\n    C[e] = acc;\n}\n\n";
+    out->source = os.str();
+    KernelLaunch l;
+    l.entry = name;
+    l.grid_x = (uint32_t)div_round_up(out_count, 256);
+    l.label = c.label;
+    l.cluster = ci;
+    l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
+    l.algorithmic_bytes = chain_bytes(g, a) + chain_bytes(g, b) + 4.0 * (double)out_count;
+    l.flops = 2.0 * (double)BC * (double)M * (double)N * (double)K;
+    out->launches.push_back(l);
+    return true;
+}
+
 ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
     const OpNode& mm = g.ops().nodes[c.node_id];
     const ClusterInput& a = c.inputs[0];
@@ -1630,6 +1728,11 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     const int64_t BC = a.arg_shape[0], M = a.arg_shape[1], K = a.arg_shape[2], N = b.arg_shape[2];
     const int64_t r_graph = mm.shape[0];
     const auto& cbi = c.conv_backward_input;
+    if (cbi.enabled && cbi.strided) {
+        ClusterCode code;
+        DSC_CHECK(gen_conv_backward_gather(g, c, ci, &code), "strided conv backward-input cluster without a kernel");
+        return code;
+    }
     if (!c.epilogue.empty()) {
         // an absorbed per-element cluster runs in the epilogue of the kernels that support it ...
         ClusterCode code;
@@ -1657,6 +1760,10 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
         ClusterCode code;
         if (cbi.enabled ? gen_conv_backward_input(g, c, ci, opt, &code) : gen_conv_forward(g, c, ci, opt, &code)) return code;
         if (!cbi.enabled && gen_conv_weight_gradient(g, c, ci, opt, &code)) return code;
+    }
+    {
+        ClusterCode code;
+        if (gen_grouped_dot(g, c, ci, &code)) return code;
     }
     const bool rows_mode = mm.op.output_mode == MatMulOutputMode::Rows || cbi.enabled;  // fused output is [pixel, group, channel]
     const int64_t out_count = BC * M * N;
@@ -1964,8 +2071,8 @@ ClusterCode gen_unpad(const Graph& g, const Cluster& c, int ci) {
 // inside [0,out_h) x [0,out_w): the mathematically correct adjoint.
 
 const char* kW2ITemplate = R"(
-// {{LABEL}}
-extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, float* out0, const unsigned* dsc_step) {
+{{FUNCS}}// {{LABEL}}
+extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* A, float* out0, {{PARAMS}}const unsigned* dsc_step) {
     constexpr unsigned COUNT = {{COUNT}}u;
     constexpr int IN_H = {{IN_H}}, IN_W = {{IN_W}}, IN_C = {{IN_C}};
     constexpr int OUT_H = {{OUT_H}}, OUT_W = {{OUT_W}}, GROUPS = {{GROUPS}}, FH = {{FH}}, FW = {{FW}}, GNC = {{GNC}}, SW = {{SW}}, SH = {{SH}};
@@ -1983,14 +2090,18 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}(const float* in0, flo
             if (x < fx || ox >= OUT_W) continue;
             const unsigned e = (((((batch * OUT_H + oy) * OUT_W + ox) * GROUPS + group) * FH + fy) * FW + fx) * GNC + gc;
 {{CHAIN}}
-            sum += in0[{{IDX}}];
+            sum += {{LOAD}};
         }
     }
     out0[o] = sum;
 }
 )";
 
-ClusterCode gen_w2i(const Graph& g, const Cluster& c, int ci) {
+// The window values may come from an operand prologue (graph.hpp OperandPrologue): max_pool2d's backward pass with
+// overlapping windows (MaxBlurPool2D's stride-1 pooling, module.rs:221-245) selects the output gradient where the window
+// element equals the window's maximum -- a per-element program over the 4x-expanded window array, whose only reader is this
+// gather.  Evaluated here per gathered element, that array (1.5 GB at m = 8192 for the first pooling layer) never exists.
+ClusterCode gen_w2i(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
     const OpNode& node = g.ops().nodes[c.node_id];
     const ClusterInput& in = c.inputs[0];
     const Shape& ws = in.arg_shape;
@@ -2001,18 +2112,20 @@ ClusterCode gen_w2i(const Graph& g, const Cluster& c, int ci) {
     const std::string name = "k" + num(ci);
     const int64_t count = node.shape.element_count();
     ClusterCode code;
+    const OperandLoad la = operand_load(g, 0, name, in, opt);
     code.source = subst(kW2ITemplate,
                         {{"LABEL", c.label}, {"NAME", name}, {"COUNT", num(count)}, {"IN_H", num(node.shape[ni - 3])}, {"IN_W", num(node.shape[ni - 2])},
                          {"IN_C", num(node.shape[ni - 1])}, {"OUT_H", num(ws[n - 6])}, {"OUT_W", num(ws[n - 5])}, {"GROUPS", num(ws[n - 4])},
                          {"FH", num(ws[n - 3])}, {"FW", num(ws[n - 2])}, {"GNC", num(ws[n - 1])}, {"SW", num(node.op.stride_w)},
-                         {"SH", num(node.op.stride_h)}, {"CHAIN", chain.str()}, {"IDX", idx}});
+                         {"SH", num(node.op.stride_h)}, {"CHAIN", chain.str()}, {"LOAD", la.load1(idx)}, {"FUNCS", la.funcs}, {"PARAMS", la.params}});
     KernelLaunch l;
     l.entry = name;
     l.grid_x = (uint32_t)div_round_up(count, 256);
-    l.label = c.label;
+    l.label = c.label + (la.fused ? "  [windows = " + g_prologue->producer[0]->label + "]" : "");
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, in.node_id, 0}, {KernelArg::NodeBuffer, c.outputs[0], 0}};
-    l.algorithmic_bytes = chain_bytes(g, in) + 4.0 * (double)count;
+    l.algorithmic_bytes = la.bytes + 4.0 * (double)count;
+    bind_operand_loads(l, &code, &la, nullptr);
     code.launches.push_back(l);
     return code;
 }
@@ -3119,7 +3232,7 @@ ClusterCode generate_cluster_code(const Graph& graph, int ci, const CodegenOptio
     struct Scoped {  // the request is visible to the generators of this one cluster only
         explicit Scoped(PrologueRequest* r) { g_prologue = r; }
         ~Scoped() { g_prologue = nullptr; }
-    } scoped(c.kind == ClusterKind::MatMul ? prologue : nullptr);
+    } scoped(c.kind == ClusterKind::MatMul || c.kind == ClusterKind::WindowsToImage ? prologue : nullptr);
     if (prologue) prologue->fused[0] = prologue->fused[1] = false;
     switch (c.kind) {
         case ClusterKind::PerElement: return gen_per_element(graph, c, ci, opt);
@@ -3170,7 +3283,7 @@ ClusterCode generate_cluster_code(const Graph& graph, int ci, const CodegenOptio
             return code;
         }
         case ClusterKind::Unpad: return gen_unpad(graph, c, ci);
-        case ClusterKind::WindowsToImage: return gen_w2i(graph, c, ci);
+        case ClusterKind::WindowsToImage: return gen_w2i(graph, c, ci, opt);
         case ClusterKind::ScatterAdd: return gen_scatter_add(graph, c, ci, opt);
         case ClusterKind::AllReduce: {
             ClusterCode code;

@@ -1117,7 +1117,7 @@ bool Graph::absorb_unpad(std::vector<Cluster>& clusters, const std::vector<std::
 // rewriting the MatMul's cluster in place; the caller skips the stand-alone WindowsToImage kernel.
 bool Graph::absorb_windows_to_image(std::vector<Cluster>& clusters, const std::vector<std::vector<std::pair<int, int>>>& cons, int id) {
     OpNode& node = ops_.nodes[id];
-    if (node.op.stride_w != 1 || node.op.stride_h != 1) return false;
+    const bool strided = node.op.stride_w != 1 || node.op.stride_h != 1;
     const OpEdge& e = node.in[0];
     const OpNode& mm = ops_.nodes[e.src];
     if (mm.op.kind != OpKind::MatMul || mm.cluster_id < 0 || cons[e.src].size() != 1 || mm.shape[0] != 1) return false;
@@ -1143,6 +1143,22 @@ bool Graph::absorb_windows_to_image(std::vector<Cluster>& clusters, const std::v
     for (int axis = 0; axis < 7; ++axis)
         if (ws[axis] > 1 && eval_chain(e.chain, ws_strides[axis]) != want[axis]) return false;
 
+    if (strided) {
+        // see ConvBackwardInput::strided: only for tiny per-group products (depthwise-like), where a gather over the few
+        // windows that contain a pixel beats a GEMM that writes the window matrix
+        if (K * GC > 16 || FH * FW > 25) return false;
+        mc.conv_backward_input = {true, IH, IW, OH, OW, FH, FW, K, {a, b}};
+        mc.conv_backward_input.strided = true;
+        mc.conv_backward_input.stride_h = node.op.stride_h;
+        mc.conv_backward_input.stride_w = node.op.stride_w;
+        mc.members.push_back(id);
+        mc.outputs[0] = id;
+        std::ostringstream label;
+        label << "MatMul+WindowsToImage/" << node.op.stride_h << "x" << node.op.stride_w << " (k=" << K << ") " << node.shape.str();
+        mc.label = label.str();
+        node.cluster_id = mm.cluster_id;
+        return true;
+    }
     // A'[group, (image, y, x), (fy, fx, k)] = A[group, (image, y - fy, x - fx), k]; positions outside the window
     // grid are clamped here (so the address is always legal) and zeroed by the kernel's validity test
     View va;
@@ -1747,6 +1763,10 @@ void Graph::find_operand_prologues() {
             if (!d.alive) continue;
             if (d.op.kind == OpKind::Output || d.cluster_id < 0 || d.cluster_id == pi) { ok = false; break; }
             const Cluster& mc = clusters_[d.cluster_id];
+            if (mc.kind == ClusterKind::WindowsToImage && mc.inputs[0].node_id == x) {  // the gather evaluates its windows itself (codegen gen_w2i)
+                cand.uses.push_back({d.cluster_id, 0});
+                continue;
+            }
             if (mc.kind != ClusterKind::MatMul || !mc.epilogue.empty()) { ok = false; break; }
             bool as_operand = false;
             for (int operand = 0; operand < 2; ++operand) {

@@ -67,6 +67,12 @@ struct Cluster {
         // amounts along the image's h and w axes and which of the two the graph applies first (1 = h, 2 = w, 0 = none)
         int64_t unpad_h = 0, unpad_w = 0;
         int unpad_first_axis = 0;
+        // Strided windows (MaxBlurPool2D's depthwise stride-2 blur, module.rs:139-163): a window position is a division by
+        // the stride, which no view expresses, so the MatMul's operands keep their own chains (`unfused` = `inputs`) and the
+        // cluster runs as ONE gather kernel: one thread per element of the final image gradient sums the few (window, tap)
+        // pairs that contain it -- dY x W^T, col2im and both Unpads without the 9x window matrix or the padded gradient.
+        bool strided = false;
+        int64_t stride_h = 1, stride_w = 1;
     } conv_backward_input;
     int copy_from = -1;                // ScatterAdd: accumulator node taken in place (graph.rs:601-621)
     // MatMul whose product is consumed, element for element, by exactly one per-element cluster (conv2d's bias +
