@@ -1655,10 +1655,11 @@ bool gen_conv_backward_gather(const Graph& g, const Cluster& c, int ci, ClusterC
     os << "    const int x_lo = x == 0 ? 0 : x + " << PX << ", x_hi = x == " << W - 1 << " ? " << IW - 1 << " : x + " << PX << ";\n";
     os << "    float acc = 0.f;\n";
     os << "    for (int yp = y_lo; yp <= y_hi; ++yp)\n    for (int xp = x_lo; xp <= x_hi; ++xp) {\n";
-    os << "        #pragma unroll\n        for (int fy = 0; fy < " << FH << "; ++fy) {\n";
-    os << "            const int ty = yp - fy;\n            if (ty < 0 || ty % " << cbi.stride_h << " != 0 || ty / " << cbi.stride_h << " >= " << OH << ") continue;\n";
-    os << "            #pragma unroll\n            for (int fx = 0; fx < " << FW << "; ++fx) {\n";
-    os << "                const int tx = xp - fx;\n                if (tx < 0 || tx % " << cbi.stride_w << " != 0 || tx / " << cbi.stride_w << " >= " << OW << ") continue;\n";
+    // only the taps congruent to the position modulo the stride can be window elements
+    os << "        for (int fy = yp % " << cbi.stride_h << "; fy < " << FH << "; fy += " << cbi.stride_h << ") {\n";
+    os << "            const int ty = yp - fy;\n            if (ty < 0 || ty / " << cbi.stride_h << " >= " << OH << ") continue;\n";
+    os << "            for (int fx = xp % " << cbi.stride_w << "; fx < " << FW << "; fx += " << cbi.stride_w << ") {\n";
+    os << "                const int tx = xp - fx;\n                if (tx < 0 || tx / " << cbi.stride_w << " >= " << OW << ") continue;\n";
     os << "                const int gm = (image * " << OH << " + ty / " << cbi.stride_h << ") * " << OW << " + tx / " << cbi.stride_w << ";\n";
     os << "                const int gn = (fy * " << FW << " + fx) * " << GC << " + gc;\n";
     os << "                #pragma unroll\n                for (int gk = 0; gk < " << K << "; ++gk) {\n";
