@@ -340,11 +340,25 @@ void emit_per_element_ops(std::ostringstream& os, const Cluster& c, const Codege
     }
 }
 
+// Elements per thread.  Four (128-bit loads and stores on identity operands) when that still leaves a couple of waves of
+// threads.  Programs over a few hundred thousand elements (the hash-grid index / interpolation / weighted-gradient kernels
+// of image_fit: 262144-524288 elements, tens of dependent loads) are latency-bound, and at four elements per thread they
+// fill less than half of the machine's thread slots: one element per thread there (multi-hash m = 262144: 0.419 -> 0.382
+// ms/step).  Measurement hooks: DSC_PE_VEC_MIN (thread threshold, 0 = always four), DSC_PE_VEC_ALL=0 (only gathering programs).
+int per_element_vector_width(const Cluster& c) {
+    static const int64_t min_threads = [] { const char* e = std::getenv("DSC_PE_VEC_MIN"); return e ? std::atoll(e) : (int64_t)148 * 2048 * 2; }();
+    static const bool all_small = [] { const char* e = std::getenv("DSC_PE_VEC_ALL"); return !e || std::atoi(e) != 0; }();
+    if (c.element_count % 4 != 0) return 1;
+    bool narrow = all_small;
+    for (const auto& op : c.ops) narrow |= op.kind == PerElementOp::Gather;
+    return (narrow && c.element_count / 4 < min_threads) ? 1 : 4;
+}
+
 // Body of a per-element kernel for the block `block` (an expression): loads, the straight-line program, stores.
 // Uses the names in<i> / out<i> of the cluster's own inputs and outputs.
 void emit_per_element_body(std::ostringstream& os, const Cluster& c, const CodegenOptions& opt, const std::string& block) {
     const int64_t n = c.element_count;
-    const int vec = (n % 4 == 0) ? 4 : 1;
+    const int vec = per_element_vector_width(c);
     os << "    const unsigned base = (" << block << " * 256u + threadIdx.x) * " << vec << "u;\n";
     os << "    if (base >= " << unum(n) << ") return;\n";
     std::vector<bool> vector_load(c.inputs.size(), false);
@@ -378,7 +392,7 @@ void emit_per_element_body(std::ostringstream& os, const Cluster& c, const Codeg
                << "[2], vout" << i << "[3]);\n";
 }
 
-int64_t per_element_blocks(const Cluster& c) { return div_round_up(div_round_up(c.element_count, c.element_count % 4 == 0 ? 4 : 1), 256); }
+int64_t per_element_blocks(const Cluster& c) { return div_round_up(div_round_up(c.element_count, per_element_vector_width(c)), 256); }
 
 ClusterCode gen_per_element(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt, const std::string& name_suffix = "") {
     std::ostringstream os;
