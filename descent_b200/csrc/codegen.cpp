@@ -2424,15 +2424,42 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
     const bool acc_literal = acc_node.op.kind == OpKind::Literal;
 
     int uniq = 0;
-    std::ostringstream params, load_keys, load_values;
+    std::ostringstream params, load_keys, load_values, value_funcs;
     int64_t chunk_base = 0;
     double bytes = 2.0 * 4.0 * (double)total;
+    const std::string name = "k" + num(ci);
+    // values of a source: an array element, or (Cluster::value_programs) a per-element program on loaded operands
+    std::vector<std::string> value_params(nsrc), value_call(nsrc);
+    auto has_program = [&](int s) { return s < (int)c.value_programs.size() && !c.value_programs[s].members.empty(); };
+    for (int s = 0; s < nsrc; ++s) {
+        if (!has_program(s)) {
+            value_params[s] = "const float* values" + num(s) + ", ";
+            continue;
+        }
+        const Cluster& vp = c.value_programs[s];
+        std::ostringstream fparams, fargs;
+        for (size_t i = 0; i < vp.inputs.size(); ++i) {
+            value_params[s] += "const float* v" + num(s) + "_" + num((int64_t)i) + ", ";
+            fparams << ", const float* in" << i;
+            fargs << ", v" << s << "_" << i;
+        }
+        value_call[s] = fargs.str();
+        value_funcs << "// values of source " << s << " computed while loading: " << vp.label << "\n";
+        value_funcs << "__device__ __forceinline__ float " << name << "_value" << s << "(unsigned e" << fparams.str() << ") {\n";
+        int vuniq = 0;
+        std::vector<bool> no_vector(vp.inputs.size(), false);
+        emit_per_element_ops(value_funcs, vp, opt, vuniq, no_vector, -1);
+        value_funcs << "    return t" << vp.output_ops[0] << ";\n}\n";
+    }
+    auto value_at = [&](int s, const std::string& index) {
+        return has_program(s) ? name + "_value" + num(s) + "((unsigned)(" + index + ")" + value_call[s] + ")" : "values" + num(s) + "[" + index + "]";
+    };
     for (int s = 0; s < nsrc; ++s) {
         const ClusterInput& values = c.inputs[2 * s];
         const ClusterInput& indices = c.inputs[2 * s + 1];
         const int64_t count = values.arg_shape[axis];
         const int64_t nchunk = div_round_up(count, ch);
-        params << "const float* values" << s << ", const float* indices" << s << ", ";
+        params << value_params[s] << "const float* indices" << s << ", ";
         const std::string cond = "gchunk >= " + unum(chunk_base) + " && gchunk < " + unum(chunk_base + nchunk);
         load_keys << "        if (" << cond << ") {\n            const unsigned pos = (gchunk - " << unum(chunk_base) << ") * CH + lp;\n"
                   << "            if (pos < " << unum(count) << ") {\n                const unsigned e = pos;\n";
@@ -2442,9 +2469,11 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
         load_values << "                if (" << cond << ") {\n                    const unsigned e = (outer * " << unum(count) << " + (gchunk - "
                     << unum(chunk_base) << ") * CH + lp) * INNER + w;\n";
         std::string vi = emit_chain(load_values, values.chain, "e", uniq, "                    ");
-        load_values << "                    v = values" << s << "[" << vi << "];\n                }\n";
+        load_values << "                    v = " << value_at(s, vi) << ";\n                }\n";
         chunk_base += nchunk;
-        bytes += chain_bytes(g, values) + chain_bytes(g, indices);
+        bytes += chain_bytes(g, indices);
+        if (has_program(s)) for (const auto& in : c.value_programs[s].inputs) bytes += chain_bytes(g, in);
+        else bytes += chain_bytes(g, values);
     }
     const int64_t nchunk_total = chunk_base;
     // warp-sorted form for tables that fit in shared memory (see kScatterWarpTemplate)
@@ -2466,7 +2495,7 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
                       << "                #pragma unroll\n                for (unsigned w = 0; w < INNER; ++w) {\n"
                       << "                    const unsigned e = (outer * " << unum(count) << " + pos) * INNER + w;\n";
             std::string vi = emit_chain(warp_load, values.chain, "e", wuniq, "                    ");
-            warp_load << "                    val[w] = values" << s << "[" << vi << "];\n                }\n            }\n        }\n";
+            warp_load << "                    val[w] = " << value_at(s, vi) << ";\n                }\n            }\n        }\n";
             nround_total += nround;
         }
     }
@@ -2474,12 +2503,12 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
     std::string acc_value;
     if (acc_literal) acc_value = "__uint_as_float(" + num(acc_node.op.literal_bits) + "u)";
     else acc_value = "acc_in[" + emit_chain(ac, c.inputs[2 * nsrc].chain, "e", uniq, "    ") + "]";
-    const std::string name = "k" + num(ci);
     // small tables are accumulated in shared memory, several chunks per CTA (two waves of CTAs at least)
     const bool table = rows * inner <= 8192;
     int64_t cpb = table ? std::max<int64_t>(1, std::min<int64_t>(8, nchunk_total / (2 * opt.sm_count))) : 1;
     int64_t nblocks = div_round_up(nchunk_total, cpb);
     ClusterCode code;
+    code.source = value_funcs.str();
     if (warp_form) {
         // CTAs: enough to fill the machine, but each writes a whole table as its partial, so no more than the operands weigh
         const int64_t data_bytes = (int64_t)(bytes - 2.0 * 4.0 * (double)total);
@@ -2488,7 +2517,7 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
         const int64_t rpb = div_round_up(nround_total, std::max<int64_t>(1, want));
         nblocks = div_round_up(nround_total, rpb);
         cpb = rpb;
-        code.source = subst(kScatterWarpTemplate, {{"LABEL", c.label}, {"NAME", name}, {"NSRC", num(nsrc)}, {"SRC_PARAMS", params.str()}, {"ROWS", num(rows)},
+        code.source += subst(kScatterWarpTemplate, {{"LABEL", c.label}, {"NAME", name}, {"NSRC", num(nsrc)}, {"SRC_PARAMS", params.str()}, {"ROWS", num(rows)},
                                                    {"INNER", num(inner)}, {"OUTER", num(outer)}, {"NROUND", num(nround_total)}, {"RPB", num(rpb)}, {"LOAD", warp_load.str()}});
         // the ordered sum of the partials is the second kernel of the other template: emit only that half
         std::string both = subst(kScatterTemplate,
@@ -2500,7 +2529,7 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
         DSC_CHECK(at != std::string::npos, "scatter template layout changed");
         code.source += both.substr(at);
     } else
-    code.source = subst(kScatterTemplate,
+    code.source += subst(kScatterTemplate,
                         {{"LABEL", c.label}, {"NAME", name}, {"NSRC", num(nsrc)}, {"SRC_PARAMS", params.str()}, {"CH", num(ch)}, {"ROWS", num(rows)},
                          {"INNER", num(inner)}, {"OUTER", num(outer)}, {"LOAD_KEYS", load_keys.str()}, {"LOAD_VALUES", load_values.str()},
                          {"ACC_PARAM", acc_literal ? "" : "const float* acc_in, "}, {"TOTAL", num(total)}, {"NCHUNK", num(nchunk_total)}, {"NBLOCKS", num(nblocks)},
@@ -2523,7 +2552,15 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
     p.label = c.label;
     p.cluster = ci;
     for (int s = 0; s < nsrc; ++s) {
-        p.args.push_back({KernelArg::NodeBuffer, c.inputs[2 * s].node_id, 0});
+        if (has_program(s)) {
+            for (size_t i = 0; i < c.value_programs[s].inputs.size(); ++i) {
+                const int node = c.inputs[c.value_input_base[s] + i].node_id;
+                p.args.push_back({KernelArg::NodeBuffer, node, 0});
+                code.extra_reads.push_back(node);
+            }
+        } else {
+            p.args.push_back({KernelArg::NodeBuffer, c.inputs[2 * s].node_id, 0});
+        }
         p.args.push_back({KernelArg::NodeBuffer, c.inputs[2 * s + 1].node_id, 0});
     }
     p.args.push_back({KernelArg::Scratch, -1, 0});

@@ -765,6 +765,58 @@ void Graph::absorb_column_sums(std::vector<Cluster>& clusters) {
     }
 }
 
+// See Cluster::value_programs.
+void Graph::absorb_scatter_values(std::vector<Cluster>& clusters) {
+    auto cons = ops_.consumers();
+    std::set<int> rebuilt;
+    for (size_t si = 0; si < clusters.size(); ++si) {
+        Cluster& sc = clusters[si];
+        if (sc.kind != ClusterKind::ScatterAdd || sc.members.empty()) continue;
+        const int nsrc = (int)sc.members.size();
+        sc.value_programs.assign(nsrc, Cluster());
+        sc.value_input_base.assign(nsrc, -1);
+        for (int s = 0; s < nsrc; ++s) {
+            const ClusterInput vin = sc.inputs[2 * s];
+            const int v = vin.node_id;
+            OpNode& vn = ops_.nodes[v];
+            if (!vin.chain.is_identity() || !vn.op.is_per_element() || vn.op.is_inline_source() || vn.op.kind == OpKind::Gather || vn.cluster_id < 0) continue;
+            if (cons[v].size() != 1 || ops_.nodes[cons[v][0].first].cluster_id != (int)si) continue;
+            Cluster& pc = clusters[vn.cluster_id];
+            if (pc.kind != ClusterKind::PerElement || !pc.group.empty() || pc.members.empty()) continue;
+            // a leaf of its cluster: every operand is loaded (from memory, a literal, a coordinate), none computed beside it
+            bool leaf = true;
+            for (const OpEdge& e : vn.in) {
+                const OpNode& src = ops_.nodes[e.src];
+                if (src.op.kind == OpKind::BuiltIn && src.op.built_in != BuiltInOp::Coord) leaf = false;  // (rand: keep the kernel)
+                if (!src.op.is_inline_source() && src.op.kind != OpKind::Input && src.cluster_id == vn.cluster_id && edge_is_fusable(ops_, v, e)) leaf = false;
+            }
+            if (!leaf) continue;
+            const int pci = vn.cluster_id;
+            pc.members.erase(std::remove(pc.members.begin(), pc.members.end(), v), pc.members.end());
+            rebuilt.insert(pci);
+            vn.cluster_id = (int)si;
+            Cluster vp;
+            vp.kind = ClusterKind::PerElement;
+            vp.level = sc.level;
+            vp.element_count = vn.shape.element_count();
+            vp.members = {v};
+            build_per_element_program(vp);
+            DSC_CHECK(vp.outputs.size() == 1 && vp.outputs[0] == v, "scatter value program must produce exactly the values");
+            sc.value_input_base[s] = (int)sc.inputs.size();
+            for (const auto& in : vp.inputs) sc.inputs.push_back(in);
+            sc.value_programs[s] = vp;
+        }
+    }
+    for (int pci : rebuilt) {
+        Cluster& pc = clusters[pci];
+        pc.ops.clear();
+        pc.inputs.clear();
+        pc.outputs.clear();
+        pc.output_ops.clear();
+        if (!pc.members.empty()) build_per_element_program(pc);
+    }
+}
+
 // Launch-bound tails (a few thousand elements per kernel, microseconds each) are merged per dependency level: the
 // programs are independent by construction of the levels.  A program that reads a parameter is never grouped with
 // one that writes the same parameter: the planner lets a kernel update a parameter in place when it reads the old
@@ -1451,6 +1503,7 @@ void Graph::build_clusters() {
     absorb_per_element_epilogues(clusters);
     absorb_column_sums(clusters);
     absorb_max_pools(clusters);
+    absorb_scatter_values(clusters);
     fuse_rows(clusters);
     schedule_after_dense_chains(clusters);
     sink_parameter_updates(clusters);

@@ -75,6 +75,14 @@ struct Cluster {
         int64_t stride_h = 1, stride_w = 1;
     } conv_backward_input;
     int copy_from = -1;                // ScatterAdd: accumulator node taken in place (graph.rs:601-621)
+    // ScatterAdd: the values of source s computed while they are loaded.  A hash grid's backward pass scatters
+    // (gradient of the interpolated feature) x (corner weight) into the table (examples/image_fit/main.rs:190-199): forty
+    // [m, 2] products per step that exist only to be read once by a scatter.  When a source's values are a per-element op
+    // on loaded operands with no other reader, the op joins the scatter's cluster: `value_programs[s]` (members empty = the
+    // source is an ordinary array) is its program, its operands are `inputs[value_input_base[s] + i]`, and the product
+    // array is never written or read back (Graph::absorb_scatter_values).
+    std::vector<Cluster> value_programs;
+    std::vector<int> value_input_base;
     // MatMul whose product is consumed, element for element, by exactly one per-element cluster (conv2d's bias +
     // activation): that cluster is evaluated on the accumulator in the GEMM's epilogue and the raw product never
     // exists in memory.  `epilogue[0]` is the absorbed cluster; its input `epilogue_product_input` is the product;
@@ -172,6 +180,7 @@ private:
     void absorb_per_element_epilogues(std::vector<Cluster>& clusters);
     void absorb_column_sums(std::vector<Cluster>& clusters);
     void absorb_max_pools(std::vector<Cluster>& clusters);
+    void absorb_scatter_values(std::vector<Cluster>& clusters);
     void fuse_rows(std::vector<Cluster>& clusters);
     void sink_parameter_updates(std::vector<Cluster>& clusters);
     void group_small_per_element(std::vector<Cluster>& clusters);
