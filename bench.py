@@ -301,7 +301,11 @@ def measure_workload(d, rig, workload, m, precision, steps, warmup, optimizer, w
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},
         "step_roofline": {"algorithmic_bytes": stats["algorithmic_bytes"], "flops": stats["flops"],
                           "achieved_gbs": stats["algorithmic_bytes"] / (ms_per_step * 1e-3) / 1e9,
-                          "frac": stats["algorithmic_bytes"] / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
+                          "frac": stats["algorithmic_bytes"] / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                          # a fused launch (the dense-chain MLP kernel) removes traffic instead of moving it faster: the same
+                          # fraction with that launch counted as the bytes of the kernels it replaces
+                          "unfused_algorithmic_bytes": stats.get("unfused_algorithmic_bytes", stats["algorithmic_bytes"]),
+                          "frac_of_unfused_traffic": stats.get("unfused_algorithmic_bytes", stats["algorithmic_bytes"]) / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
         "l2_policy": ("256 MB fill between timed steps (working set %.0f MB is L2-sized)" if flush else
                       "working set per step (%.0f MB arena) exceeds the 126 MB L2") % (stats["arena_bytes"] / 1e6),
         "loss_sum_finite": bool(np.isfinite(loss)), "jit_ms": stats["jit_ms"], "_profile": profile, "_stats": stats,

@@ -197,7 +197,7 @@ int dsc_env_graph_stats(dsc_env* env, dsc_graphdef* graph, char** json_out) {
         GraphStats s = env->env->stats(*graph->graph);
         std::ostringstream os;
         os << "{\"kernel_launches\":" << s.kernel_launches << ",\"total_nodes\":" << s.total_nodes << ",\"arena_bytes\":" << s.arena_bytes
-           << ",\"algorithmic_bytes\":" << s.algorithmic_bytes << ",\"flops\":" << s.flops << ",\"jit_ms\":" << s.jit_ms << "}";
+           << ",\"algorithmic_bytes\":" << s.algorithmic_bytes << ",\"unfused_algorithmic_bytes\":" << s.unfused_algorithmic_bytes << ",\"flops\":" << s.flops << ",\"jit_ms\":" << s.jit_ms << "}";
         *json_out = dup_string(os.str());
     });
 }

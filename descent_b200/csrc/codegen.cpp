@@ -3212,6 +3212,12 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
     l.args.push_back({KernelArg::Scratch, -1, 0});
     l.algorithmic_bytes = bytes;
     for (int k = 0; k < L; ++k) l.flops += 6.0 * (double)M * (double)W[k] * (double)W[k + 1];
+    // what the chain's clusters would move as kernels of their own (for the traffic-based roofline of the step: the fusion
+    // removes bytes, it does not make the remaining ones faster)
+    for (int member : ch.all_clusters()) {
+        const ClusterCode unfused = generate_cluster_code(g, member, opt);
+        for (const auto& ul : unfused.launches) l.replaced_bytes += ul.algorithmic_bytes;
+    }
     out->launches.push_back(l);
     KernelLaunch s;
     s.entry = sname;

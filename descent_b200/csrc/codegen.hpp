@@ -28,6 +28,7 @@ struct KernelLaunch {
     std::vector<int> covers;       // clusters whose work this launch does besides its own (a fused dense chain)
     double algorithmic_bytes = 0;  // 4*(sum of min(source, addressed) input elements + outputs)
     double flops = 0;              // 2*b*m*n*k for GEMMs
+    double replaced_bytes = 0;     // a fused launch: the algorithmic bytes of the kernels it replaces (0 = its own)
 };
 
 struct ClusterCode {

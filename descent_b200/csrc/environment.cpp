@@ -599,6 +599,7 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
                 r.gemm_splits = l.gemm_splits;
                 exec.stats.kernel_launches += 1;
                 exec.stats.algorithmic_bytes += l.algorithmic_bytes;
+                exec.stats.unfused_algorithmic_bytes += l.replaced_bytes > 0 ? l.replaced_bytes : l.algorithmic_bytes;
                 exec.stats.flops += l.flops;
             } else {
                 check(dsc_module_get_kernel(exec.module, l.entry.c_str(), &r.kernel));
@@ -609,6 +610,7 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
                                                                         : exec.arena + (uint64_t)(scratch_offset[ci] + a.scratch_offset));
                 exec.stats.kernel_launches += 1;
                 exec.stats.algorithmic_bytes += l.algorithmic_bytes;
+                exec.stats.unfused_algorithmic_bytes += l.replaced_bytes > 0 ? l.replaced_bytes : l.algorithmic_bytes;
                 exec.stats.flops += l.flops;
             }
             exec.launches.push_back(r);

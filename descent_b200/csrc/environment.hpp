@@ -54,6 +54,7 @@ struct GraphStats {
     int total_nodes = 0;       // every node of the captured step
     int64_t arena_bytes = 0;
     double algorithmic_bytes = 0;
+    double unfused_algorithmic_bytes = 0;  // the same with every fused launch counted as the kernels it replaces
     double flops = 0;
     double jit_ms = 0;
 };

@@ -139,34 +139,41 @@ constexpr int kXchgMaxRanks = 16;
 constexpr size_t kXchgSlotFloats = 64 * 1024;  // 256 KB per slot
 struct XchgArea {
     unsigned epoch;
-    unsigned pad[31];
+    unsigned done;   // CTAs of the current launch that have finished (the last one advances `epoch`)
+    unsigned pad[30];
     unsigned flags[2][kXchgMaxRanks * 32];  // one 128-byte line per (slot, peer)
     float data[2][kXchgSlotFloats];
 };
 struct XchgPeers { XchgArea* area[kXchgMaxRanks]; };
 
+// Several CTAs per rank (round 2: the hash tables' 150 KB bucket took 20+ us of dependent P2P loads in one CTA): CTA c owns a
+// contiguous slice of the bucket and has its own flag per (slot, peer) -- 32 flags fit the peer's 128-byte line -- so the
+// CTAs never wait for each other; the last CTA to finish advances the epoch (it can only be last once every CTA of this
+// launch has read the old value).
 __global__ void __launch_bounds__(1024) dsc_oneshot_allreduce_kernel(float* bucket, unsigned count, XchgPeers peers, int rank, int world) {
     XchgArea* mine = peers.area[rank];
     const unsigned epoch = mine->epoch + 1u, slot = epoch & 1u;
-    const unsigned tid = threadIdx.x;
-    for (unsigned i = tid * 4u; i < count; i += 4096u) {
-        if (i + 4u <= count) *reinterpret_cast<float4*>(&mine->data[slot][i]) = *reinterpret_cast<const float4*>(bucket + i);
-        else for (unsigned j = i; j < count; ++j) mine->data[slot][j] = bucket[j];
+    const unsigned tid = threadIdx.x, cta = blockIdx.x;
+    const unsigned chunk = ((count + gridDim.x - 1u) / gridDim.x + 3u) & ~3u;
+    const unsigned begin = min(count, cta * chunk), end = min(count, begin + chunk);
+    for (unsigned i = begin + tid * 4u; i < end; i += 4096u) {
+        if (i + 4u <= end) *reinterpret_cast<float4*>(&mine->data[slot][i]) = *reinterpret_cast<const float4*>(bucket + i);
+        else for (unsigned j = i; j < end; ++j) mine->data[slot][j] = bucket[j];
     }
     __threadfence_system();
     __syncthreads();
     if (tid < (unsigned)world) {
-        unsigned* flag = &peers.area[tid]->flags[slot][rank * 32];
+        unsigned* flag = &peers.area[tid]->flags[slot][rank * 32 + cta];
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-        const unsigned* wait_on = &mine->flags[slot][tid * 32];
+        const unsigned* wait_on = &mine->flags[slot][tid * 32 + cta];
         unsigned seen;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(wait_on) : "memory");
         } while (seen != epoch);
     }
     __syncthreads();
-    for (unsigned i = tid * 4u; i < count; i += 4096u) {
-        if (i + 4u <= count) {
+    for (unsigned i = begin + tid * 4u; i < end; i += 4096u) {
+        if (i + 4u <= end) {
             float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int p = 0; p < world; ++p) {
                 float4 v;
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(1024) dsc_oneshot_allreduce_kernel(float* buck
             }
             *reinterpret_cast<float4*>(bucket + i) = sum;
         } else {
-            for (unsigned j = i; j < count; ++j) {
+            for (unsigned j = i; j < end; ++j) {
                 float sum = 0.f;
                 for (int p = 0; p < world; ++p) {
                     float v;
@@ -187,7 +194,14 @@ __global__ void __launch_bounds__(1024) dsc_oneshot_allreduce_kernel(float* buck
         }
     }
     __syncthreads();
-    if (tid == 0) mine->epoch = epoch;
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&mine->done, 1u) == gridDim.x - 1u) {
+            mine->done = 0u;
+            __threadfence();
+            mine->epoch = epoch;
+        }
+    }
 }
 
 constexpr size_t kStagingSlotBytes = 16u << 20;
@@ -618,7 +632,9 @@ int dsc_dp_allreduce_sum_f32(dsc_ctx* ctx, uint64_t id, size_t count) {
     if (!ctx->comm) return set_error(DSC_ERR_NCCL, "data-parallel communicator not initialised");
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (ctx->xchg_ready && count <= kXchgSlotFloats && (id & 15) == 0) {  // small bucket: one CTA over peer-mapped memory (NVLink P2P)
-        dsc_oneshot_allreduce_kernel<<<1, 1024, 0, ctx->stream>>>((float*)id, (unsigned)count, ctx->xchg, ctx->rank, ctx->world);
+        // one CTA per 16 KB of gradients, at most the 32 flags of a peer's line
+        const unsigned ctas = (unsigned)std::min<size_t>(32, std::max<size_t>(1, (count * 4 + 16383) / 16384));
+        dsc_oneshot_allreduce_kernel<<<ctas, 1024, 0, ctx->stream>>>((float*)id, (unsigned)count, ctx->xchg, ctx->rank, ctx->world);
         CUDA_TRY(cudaGetLastError());
         return DSC_OK;
     }
