@@ -1736,6 +1736,13 @@ bool gen_grouped_dot(const Graph& g, const Cluster& c, int ci, ClusterCode* out)
     return true;
 }
 
+// A dense layer's bias + activation (or activation backward) in the epilogue of the JIT tcgen05 GEMM: set while gen_matmul
+// generates the product of a cluster whose absorbed epilogue the tensor-core kernel may evaluate on its accumulator; the
+// kernel emitter sets `fused` when it did (SIREN / ReLU+PE layers: the TMA GEMM + a separate epilogue kernel moved every
+// activation three times).
+const Cluster* g_tc_epilogue = nullptr;
+bool g_tc_epilogue_fused = false;
+
 ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
     const OpNode& mm = g.ops().nodes[c.node_id];
     const ClusterInput& a = c.inputs[0];
@@ -1760,6 +1767,17 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
         plain.epilogue_product_input = -1;
         plain.inputs.resize(2);
         plain.outputs = {c.node_id};
+        // Measured and rejected (B200, relu-pe / siren at m = 65536): 0.369 -> 0.450 ms and 0.388 -> 0.551 ms per step.  The
+        // gathered GEMM runs one 128 x 256 tile per CTA with the epilogue serialised behind its MMAs (94 us for the widest
+        // layer against 22 us TMA GEMM + 34 us epilogue kernel).  Kept behind DSC_TC_FUSE_EPILOGUE=1 as a measurement hook.
+        static const bool fuse_in_tc = [] { const char* e = std::getenv("DSC_TC_FUSE_EPILOGUE"); return e && std::atoi(e) != 0; }();
+        if (fuse_in_tc && opt.use_tf32 && !cbi.enabled && BC == 1 && r_graph == 1 && N % 4 == 0 && K <= 512 && !c.pool.enabled) {
+            g_tc_epilogue = &c;
+            g_tc_epilogue_fused = false;
+            ClusterCode fused = gen_matmul(g, plain, ci, opt);
+            g_tc_epilogue = nullptr;
+            if (g_tc_epilogue_fused) return fused;
+        }
         code = gen_matmul(g, plain, ci, opt);
         const int64_t product_offset = div_round_up(code.scratch_bytes, 256) * 256;
         code.scratch_bytes = product_offset + BC * M * N * 4;
@@ -1793,7 +1811,7 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
 
     // Plain dense operands (row-major or transposed whole buffers) take the TMA + tcgen05 TF32 kernel when the
     // environment allows reduced operand precision; everything else stays on the strict-FP32 JIT path below.
-    if (opt.use_tf32 && BC == 1 && (c.matmul_absorbs_reduce || r_graph == 1) && M * N >= 128 * 128 && K >= 32) {
+    if (opt.use_tf32 && !g_tc_epilogue && BC == 1 && (c.matmul_absorbs_reduce || r_graph == 1) && M * N >= 128 * 128 && K >= 32) {
         auto plain = [&](const ClusterInput& in, int64_t rows, int64_t cols, bool* row_major) {
             if (in.chain.input_count != rows * cols || in.chain.views.size() > 1) return false;
             if (!in.chain.views.empty() && in.chain.views[0].any_clamp()) return false;
@@ -1937,9 +1955,11 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     // short-K GEMMs (convolution forward / backward-input) use the persistent register-staged kernel instead
     const bool async_copy = tc && a_vec && b_vec && k_tiles >= 8 && !cbi.enabled;
     const int64_t stages = async_copy ? std::max<int64_t>(2, std::min<int64_t>({4, 196608 / std::max<int64_t>(one_stage, 1), k_tiles})) : 2;
+    const bool fuse_epilogue = tc && g_tc_epilogue != nullptr && !via_scratch && N % 4 == 0;
+    const EpilogueCode epi = tc ? gen_epilogue(g, fuse_epilogue ? *g_tc_epilogue : c, name, opt) : EpilogueCode();
     if (tc)
         code.source = subst(async_copy ? kMatMulTc3Template : kMatMulTc2Template,
-                            {{"LABEL", c.label}, {"NAME", name}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)},
+                            {{"LABEL", fuse_epilogue ? g_tc_epilogue->label : c.label}, {"NAME", name}, {"STORE4", epi.store4}, {"EPI_PARAMS", epi.params}, {"EPI_ARGS", epi.args}, {"BN", num(t.bn)}, {"BK", num(t.bk)}, {"M", num(M)}, {"N", num(N)}, {"K", num(K)},
                              {"KC", num(KC)}, {"BC", num(BC)}, {"TMEM_COLS", num(tmem_cols)}, {"A_MN", a_mn ? "true" : "false"}, {"STAGES", num(stages)},
                              {"B_MN", b_mn ? "true" : "false"}, {"A_LAYOUT", a_mn ? "MN-major" : "K-major"}, {"B_LAYOUT", b_mn ? "MN-major" : "K-major"},
                              {"A_VEC", a_vec ? "true" : "false"}, {"B_VEC", b_vec ? "true" : "false"}, {"A_CHAIN", ca.str()}, {"A_IDX", ia},
@@ -1981,9 +2001,15 @@ ClusterCode gen_matmul(const Graph& g, const Cluster& c, int ci, const CodegenOp
     l.cluster = ci;
     l.args = {{KernelArg::NodeBuffer, a.node_id, 0}, {KernelArg::NodeBuffer, b.node_id, 0}};
     if (via_scratch) l.args.push_back({KernelArg::Scratch, -1, 0});
+    else if (fuse_epilogue) l.args.push_back({KernelArg::NodeBuffer, g_tc_epilogue->outputs[0], 0});  // the raw product is never stored: any valid address
     else l.args.push_back({KernelArg::NodeBuffer, c.outputs[0], 0});
+    if (fuse_epilogue) {
+        l.args.insert(l.args.end(), epi.launch_args.begin(), epi.launch_args.end());
+        l.label = "TensorCore" + g_tc_epilogue->label;
+        g_tc_epilogue_fused = true;
+    }
     bind_operand_loads(l, &code, &la, &lb);
-    l.algorithmic_bytes = la.bytes + lb.bytes + 4.0 * (double)out_count;
+    l.algorithmic_bytes = la.bytes + lb.bytes + (fuse_epilogue ? epi.bytes : 4.0 * (double)out_count);
     l.flops = 2.0 * (double)BC * (double)M * (double)N * (double)K;
     code.launches.push_back(l);
     if (via_scratch) {
