@@ -2562,6 +2562,11 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
                          {"CPB", num(cpb)}, {"TABLE", table ? "true" : "false"},
                          {"ACC_CHAIN", ac.str()}, {"ACC_VALUE", acc_value}});
     code.scratch_bytes = nblocks * total * 4;
+    // one table-sized partial per block: fine for the hash grids this was built for, not for a large embedding
+    // table with few indices -- refuse with a message instead of planning tens of GB of scratch
+    DSC_CHECK(code.scratch_bytes <= ((int64_t)8 << 30),
+              "scatter_add into a [" << rows << ", " << inner << "] table from " << max_count << " positions would need " << (code.scratch_bytes >> 20)
+                                     << " MB of per-block partial tables; this backend's deterministic scatter keeps one table copy per block (tables up to ~1M floats)");
     if (!table) {
         KernelLaunch z;
         z.kind = KernelLaunch::ZeroScratch;

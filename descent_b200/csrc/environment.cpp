@@ -219,6 +219,7 @@ struct ResolvedLaunch {
     bool async_collective = false, join_collectives = false;  // AllReduce: on the side stream / wait for the side stream first
     std::string label, entry;
     int cluster = -1;
+    int branch = -1, level = -1;  // parallel branch of its dependency level (-1: the main stream)
     std::vector<int> covers;
     double algorithmic_bytes = 0, flops = 0;
     int64_t gemm_m = 0, gemm_n = 0, gemm_k = 0;
@@ -502,12 +503,45 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
     }
     for (int ci = 0; ci < nc; ++ci)  // producers evaluated inside this cluster's operand loaders: their inputs live until here
         for (int id : codes[ci].extra_reads) death[id] = std::max(death[id], ci);
+    // Parallel levels.  Clusters of one dependency level are independent by construction (graph.cpp build_clusters), so a
+    // level with several kernels runs on parallel branches of the step's CUDA graph (dsc_branch_fork / select / join):
+    // the hash-grid index and interpolation kernels, the column-sum / split-sum tails of weight gradients, the gates of an
+    // unrolled LSTM step are small latency-bound launches that overlap instead of running back to back.  Not for a level
+    // that holds an all-reduce (its own side stream) or a kernel that writes a parameter in place (another kernel of the
+    // level may read the old value: the in-place rule above only orders EARLIER readers).  Memory follows: nothing that
+    // dies inside a parallel level, and no scratch area of it, is reused before the level has ended.
+    static const bool parallel_levels_enabled = [] { const char* e = std::getenv("DSC_PARALLEL_LEVELS"); return !e || std::atoi(e) != 0; }();
+    std::map<int, int> level_kernels;      // level -> clusters with launches
+    std::map<int, bool> level_sequential;  // level -> must stay on the main stream
+    for (int ci = 0; ci < nc; ++ci) {
+        const int lv = clusters[ci].level;
+        if (codes[ci].skipped || codes[ci].launches.empty()) continue;
+        level_kernels[lv] += 1;
+        if (clusters[ci].kind == ClusterKind::AllReduce) level_sequential[lv] = true;
+        auto writes_parameter = [&](int out) { return storage[out].kind == Storage::Param; };
+        for (int out : clusters[ci].outputs) if (writes_parameter(out)) level_sequential[lv] = true;
+        for (int out : codes[ci].extra_writes) if (writes_parameter(out)) level_sequential[lv] = true;
+    }
+    auto parallel_level = [&](int lv) { return parallel_levels_enabled && level_kernels[lv] >= 2 && !level_sequential[lv]; };
+    std::vector<int> branch_of(nc, -1);
+    {
+        std::map<int, int> next_branch;
+        for (int ci = 0; ci < nc; ++ci)
+            if (!codes[ci].skipped && !codes[ci].launches.empty() && parallel_level(clusters[ci].level)) branch_of[ci] = next_branch[clusters[ci].level]++ % 4;
+    }
     std::vector<int64_t> scratch_offset(nc, 0);
     std::vector<std::vector<int>> dying_at(nc + 1);
+    std::vector<std::pair<int64_t, int64_t>> held_scratch;  // scratch areas of the current parallel level
+    int released_upto = -1;
     for (int ci = 0; ci < nc; ++ci) {
-        // release what nobody after the previous cluster needs
-        if (ci > 0)
-            for (int id : dying_at[ci - 1]) arena.release(storage[id].offset, ops.nodes[id].shape.buffer_size());
+        // release what nobody after the previous cluster needs -- at the end of its level when that level runs in parallel
+        if (ci > 0 && (clusters[ci].level != clusters[ci - 1].level || !parallel_level(clusters[ci - 1].level))) {
+            for (int c = released_upto + 1; c <= ci - 1; ++c)
+                for (int id : dying_at[c]) arena.release(storage[id].offset, ops.nodes[id].shape.buffer_size());
+            released_upto = ci - 1;
+            for (auto [off, bytes] : held_scratch) arena.release(off, bytes);
+            held_scratch.clear();
+        }
         auto place = [&](int out) {
             if (alias[out] >= 0) {
                 storage[out] = storage[alias[out]];
@@ -524,7 +558,8 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
         for (int out : codes[ci].extra_writes) place(out);
         if (codes[ci].scratch_bytes > 0) {
             scratch_offset[ci] = arena.alloc(codes[ci].scratch_bytes);
-            arena.release(scratch_offset[ci], codes[ci].scratch_bytes);  // free again for the next cluster...
+            if (parallel_level(clusters[ci].level)) held_scratch.push_back({scratch_offset[ci], codes[ci].scratch_bytes});  // ... until the level ends
+            else arena.release(scratch_offset[ci], codes[ci].scratch_bytes);  // free again for the next cluster...
         }
         // ...but outputs of this cluster were allocated before the scratch, so they never overlap it
     }
@@ -572,6 +607,8 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
             r.label = l.label;
             r.entry = l.entry;
             r.cluster = ci;
+            r.branch = branch_of[ci];
+            r.level = clusters[ci].level;
             r.covers = l.covers;
             r.algorithmic_bytes = l.algorithmic_bytes;
             r.flops = l.flops;
@@ -632,8 +669,17 @@ void Environment::launch_all(GraphExec& exec, std::vector<float>* per_launch_ms)
         for (auto& e : events) check(dsc_event_create(&e));
         check(dsc_event_record(ctx_, events[0]));
     }
+    bool forked = false;
+    int forked_level = -1;
     for (size_t i = 0; i < exec.launches.size(); ++i) {
         const ResolvedLaunch& r = exec.launches[i];
+        if (!per_launch_ms) {  // (per-launch timing keeps everything on one stream)
+            if (forked && (r.branch < 0 || r.level != forked_level)) { check(dsc_branch_join(ctx_)); forked = false; }
+            if (r.branch >= 0) {
+                if (!forked) { check(dsc_branch_fork(ctx_)); forked = true; forked_level = r.level; }
+                check(dsc_branch_select(ctx_, r.branch));
+            }
+        }
         if (r.is_copy) check(dsc_copy(ctx_, r.ptr, r.src, r.bytes));
         else if (r.is_fill) check(dsc_fill_u32(ctx_, r.ptr, 0, r.fill_bits, r.bytes / 4));
         else if (r.kind == KernelLaunch::ZeroScratch) check(dsc_fill_u32(ctx_, r.ptr, 0, 0, r.bytes / 4));
@@ -647,6 +693,7 @@ void Environment::launch_all(GraphExec& exec, std::vector<float>* per_launch_ms)
         else check(dsc_launch(ctx_, r.kernel, r.gx, r.gy, r.gz, r.block, r.smem, r.buffers.data(), (int)r.buffers.size()));
         if (per_launch_ms) check(dsc_event_record(ctx_, events[i + 1]));
     }
+    if (forked) check(dsc_branch_join(ctx_));
     if (per_launch_ms) {
         per_launch_ms->resize(exec.launches.size());
         for (size_t i = 0; i < exec.launches.size(); ++i) check(dsc_event_elapsed_ms(events[i], events[i + 1], &(*per_launch_ms)[i]));

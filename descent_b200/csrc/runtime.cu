@@ -225,6 +225,14 @@ struct dsc_ctx {
     cudaStream_t comm_stream = nullptr;   // early gradient bucket: all-reduced here while the backward pass continues on `stream`
     cudaEvent_t comm_fork = nullptr, comm_join = nullptr;
     bool comm_pending = false;
+    // independent kernels of one dependency level on parallel branches (dsc_branch_*): kernels, fills and copies go to
+    // `launch_stream`, which is `stream` outside a fork
+    static constexpr int kBranches = 4;
+    cudaStream_t branch[kBranches] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t branch_fork = nullptr, branch_done[kBranches] = {nullptr, nullptr, nullptr, nullptr};
+    bool branch_used[kBranches] = {false, false, false, false};
+    bool forked = false;
+    cudaStream_t launch_stream = nullptr;
     XchgPeers xchg;             // peer-mapped exchange areas (own entry = local allocation); valid when xchg_ready
     bool xchg_ready = false;
     bool capturing = false;
@@ -268,6 +276,12 @@ int dsc_ctx_create(int device, dsc_ctx** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->launch_stream = ctx->stream;
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->branch_fork, cudaEventDisableTiming));  // (created here: nothing is created while a graph is being captured)
+    for (int b = 0; b < dsc_ctx::kBranches; ++b) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->branch[b], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->branch_done[b], cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->prefetch_done, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->staged_read, cudaEventDisableTiming));
@@ -314,6 +328,10 @@ int dsc_ctx_destroy(dsc_ctx* ctx) {
     cudaEventDestroy(ctx->comm_join);
     cudaStreamDestroy(ctx->comm_stream);
     cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->branch_fork) {
+        cudaEventDestroy(ctx->branch_fork);
+        for (int b = 0; b < dsc_ctx::kBranches; ++b) { cudaEventDestroy(ctx->branch_done[b]); cudaStreamDestroy(ctx->branch[b]); }
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DSC_OK;
@@ -341,17 +359,17 @@ int dsc_fill_u32(dsc_ctx* ctx, uint64_t id, size_t offset_bytes, uint32_t value,
     if (count == 0) return DSC_OK;
     unsigned* p = (unsigned*)(id + offset_bytes);
     if (value == 0) {
-        CUDA_TRY(cudaMemsetAsync(p, 0, count * 4, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(p, 0, count * 4, ctx->launch_stream));
     } else {
         unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, (size_t)ctx->sm_count * 8);
-        dsc_fill_u32_kernel<<<blocks, 256, 0, ctx->stream>>>(p, value, count);
+        dsc_fill_u32_kernel<<<blocks, 256, 0, ctx->launch_stream>>>(p, value, count);
         CUDA_TRY(cudaGetLastError());
     }
     return DSC_OK;
 }
 int dsc_copy(dsc_ctx* ctx, uint64_t dst, uint64_t src, size_t bytes) {
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUDA_TRY(cudaMemcpyAsync((void*)dst, (const void*)src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync((void*)dst, (const void*)src, bytes, cudaMemcpyDeviceToDevice, ctx->launch_stream));
     return DSC_OK;
 }
 
@@ -492,7 +510,7 @@ int dsc_launch(dsc_ctx* ctx, dsc_kernel kernel, uint32_t gx, uint32_t gy, uint32
     }
     values[num_buffers] = (uint64_t)ctx->step_params;
     params[num_buffers] = &values[num_buffers];
-    CU_TRY(g_drv.LaunchKernel((CUfunction)kernel, gx, gy, gz, block_x, 1, 1, smem, (CUstream)ctx->stream, params, nullptr));
+    CU_TRY(g_drv.LaunchKernel((CUfunction)kernel, gx, gy, gz, block_x, 1, 1, smem, (CUstream)ctx->launch_stream, params, nullptr));
     return DSC_OK;
 }
 int dsc_set_rand_seed(dsc_ctx* ctx, uint32_t rand_seed) {
@@ -689,5 +707,42 @@ extern "C" int dsc_internal_encode_tiled_2d_f32(void* tensor_map, uint64_t base,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
     return DSC_OK;
 }
-extern "C" void* dsc_internal_stream(dsc_ctx* ctx) { return (void*)ctx->stream; }
+extern "C" void* dsc_internal_stream(dsc_ctx* ctx) { return (void*)ctx->launch_stream; }
+
+// ---- parallel branches --------------------------------------------------------------------------------------------------
+// Kernels of one dependency level are independent by construction (graph.cpp build_clusters).  dsc_branch_fork makes up to
+// four side streams wait for everything issued so far on the context's stream; dsc_branch_select routes the following
+// dsc_launch / dsc_gemm_tf32* / dsc_fill_u32 / dsc_copy calls to one of them; dsc_branch_join makes the context's stream
+// wait for every branch that was used.  All of it is event record / wait, so inside dsc_graph_begin_capture / end_capture
+// the level becomes parallel nodes of the CUDA graph (a fork and a join), and the GPU overlaps the small latency-bound
+// kernels of a level instead of running them back to back.
+int dsc_branch_fork(dsc_ctx* ctx) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->forked) return set_error(DSC_ERR_INVALID, "dsc_branch_fork: already forked");
+    CUDA_TRY(cudaEventRecord(ctx->branch_fork, ctx->stream));
+    for (int b = 0; b < dsc_ctx::kBranches; ++b) ctx->branch_used[b] = false;
+    ctx->forked = true;
+    return DSC_OK;
+}
+int dsc_branch_select(dsc_ctx* ctx, int branch) {
+    if (!ctx->forked) return set_error(DSC_ERR_INVALID, "dsc_branch_select outside dsc_branch_fork / dsc_branch_join");
+    const int b = ((branch % dsc_ctx::kBranches) + dsc_ctx::kBranches) % dsc_ctx::kBranches;
+    if (!ctx->branch_used[b]) {
+        CUDA_TRY(cudaStreamWaitEvent(ctx->branch[b], ctx->branch_fork, 0));
+        ctx->branch_used[b] = true;
+    }
+    ctx->launch_stream = ctx->branch[b];
+    return DSC_OK;
+}
+int dsc_branch_join(dsc_ctx* ctx) {
+    if (!ctx->forked) return DSC_OK;
+    for (int b = 0; b < dsc_ctx::kBranches; ++b) {
+        if (!ctx->branch_used[b]) continue;
+        CUDA_TRY(cudaEventRecord(ctx->branch_done[b], ctx->branch[b]));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->branch_done[b], 0));
+    }
+    ctx->launch_stream = ctx->stream;
+    ctx->forked = false;
+    return DSC_OK;
+}
 extern "C" int dsc_internal_set_error(int code, const char* msg) { return set_error(code, "%s", msg); }
