@@ -227,10 +227,10 @@ struct dsc_ctx {
     bool comm_pending = false;
     // independent kernels of one dependency level on parallel branches (dsc_branch_*): kernels, fills and copies go to
     // `launch_stream`, which is `stream` outside a fork
-    static constexpr int kBranches = 4;
-    cudaStream_t branch[kBranches] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t branch_fork = nullptr, branch_done[kBranches] = {nullptr, nullptr, nullptr, nullptr};
-    bool branch_used[kBranches] = {false, false, false, false};
+    static constexpr int kBranches = 16;
+    cudaStream_t branch[kBranches] = {};
+    cudaEvent_t branch_fork = nullptr, branch_done[kBranches] = {};
+    bool branch_used[kBranches] = {};
     bool forked = false;
     cudaStream_t launch_stream = nullptr;
     XchgPeers xchg;             // peer-mapped exchange areas (own entry = local allocation); valid when xchg_ready
@@ -711,7 +711,7 @@ extern "C" void* dsc_internal_stream(dsc_ctx* ctx) { return (void*)ctx->launch_s
 
 // ---- parallel branches --------------------------------------------------------------------------------------------------
 // Kernels of one dependency level are independent by construction (graph.cpp build_clusters).  dsc_branch_fork makes up to
-// four side streams wait for everything issued so far on the context's stream; dsc_branch_select routes the following
+// sixteen side streams wait for everything issued so far on the context's stream; dsc_branch_select routes the following
 // dsc_launch / dsc_gemm_tf32* / dsc_fill_u32 / dsc_copy calls to one of them; dsc_branch_join makes the context's stream
 // wait for every branch that was used.  All of it is event record / wait, so inside dsc_graph_begin_capture / end_capture
 // the level becomes parallel nodes of the CUDA graph (a fork and a join), and the GPU overlaps the small latency-bound

@@ -129,7 +129,7 @@ int dsc_dp_peer_memory_ready(dsc_ctx* ctx, int* ready);
 int dsc_dp_world(dsc_ctx* ctx, int* world, int* rank);
 
 /* Parallel branches for the independent kernels of one dependency level (the reference issues every cluster with a full
- * barrier in between, environment.rs:326-516): fork makes up to four side streams wait for the context's stream, select
+ * barrier in between, environment.rs:326-516): fork makes up to sixteen side streams wait for the context's stream, select
  * routes the following dsc_launch / dsc_gemm_tf32* / dsc_fill_u32 / dsc_copy calls to one of them, join makes the context's
  * stream wait for the branches used.  Capturable: inside dsc_graph_begin_capture they become parallel nodes of the graph. */
 int dsc_branch_fork(dsc_ctx* ctx);
