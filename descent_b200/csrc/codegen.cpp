@@ -2433,6 +2433,8 @@ extern "C" __global__ void __launch_bounds__(256) {{NAME}}_part({{SRC_PARAMS}}fl
 }
 )";
 
+int g_scatter_group_size = 1;  // members of the group being generated (generate_scatter_group_code), 1 = a kernel of its own
+
 ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const CodegenOptions& opt) {
     const OpNode& node = g.ops().nodes[c.node_id];  // the first scatter of the chain: same table shape and axis as the rest
     const int nsrc = (int)c.members.size();
@@ -2539,6 +2541,9 @@ ClusterCode gen_scatter_add(const Graph& g, const Cluster& c, int ci, const Code
         // CTAs: enough to fill the machine, but each writes a whole table as its partial, so no more than the operands weigh
         const int64_t data_bytes = (int64_t)(bytes - 2.0 * 4.0 * (double)total);
         int64_t want = std::max<int64_t>(opt.sm_count, std::min<int64_t>(4 * (int64_t)opt.sm_count, data_bytes / std::max<int64_t>(1, total * 4)));
+        // launched together with other tables (generate_scatter_group_code): the group as a whole fills the machine, so each
+        // member takes its share of about two waves of CTAs -- fewer table-sized partials to write and to add up
+        if (g_scatter_group_size > 1) want = std::min<int64_t>(want, std::max<int64_t>(32, 12 * (int64_t)opt.sm_count / g_scatter_group_size));
         want = std::min<int64_t>(want, nround_total);
         const int64_t rpb = div_round_up(nround_total, std::max<int64_t>(1, want));
         nblocks = div_round_up(nround_total, rpb);
@@ -2637,7 +2642,9 @@ bool generate_scatter_group_code(const Graph& g, const std::vector<int>& members
         const int ci = members[m];
         const Cluster& c = g.clusters()[ci];
         if (c.kind != ClusterKind::ScatterAdd) return false;
+        g_scatter_group_size = (int)members.size();
         ClusterCode code = gen_scatter_add(g, c, ci, opt);
+        g_scatter_group_size = 1;
         if (code.launches.size() != 2 || code.launches[0].grid_y != 1 || code.source.find("per-warp sorted partial sums") == std::string::npos) return false;
         const std::string k = "k" + num(ci);
         std::string text = code.source;
