@@ -257,7 +257,9 @@ std::unique_ptr<Example> build_image_fit(Environment& env, const ExampleConfig& 
         Array lr_scale = scope->parameter_value(ex->learning_rate_scale);
         ex->parameters = scope->trainable_parameters();
         scope->all_reduce_gradients(ex->parameters);
-        ex->optimizer = std::make_unique<Adam>(env, *scope, ex->parameters, 0.02f * lr_scale, 0.9f, 0.99f, 1.0e-8f);
+        // main.rs:319 always uses Adam(0.02, 0.9, 0.99); "descent" is accepted so that the parity tests can hold the parameters
+        // of these networks to 1e-5 after an SGD step as well (Adam's first step is sign-like in near-zero gradients)
+        ex->optimizer = make_optimizer(env, *scope, ex->parameters, cfg.optimizer, lr_scale, 0.02f, 0.99f);
         ex->train_graph_json = scope->export_json();
         ex->train_graph.reset(scope->build_graph());
     }
