@@ -50,7 +50,7 @@ for name, ns in sorted(ncu_ns.items(), key=lambda kv: -kv[1]):
     ev = dense_ms if name == "dsc_gemm_tf32" else event_ms.get(name, 0.0)
     if ns / ncu_total < 0.002:
         continue
-    out.append("| %s | %s | %d | %.1f | %.1f%% | %.1f | %.1f%% |" % (name, label_of.get(name, "TMA-fed dense tcgen05 TF32 GEMM (precompiled)"), ncu_count[name],
+    out.append("| %s | %s | %d | %.1f | %.1f%% | %.1f | %.1f%% |" % (name, label_of.get(name, "TMA-fed dense tcgen05 TF32 GEMM (precompiled)" if "gemm_tf32" in name else "runtime helper (seed store / fill / one-shot all-reduce)"), ncu_count[name],
                                                                  ns / 1e3 / steps, 100 * ns / ncu_total, ev * 1e3, 100 * ev / event_total))
 out += ["", "Totals: ncu %.2f ms/step (serialised, cold); CUDA-event eager pass %.2f ms/step; CUDA-graph replay measured by bench.py: %.2f ms/step "
         "(%.0f samples/s)." % (ncu_total / 1e6 / steps, event_total, bench["ms_per_step"], bench["value"])]
