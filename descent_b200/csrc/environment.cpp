@@ -511,6 +511,7 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
     // level may read the old value: the in-place rule above only orders EARLIER readers).  Memory follows: nothing that
     // dies inside a parallel level, and no scratch area of it, is reused before the level has ended.
     static const bool parallel_levels_enabled = [] { const char* e = std::getenv("DSC_PARALLEL_LEVELS"); return !e || std::atoi(e) != 0; }();
+    static const double parallel_bytes_limit = [] { const char* e = std::getenv("DSC_PARALLEL_MB"); return (e ? std::atof(e) : 16.0) * 1.0e6; }();
     std::map<int, int> level_kernels;      // level -> clusters with launches
     std::map<int, bool> level_sequential;  // level -> must stay on the main stream
     for (int ci = 0; ci < nc; ++ci) {
@@ -521,7 +522,7 @@ Environment::GraphExec& Environment::prepare(const Graph& graph) {
         // kernels that fill the machine on their own gain nothing from a neighbour and lose cache to it (relu-pe m = 65536:
         // a 100 MB weight-gradient GEMM beside a 100 MB backward GEMM measured 3 % slower than back to back)
         for (const auto& l : codes[ci].launches)
-            if (l.algorithmic_bytes > 64.0e6) level_sequential[lv] = true;
+            if (l.algorithmic_bytes > parallel_bytes_limit) level_sequential[lv] = true;
         auto writes_parameter = [&](int out) { return storage[out].kind == Storage::Param; };
         for (int out : clusters[ci].outputs) if (writes_parameter(out)) level_sequential[lv] = true;
         for (int out : codes[ci].extra_writes) if (writes_parameter(out)) level_sequential[lv] = true;
