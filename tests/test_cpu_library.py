@@ -233,3 +233,40 @@ def test_kernels_refuse_arrays_beyond_32_bit_indexing(built_library, host_env):
     ex = host_env.example("conv-net", 200000)  # [m, 28, 28, 16] = 2.5e9 elements
     with pytest.raises(built_library.DescentError, match="index with 32 bits"):
         ex.train_graph.kernel_source()
+
+
+def test_round2_fusions_are_planned(built_library, host_env):
+    """Structure of the image_fit multi-hash step after the round-2 passes (no GPU): one dense chain over the MLP's twelve
+    clusters, emitted as ONE tcgen05 kernel under TF32 only; the nine concat selects folded into one kernel; the ten
+    tables' scatter_adds grouped into one partial + one sum launch with their values computed in the loader."""
+    ex = host_env.example("multi-hash", 262144, image_width=1024, image_height=1024)
+    graph = ex.train_graph.export_json()
+    chains = graph["dense_chains"]
+    assert len(chains) == 1 and chains[0]["widths"] == [20, 64, 64, 3] and chains[0]["rows"] == 262144
+    assert len(chains[0]["clusters"]) == 12 and len(chains[0]["forward"]) == 3 and all(b >= 0 for b in chains[0]["backward"])
+    labels = [c["label"] for c in graph["clusters"]]
+    assert sum(l.startswith("ScatterAdd") for l in labels) == 10
+    assert sum(l.startswith("PerElement (5 ops)") for l in labels) <= 1  # the concat chain is one select kernel, not nine
+    tf32, strict = ex.train_graph.kernel_source(tf32=True), ex.train_graph.kernel_source(tf32=False)
+    assert "dense chain: 3 layers, widths 20 64 64 3" in tf32 and "tcgen05.mma.cta_group::1.kind::tf32" in tf32
+    assert "dense chain" not in strict  # strict FP32: the chain's clusters run one by one
+    for source in (tf32, strict):
+        assert source.count("_parts(") == 1 and source.count("_sums(") >= 1  # grouped scatter launches
+        assert "_value0(" in source  # scatter values evaluated while loading
+    assert tf32.count("__global__") <= 20, tf32.count("__global__")
+    # wide heads are detected but not fused (shared memory), networks without an MLP head have no chain
+    assert host_env.example("relu-pe", 65536, image_width=512, image_height=512).train_graph.export_json()["dense_chains"][0]["widths"] == [32, 256, 128, 64, 32, 3]
+    assert "dense chain" not in host_env.example("relu-pe", 65536, image_width=512, image_height=512).train_graph.kernel_source(tf32=True)
+    assert host_env.example("conv-net", 64).train_graph.export_json()["dense_chains"] == []
+
+
+def test_conv_blur_net_kernels(built_library, host_env):
+    """MaxBlurPool2D (module.rs:139-163, 221-245): depthwise blur forward as per-output dot products, its strided backward
+    as one gather cluster (MatMul + WindowsToImage + two Unpads), the overlapping max-pool backward inside the col2im gather."""
+    ex = host_env.example("conv-blur-net", 64)
+    labels = [c["label"] for c in ex.train_graph.export_json()["clusters"]]
+    assert sum("MatMul+WindowsToImage/2x2" in l and l.endswith("+Unpad+Unpad") for l in labels) == 2, labels
+    assert not any(l.startswith("Unpad") for l in labels)
+    source = ex.train_graph.kernel_source(tf32=False)
+    assert source.count("[gather: one thread per image-gradient element]") == 2
+    assert "_opA1(" in source  # window values of the stand-alone col2im come from an operand prologue
