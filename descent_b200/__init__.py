@@ -820,6 +820,12 @@ class ChaCha20Rng:
         _check(lib.dsc_rng_gen_range(self._h, ctypes.c_uint64(low), ctypes.c_uint64(high), int(u32), ctypes.byref(out)))
         return out.value
 
+    def gen_range_pairs(self, high0, high1, pairs):
+        """`pairs` draws of (gen_range(0..high0), gen_range(0..high1)) as usize, in that order (image_fit/main.rs:376-378): [pairs, 2] uint64."""
+        out = np.empty((pairs, 2), dtype=np.uint64)
+        _check(lib.dsc_rng_gen_range_pairs(self._h, ctypes.c_uint64(high0), ctypes.c_uint64(high1), out.ctypes.data_as(c_u64_p), ctypes.c_size_t(pairs)))
+        return out
+
     def shuffle(self, indices):
         """indices.shuffle(&mut rng) (fashion_mnist/main.rs:382): returns the shuffled copy as uint64."""
         arr = np.ascontiguousarray(indices, dtype=np.uint64).copy()

@@ -489,6 +489,15 @@ int dsc_rng_gen_range(dsc_rng* rng, uint64_t low, uint64_t high, int as_u32, uin
         *out = as_u32 ? (uint64_t)rng->rng.gen_range_u32((uint32_t)low, (uint32_t)high) : rng->rng.gen_range_u64(low, high);
     });
 }
+int dsc_rng_gen_range_pairs(dsc_rng* rng, uint64_t high0, uint64_t high1, uint64_t* out, size_t pairs) {
+    return guarded([&] {
+        DSC_CHECK(high0 > 0 && high1 > 0, "gen_range needs a non-empty range");
+        for (size_t i = 0; i < pairs; ++i) {
+            out[2 * i] = rng->rng.gen_range_u64(0, high0);
+            out[2 * i + 1] = rng->rng.gen_range_u64(0, high1);
+        }
+    });
+}
 int dsc_rng_shuffle(dsc_rng* rng, uint64_t* indices, size_t count) { return guarded([&] { rng->rng.shuffle(indices, count); }); }
 int dsc_env_reset_parameter_rng(dsc_env* env, int param, dsc_rng* rng) {
     return guarded([&] { env->env->reset_parameter(env->param(param), rng->rng); });

@@ -154,6 +154,7 @@ int dsc_rng_next_u32(dsc_rng* rng, uint32_t* out);                      /* RngCo
 int dsc_rng_next_u64(dsc_rng* rng, uint64_t* out);
 int dsc_rng_open01_f32(dsc_rng* rng, float* out, size_t count);        /* rng.sample(Open01), environment.rs:22,35 */
 int dsc_rng_gen_range(dsc_rng* rng, uint64_t low, uint64_t high, int as_u32, uint64_t* out);  /* gen_range(low..high): u32 or usize draws */
+int dsc_rng_gen_range_pairs(dsc_rng* rng, uint64_t high0, uint64_t high1, uint64_t* out, size_t pairs); /* `pairs` x (gen_range(0..high0), gen_range(0..high1)) as usize draws: image_fit/main.rs:376-378 */
 int dsc_rng_shuffle(dsc_rng* rng, uint64_t* indices, size_t count);    /* SliceRandom::shuffle, main.rs:382 */
 int dsc_env_reset_parameter_rng(dsc_env* env, int param, dsc_rng* rng); /* Environment::reset_parameter(param, &mut rng), environment.rs:190-202 */
 

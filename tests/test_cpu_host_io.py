@@ -41,6 +41,8 @@ def test_library_rng_matches_the_restated_crates(built_library, seed):
         assert g == w and 0 <= g < bound
         g, w = got.gen_range(3, 3 + bound), want.gen_range(3, 3 + bound)
         assert g == w and 3 <= g < 3 + bound
+    pairs = got.gen_range_pairs(512, 300, 20)
+    assert pairs.tolist() == [[want.gen_range(0, 512), want.gen_range(0, 300)] for _ in range(20)]
     shuffled = got.shuffle(np.arange(1000))
     assert shuffled.tolist() == want.shuffle(range(1000)) and sorted(shuffled.tolist()) == list(range(1000))
 
