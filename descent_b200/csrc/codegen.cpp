@@ -2871,11 +2871,11 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
     off += 64;  // mbarrier, TMEM slot
     const int64_t red_off = off;
     off += 64;  // 16 warp partials of a loss sum
+    // the widest read an M = 128 MN-major A operand can make starts at the last MN buffer and spans four 32-wide blocks:
+    // small networks pad the allocation so that those addresses exist
+    off = std::max(off, mn_dy + 4 * 16384);
     const int64_t smem_bytes = off + 1024;  // + alignment slack
     if (smem_bytes > 227 * 1024) return false;
-    for (int l = 0; l < L; ++l)  // the widest read an M = 128 MN-major A operand can make from buffer l
-        if (mn_act[l] + 4 * 16384 > off) return false;
-    if (mn_dy + 4 * 16384 > off) return false;
     (void)mn_end;
 
     // ---- tensor memory plan: the working accumulator, then one weight-gradient accumulator per layer ---------------------
@@ -3092,14 +3092,14 @@ bool generate_dense_chain_code(const Graph& g, const DenseChain& ch, const Codeg
             body << "        }\n";
         } else {
             // the loss program on the last product: dz_{L-1} and the values that are summed over the batch
-            const Cluster& p = clusters[ch.loss];
-            int product = -1;
-            for (size_t i = 0; i < p.inputs.size(); ++i)
+            const Cluster& p = ch.loss_in_epilogue ? fc.epilogue[0] : clusters[ch.loss];
+            int product = ch.loss_in_epilogue ? fc.epilogue_product_input : -1;
+            for (size_t i = 0; i < p.inputs.size() && !ch.loss_in_epilogue; ++i)
                 if (p.inputs[i].node_id == fc.outputs[0]) product = (int)i;
             const int64_t out_slot = km_slot[km_next];
             body << "        for (int ch = grp; ch < " << n16 / 16 << "; ch += 4) {  // loss program on the last product -> dz_" << l << "\n";
             body << "            const int c0 = ch * 16;\n            float acc[16], o[16];\n            dc_ld16(tlane + (unsigned)c0, acc);\n";
-            if (!fc.epilogue.empty()) return false;  // (a bias absorbed into the last layer would need two programs here)
+            if (!fc.epilogue.empty() && !ch.loss_in_epilogue) return false;  // (a bias absorbed into the last layer would need two programs here)
             emit_program(body, p, product, -1, N, "            ", true);
             body << "                o[j] = t" << p.output_ops[ch.loss_gradient_output] << ";\n";
             for (size_t s = 0; s < ch.sums.size(); ++s) body << "                lsum" << s << " += t" << p.output_ops[ch.sums[s].output] << ";\n";

@@ -1549,7 +1549,7 @@ std::vector<int> DenseChain::all_clusters() const {
     for (int c : forward) all.push_back(c);
     for (int c : weight_gradient) all.push_back(c);
     for (int c : backward) if (c >= 0) all.push_back(c);
-    all.push_back(loss);
+    if (!loss_in_epilogue) all.push_back(loss);
     for (const auto& s : sums) { all.push_back(s.row_reduce); all.push_back(s.batch_reduce); }
     std::sort(all.begin(), all.end());
     return all;
@@ -1583,11 +1583,12 @@ std::vector<DenseChain> Graph::detect_dense_chains(const std::vector<Cluster>& c
     };
     auto is_parameter = [&](int node) { return ops_.nodes[node].op.kind == OpKind::Input; };
     // forward layer candidates: [M, K] activation (plain) x [K, N] parameter (plain)
-    struct Forward { int64_t m, k, n; int a, w, out; };
+    struct Forward { int64_t m, k, n; int a, w, out; bool terminal; };  // terminal: the loss program is this cluster's epilogue
     std::map<int, Forward> forward;  // cluster -> shape
     for (int ci = 0; ci < nc; ++ci) {
         const Cluster& c = clusters[ci];
-        if (!plain_matmul(c) || c.matmul_absorbs_reduce || !c.column_sum.empty() || c.outputs.size() != 1) continue;
+        if (!plain_matmul(c) || c.matmul_absorbs_reduce || !c.column_sum.empty() || c.outputs.empty()) continue;
+        if (c.outputs.size() != 1 && (c.epilogue.empty() || c.epilogue[0].outputs.size() != c.outputs.size())) continue;
         const OpNode& mm = ops_.nodes[c.node_id];
         if (mm.op.kind != OpKind::MatMul || mm.shape.len() != 4 || mm.shape[0] != 1 || mm.shape[1] != 1) continue;
         const int64_t M = mm.shape[2], N = mm.shape[3], K = c.inputs[0].arg_shape.at(-1);
@@ -1595,12 +1596,13 @@ std::vector<DenseChain> Graph::detect_dense_chains(const std::vector<Cluster>& c
         bool ok = true;
         if (!c.epilogue.empty()) {
             const Cluster& p = c.epilogue[0];
-            ok = p.outputs.size() == 1 && p.element_count == M * N;
+            ok = p.outputs.size() >= 1 && p.element_count == M * N;
             for (size_t i = 0; i < p.inputs.size(); ++i)
                 if ((int)i != c.epilogue_product_input) ok = ok && is_parameter(p.inputs[i].node_id);
             for (const auto& op : p.ops) ok = ok && op.kind != PerElementOp::Gather && op.kind != PerElementOp::BuiltIn;
         }
-        if (ok) forward[ci] = {M, K, N, c.inputs[0].node_id, c.inputs[1].node_id, c.outputs[0]};
+        const bool terminal = c.outputs.size() > 1;  // a two-output epilogue can only be the loss (gradient + summed values)
+        if (ok) forward[ci] = {M, K, N, c.inputs[0].node_id, c.inputs[1].node_id, terminal ? -1 : c.outputs[0], terminal};
     }
     std::map<int, int> forward_reading;  // activation node -> forward cluster that takes it as A
     for (auto& [ci, f] : forward) {
@@ -1608,7 +1610,7 @@ std::vector<DenseChain> Graph::detect_dense_chains(const std::vector<Cluster>& c
         else forward_reading[f.a] = ci;
     }
     std::set<int> produced_by_forward;
-    for (auto& [ci, f] : forward) produced_by_forward.insert(f.out);
+    for (auto& [ci, f] : forward) if (!f.terminal) produced_by_forward.insert(f.out);
     for (auto& [start, f0] : forward) {
         if (produced_by_forward.count(f0.a) && forward_reading.count(f0.a) && forward_reading[f0.a] >= 0) {
             // not the first layer of its chain
@@ -1624,6 +1626,7 @@ std::vector<DenseChain> Graph::detect_dense_chains(const std::vector<Cluster>& c
             if (f.m != ch.rows || f.k != ch.widths.back()) break;
             ch.forward.push_back(ci);
             ch.widths.push_back(f.n);
+            if (f.terminal) break;
             auto it = forward_reading.find(f.out);
             if (it == forward_reading.end() || it->second < 0 || !forward.count(it->second)) break;
             ci = it->second;
@@ -1635,8 +1638,12 @@ std::vector<DenseChain> Graph::detect_dense_chains(const std::vector<Cluster>& c
         std::vector<int> act(L + 1, -1), dz(L, -1);  // act[l] = input of layer l (act[L] = last product), dz[l] = gradient at layer l's output
         act[0] = forward[ch.forward[0]].a;
         for (int l = 0; l < L; ++l) act[l + 1] = forward[ch.forward[l]].out;
-        // the loss cluster: the only reader of the last product
-        {
+        // the loss program: the epilogue of the last layer (when the graph's passes absorbed it there), else the per-element
+        // cluster that is the only reader of the last product
+        ch.loss_in_epilogue = forward[ch.forward[L - 1]].terminal;
+        if (ch.loss_in_epilogue) {
+            ch.loss = ch.forward[L - 1];
+        } else {
             std::set<int> readers;
             for (auto [dst, k] : cons[act[L]]) {
                 (void)k;
@@ -1647,15 +1654,18 @@ std::vector<DenseChain> Graph::detect_dense_chains(const std::vector<Cluster>& c
             if (!ok || readers.size() != 1) continue;
             ch.loss = *readers.begin();
         }
-        const Cluster& lc = clusters[ch.loss];
+        const Cluster& lc = ch.loss_in_epilogue ? clusters[ch.loss].epilogue[0] : clusters[ch.loss];
         if (lc.kind != ClusterKind::PerElement || !lc.group.empty() || lc.element_count != M * ch.widths[L]) continue;
-        int product_inputs = 0;
-        for (const auto& in : lc.inputs) {
-            if (in.node_id == act[L]) { product_inputs += 1; ok = ok && in.chain.is_identity(); }
-            else ok = ok && is_parameter(in.node_id);
+        if (!ch.loss_in_epilogue) {
+            int product_inputs = 0;
+            for (const auto& in : lc.inputs) {
+                if (in.node_id == act[L]) { product_inputs += 1; ok = ok && in.chain.is_identity(); }
+                else ok = ok && is_parameter(in.node_id);
+            }
+            if (product_inputs != 1) ok = false;
         }
         for (const auto& op : lc.ops) ok = ok && op.kind != PerElementOp::Gather && op.kind != PerElementOp::BuiltIn;
-        if (!ok || product_inputs != 1) continue;
+        if (!ok) continue;
         // weight gradients and backward products, last layer first
         ch.weight_gradient.assign(L, -1);
         ch.backward.assign(L, -1);
@@ -1741,7 +1751,7 @@ std::vector<DenseChain> Graph::detect_dense_chains(const std::vector<Cluster>& c
         for (int c : ch.all_clusters()) members.insert(c);
         if ((int)members.size() != (int)ch.all_clusters().size()) continue;
         std::vector<int> internal;
-        for (int l = 1; l <= L; ++l) internal.push_back(act[l]);
+        for (int l = 1; l <= L; ++l) if (act[l] >= 0) internal.push_back(act[l]);
         for (int l = 0; l < L; ++l) internal.push_back(dz[l]);
         for (const auto& s : ch.sums) { internal.push_back(lc.outputs[s.output]); internal.push_back(clusters[s.row_reduce].outputs[0]); }
         for (int node : internal)

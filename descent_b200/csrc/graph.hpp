@@ -141,6 +141,7 @@ struct DenseChain {
     std::vector<int> weight_gradient;  // per layer: MatMul cluster x_l^T dz_l (+ column sums of dz_l)
     std::vector<int> backward;         // per layer: MatMul cluster dz_l W_l^T (+ epilogue: activation backward of layer l-1); backward[0] = -1 if x_0 needs no gradient
     int loss = -1;                     // per-element cluster: last product (+ bias, target) -> dz_{L-1} and values that are summed
+    bool loss_in_epilogue = false;     // ... absorbed as the (multi-output) epilogue of the last forward cluster: loss == forward.back()
     int loss_gradient_output = 0;      // which output of the loss cluster is dz_{L-1}
     struct Sum { int output; int row_reduce; int batch_reduce; };  // loss output -> Reduce along the row -> Reduce over the batch
     std::vector<Sum> sums;
